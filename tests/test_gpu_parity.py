@@ -1,0 +1,235 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle, bit-exact.
+
+Every test calls libwordpiece_b200.so -> sm_100a kernels and compares the id
+array with oracle/wp_oracle.c on the same bytes.  Nothing here reads
+/root/reference; golden vectors are tests/golden/*.json and tests/cases.py.
+"""
+from __future__ import annotations
+
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import cases
+import textgen
+from _oracle import EmptyVocabWord, Oracle
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _vocab(tokens, dev):
+    from wordpiece_b200 import Vocab
+
+    return Vocab(tokens, device=dev)
+
+
+def _check(text, tokens, dev, tag=""):
+    if isinstance(text, str):
+        text = text.encode("utf-8")
+    exp = Oracle(tokens).encode(text)
+    v = _vocab(tokens, dev)
+    got = v.encode(text)
+    st = v.stats()
+    v.close()
+    if not np.array_equal(exp, got):
+        k = int(np.argmax(exp[: min(len(exp), len(got))] != got[: min(len(exp), len(got))])) if len(exp) and len(got) else 0
+        raise AssertionError(
+            f"{tag}: ids differ (oracle {len(exp)} vs gpu {len(got)}), first mismatch at {k}: "
+            f"oracle {exp[max(0, k - 3):k + 5].tolist()} gpu {got[max(0, k - 3):k + 5].tolist()}; text[:80]={text[:80]!r}"
+        )
+    return st
+
+
+def test_reference_golden_vectors(gpu_device):
+    """tests/tests.cpp:137-217 — the reference's own 28 known-answer cases."""
+    for text, vocab, expected in cases.REFERENCE_GOLDEN:
+        v = _vocab(vocab, gpu_device)
+        got = v.encode(text).tolist()
+        v.close()
+        assert got == expected, (text, vocab, expected, got)
+
+
+def test_reference_differential_cases(gpu_device):
+    for text, vocab in cases.REFERENCE_DIFFERENTIAL:
+        _check(text, vocab, gpu_device, "differential")
+
+
+def test_quirks_match_recorded_reference_output(gpu_device):
+    """SURVEY A.3 behaviours; expected ids were produced by the compiled reference (tests/golden/quirks.json)."""
+    with open(os.path.join(HERE, "golden", "quirks.json")) as f:
+        golden = json.load(f)
+    names = {name for name, _, _ in cases.QUIRKS}
+    assert names == set(golden), "regenerate tests/golden (make_golden.py)"
+    for name, text, vocab in cases.QUIRKS:
+        v = _vocab(vocab, gpu_device)
+        got = v.encode(text).tolist()
+        v.close()
+        assert got == golden[name]["ids"], (name, golden[name]["ids"], got)
+
+
+def test_empty_and_degenerate_inputs(gpu_device):
+    v = _vocab(["a", "[UNK]"], gpu_device)
+    assert v.encode(b"").size == 0                      # fast.cpp:145
+    assert v.encode(b"   \n\t ").size == 0
+    assert v.encode(b"\xff\xfe\x80").size == 0          # decodes to nothing (reference: SIGFPE; we return {})
+    assert v.encode(b"a").tolist() == [0]
+    assert v.encode(b" a ").tolist() == [0]
+    v.close()
+    # no usable token at all (reference divides by zero, fast.cpp:45): every word is UNK
+    v = _vocab(["[UNK]", "[CLS]"], gpu_device)
+    assert v.encode("ab, 中c".encode()).tolist() == Oracle(["[UNK]", "[CLS]"]).encode("ab, 中c".encode()).tolist()
+    v.close()
+
+
+def test_empty_vocab_word_is_an_error(gpu_device):
+    from wordpiece_b200 import WordPieceError
+
+    for vocab in (["a", "##"], ["a", ""], ["\xff".encode("latin1")]):
+        with pytest.raises(EmptyVocabWord):
+            Oracle(vocab)
+        with pytest.raises(WordPieceError) as ei:
+            _vocab(vocab, gpu_device)
+        assert ei.value.status == 2 and "Vocab word is empty" in str(ei.value)
+
+
+def test_hostile_fuzz_tiny(gpu_device):
+    """tiny vocabularies over a hostile alphabet, invalid bytes included."""
+    rng = random.Random(20240517)
+    n = 0
+    for i in range(2500):
+        text, vocab = cases.fuzz_case(rng)
+        try:
+            Oracle(vocab)
+        except EmptyVocabWord:
+            continue
+        _check(text, vocab, gpu_device, f"fuzz#{i}")
+        n += 1
+    assert n > 2000
+
+
+def test_random_split_small(gpu_device):
+    """tests.cpp:257-258 — random [a-z] strings cut into vocab pieces, positive and negative."""
+    rng = random.Random(17)
+    for text_len in range(10, 301, 10):
+        for parts in (2, 3, 7, 20, 55, 100):
+            if parts > text_len:
+                continue
+            for positive in (True, False):
+                s, vocab = cases.random_split_case(rng, text_len, parts, positive)
+                _check(s, vocab, gpu_device, f"split L={text_len} parts={parts} pos={positive}")
+
+
+@pytest.mark.parametrize("seed,n_bytes", [(11, 5000), (12, 8192), (13, 8193), (14, 8191), (15, 40000), (16, 300000)])
+def test_multilingual_multi_tile(gpu_device, seed, n_bytes):
+    text, vocab = textgen.case(seed, n_bytes)
+    st = _check(text, vocab, gpu_device, f"mixed seed={seed}")
+    assert st.n_tiles == (len(text) + 8191) // 8192
+
+
+@pytest.mark.parametrize("seed,n_bytes,rate", [(21, 3000, 0.3), (22, 30000, 0.05), (23, 100000, 0.01), (24, 60000, 0.5)])
+def test_invalid_utf8_is_dropped(gpu_device, seed, n_bytes, rate):
+    """utf8.cpp:130-147: invalid bytes vanish before word splitting, across tile borders too."""
+    text, vocab = textgen.case(seed, n_bytes, invalid_rate=rate)
+    st = _check(text, vocab, gpu_device, f"dirty seed={seed}")
+    assert st.dirty_tiles > 0
+
+
+def test_invalid_runs_across_tile_borders(gpu_device):
+    vocab = ["ab", "##cd", "abcd", "x", "中", "[UNK]"]
+    for junk in (b"\xff", b"\x80", b"\xe4\xb8", b"\xf0\x9f\x98"):
+        for pad in range(8180, 8200):
+            text = b"x " * (pad // 2) + b"ab" + junk * 7 + b"cd" + junk * 40 + " 中".encode() + junk + b" x"
+            _check(text, vocab, gpu_device, f"junk={junk!r} pad={pad}")
+    # a run of invalid bytes longer than a whole tile between the halves of one word
+    text = b"ab" + b"\xff" * 20000 + b"cd x"
+    _check(text, vocab, gpu_device, "long junk")
+
+
+def test_multibyte_chars_straddle_tile_borders(gpu_device):
+    vocab = ["中", "文", "中文", "при", "##вет", "かな", "##かな", "a", "##a", "[UNK]"]
+    unit = "中文 привет かなかな a ".encode()
+    for shift in range(0, 12):
+        text = b"a" * shift + unit * 700
+        _check(text, vocab, gpu_device, f"shift={shift}")
+
+
+@pytest.mark.parametrize("seed,n_bytes", [(31, 50000), (32, 200000)])
+def test_long_segments_leave_the_window(gpu_device, seed, n_bytes):
+    """Words longer than a tile's halo are walked from global memory (at most one per tile)."""
+    text, vocab = textgen.case(seed, n_bytes, long_run_rate=0.08, long_tokens=40)
+    st = _check(text, vocab, gpu_device, f"long seed={seed}")
+    assert st.long_segments > 0
+
+
+def test_giant_single_word(gpu_device):
+    """tests.cpp:259-272 shape: one space-free word far longer than a tile, vocab = a random cut of it."""
+    rng = random.Random(5)
+    for text_len, parts, positive in ((20000, 300, True), (20000, 300, False), (100000, 2000, True)):
+        s, vocab = cases.random_split_case(rng, text_len, parts, positive)
+        st = _check(s, vocab, gpu_device, f"giant L={text_len}")
+        assert st.long_segments >= 1
+
+
+def test_long_dirty_word(gpu_device):
+    """A long word with invalid bytes sprinkled in: the global walker must drop them on the fly."""
+    rng = random.Random(8)
+    s, vocab = cases.random_split_case(rng, 30000, 500, True)
+    b = bytearray(s.encode())
+    for _ in range(300):
+        b.insert(rng.randint(0, len(b)), 0xFF)
+    _check(bytes(b), vocab, gpu_device, "long dirty")
+
+
+def test_capacity_and_encode_into(gpu_device):
+    from wordpiece_b200 import WordPieceError
+
+    text, vocab = textgen.case(41, 50000)
+    exp = Oracle(vocab).encode(text)
+    v = _vocab(vocab, gpu_device)
+    out = np.full(len(exp) + 10, -7, np.int32)
+    n = v.encode_into(text, out)
+    assert n == len(exp) and np.array_equal(out[:n], exp) and (out[n:] == -7).all()
+    small = np.zeros(len(exp) // 2, np.int32)
+    with pytest.raises(WordPieceError) as ei:
+        v.encode_into(text, small)
+    assert ei.value.status == 5
+    v.close()
+
+
+def test_device_resident_entry_point(gpu_device):
+    import torch
+
+    text, vocab = textgen.case(42, 120000, invalid_rate=0.01)
+    exp = Oracle(vocab).encode(text)
+    v = _vocab(vocab, gpu_device)
+    d_text = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda(gpu_device)
+    d_ids, n = v.encode_device(d_text)
+    assert n == len(exp) and np.array_equal(d_ids[:n].cpu().numpy(), exp)
+    # misaligned device pointer (a slice): falls back to byte loads, same ids
+    for off in (1, 3, 8, 13):
+        sub = d_text[off:]
+        e2 = Oracle(vocab).encode(text[off:])
+        ids2, n2 = v.encode_device(sub)
+        assert n2 == len(e2) and np.array_equal(ids2[:n2].cpu().numpy(), e2), off
+    # async variant
+    d_cnt = torch.zeros(1, dtype=torch.int64, device=d_text.device)
+    d_out = torch.empty(len(text), dtype=torch.int32, device=d_text.device)
+    v.encode_device_async(d_text, d_out, d_cnt)
+    torch.cuda.synchronize()
+    assert int(d_cnt.item()) == len(exp) and np.array_equal(d_out[: len(exp)].cpu().numpy(), exp)
+    v.close()
+
+
+def test_handle_reuse_and_order_independence(gpu_device):
+    """One handle, many texts of different sizes: scratch is reset between calls."""
+    text, vocab = textgen.case(43, 90000)
+    o = Oracle(vocab)
+    v = _vocab(vocab, gpu_device)
+    for cut in (90000, 17, 8192, 50000, 1, 33333, 90000):
+        assert np.array_equal(v.encode(text[:cut]), o.encode(text[:cut])), cut
+    v.close()

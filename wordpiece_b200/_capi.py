@@ -1,0 +1,414 @@
+"""ctypes binding of include/wordpiece_b200.h.  No tokenisation logic lives here."""
+from __future__ import annotations
+
+import ctypes as C
+import mmap
+import os
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence, Union
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libwordpiece_b200.so")
+
+WP_OK = 0
+WP_ERR_INVALID_ARG = 1
+WP_ERR_EMPTY_VOCAB_WORD = 2
+WP_ERR_CUDA = 3
+WP_ERR_NO_DEVICE = 4
+WP_ERR_CAPACITY = 5
+WP_ERR_IO = 6
+WP_ERR_NOMEM = 7
+WP_ERR_ID_RANGE = 8
+
+KIND_PREFIX = 0
+KIND_SUFFIX = 1
+
+
+class WordPieceError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(message)
+        self.status = status
+
+
+class _StatsStruct(C.Structure):
+    _fields_ = [
+        ("n_bytes", C.c_uint64),
+        ("n_ids", C.c_uint64),
+        ("n_tiles", C.c_uint64),
+        ("dirty_tiles", C.c_uint64),
+        ("long_segments", C.c_uint64),
+        ("kernel_launches", C.c_uint64),
+    ]
+
+
+@dataclass
+class Stats:
+    n_bytes: int
+    n_ids: int
+    n_tiles: int
+    dirty_tiles: int
+    long_segments: int
+    kernel_launches: int
+
+
+# every symbol include/wordpiece_b200.h declares (tests check that all are exported)
+EXPORTED_SYMBOLS = [
+    "wp_last_error",
+    "wp_kernel_launch_count",
+    "wp_vocab_create",
+    "wp_vocab_create_from_file",
+    "wp_vocab_destroy",
+    "wp_vocab_size",
+    "wp_vocab_unk_id",
+    "wp_vocab_max_len",
+    "wp_vocab_device",
+    "wp_vocab_token_flags",
+    "wp_vocab_device_bytes",
+    "wp_encode",
+    "wp_encode_into",
+    "wp_encode_device",
+    "wp_encode_device_async",
+    "wp_last_stats",
+    "wp_decode",
+    "wp_free",
+    "wp_debug_longest_match",
+    "wp_debug_table_slots",
+    "wp_debug_table_nodes",
+    "wp_debug_long_tokens",
+]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libwordpiece_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise WordPieceError(
+            WP_ERR_NO_DEVICE,
+            f"{LIB_PATH} is missing: build it with `make -C wordpiece_b200/csrc` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.",
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, sz, i32p = C.c_void_p, C.c_size_t, C.POINTER(C.c_int32)
+    L.wp_last_error.restype = C.c_char_p
+    L.wp_kernel_launch_count.restype = C.c_uint64
+    L.wp_vocab_create.argtypes = [C.POINTER(C.c_char_p), C.POINTER(sz), sz, C.c_int, C.POINTER(vp)]
+    L.wp_vocab_create.restype = C.c_int
+    L.wp_vocab_create_from_file.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.wp_vocab_create_from_file.restype = C.c_int
+    L.wp_vocab_destroy.argtypes = [vp]
+    L.wp_vocab_destroy.restype = None
+    L.wp_vocab_size.argtypes = [vp]
+    L.wp_vocab_size.restype = sz
+    L.wp_vocab_unk_id.argtypes = [vp]
+    L.wp_vocab_unk_id.restype = C.c_int32
+    L.wp_vocab_max_len.argtypes = [vp]
+    L.wp_vocab_max_len.restype = sz
+    L.wp_vocab_device.argtypes = [vp]
+    L.wp_vocab_device.restype = C.c_int
+    L.wp_vocab_token_flags.argtypes = [vp, sz]
+    L.wp_vocab_token_flags.restype = C.c_int
+    L.wp_vocab_device_bytes.argtypes = [vp]
+    L.wp_vocab_device_bytes.restype = sz
+    L.wp_encode.argtypes = [vp, vp, sz, C.POINTER(i32p), C.POINTER(sz)]
+    L.wp_encode.restype = C.c_int
+    L.wp_encode_into.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz)]
+    L.wp_encode_into.restype = C.c_int
+    L.wp_encode_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), vp]
+    L.wp_encode_device.restype = C.c_int
+    L.wp_encode_device_async.argtypes = [vp, vp, sz, vp, sz, vp, vp]
+    L.wp_encode_device_async.restype = C.c_int
+    L.wp_last_stats.argtypes = [vp, C.POINTER(_StatsStruct)]
+    L.wp_last_stats.restype = C.c_int
+    L.wp_decode.argtypes = [vp, vp, sz, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
+    L.wp_decode.restype = C.c_int
+    L.wp_free.argtypes = [vp]
+    L.wp_free.restype = None
+    L.wp_debug_longest_match.argtypes = [vp, C.c_char_p, sz, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
+    L.wp_debug_longest_match.restype = C.c_int
+    for f in ("wp_debug_table_slots", "wp_debug_table_nodes", "wp_debug_long_tokens"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = sz
+    _lib = L
+    return L
+
+
+def _check(status: int) -> None:
+    if status != WP_OK:
+        msg = load_library().wp_last_error()
+        raise WordPieceError(status, (msg or b"").decode("utf-8", "replace") or f"wp_status {status}")
+
+
+def kernel_launch_count() -> int:
+    return int(load_library().wp_kernel_launch_count())
+
+
+def _as_bytes(x) -> bytes:
+    if isinstance(x, str):
+        return x.encode("utf-8")
+    if isinstance(x, np.ndarray):
+        return x.tobytes()
+    return bytes(x)
+
+
+def _buffer_address(buf) -> tuple:
+    """(address, nbytes, keepalive) of a bytes-like / numpy uint8 / mmap object, without copying."""
+    if isinstance(buf, np.ndarray):
+        a = np.ascontiguousarray(buf).view(np.uint8)
+        return a.ctypes.data, a.size, a
+    if isinstance(buf, bytes):
+        return C.cast(C.c_char_p(buf), C.c_void_p).value or 0, len(buf), buf
+    a = np.frombuffer(buf, dtype=np.uint8)
+    return a.ctypes.data, a.size, a
+
+
+class Vocab:
+    """A vocabulary resident on one GPU (``wp_vocab`` handle).
+
+    ``tokens[i]`` is the token with id ``i`` (str or bytes), as in
+    ``utils::parseVocab`` (utils.cpp:108-121).  ``device=-1`` builds a host-only
+    handle (queries and decode only).
+    """
+
+    def __init__(self, tokens: Sequence[Union[str, bytes]], device: int = 0):
+        L = load_library()
+        toks = [_as_bytes(t) for t in tokens]
+        n = len(toks)
+        arr = (C.c_char_p * max(n, 1))(*toks)
+        lens = (C.c_size_t * max(n, 1))(*[len(t) for t in toks])
+        h = C.c_void_p()
+        self._h = None
+        _check(L.wp_vocab_create(arr, lens, n, device, C.byref(h)))
+        self._h = h
+        self._L = L
+
+    @classmethod
+    def from_file(cls, vocab_file: str, device: int = 0) -> "Vocab":
+        L = load_library()
+        h = C.c_void_p()
+        _check(L.wp_vocab_create_from_file(os.fsencode(vocab_file), device, C.byref(h)))
+        self = cls.__new__(cls)
+        self._h = h
+        self._L = L
+        return self
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.wp_vocab_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return int(self._L.wp_vocab_size(self._h))
+
+    @property
+    def unk_id(self) -> int:
+        return int(self._L.wp_vocab_unk_id(self._h))
+
+    @property
+    def max_len(self) -> int:
+        return int(self._L.wp_vocab_max_len(self._h))
+
+    @property
+    def device(self) -> int:
+        return int(self._L.wp_vocab_device(self._h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self._L.wp_vocab_device_bytes(self._h))
+
+    def token_flags(self, index: int) -> int:
+        return int(self._L.wp_vocab_token_flags(self._h, index))
+
+    @property
+    def table_info(self) -> dict:
+        return {
+            "slots": int(self._L.wp_debug_table_slots(self._h)),
+            "nodes": int(self._L.wp_debug_table_nodes(self._h)),
+            "long_tokens": int(self._L.wp_debug_long_tokens(self._h)),
+        }
+
+    def debug_longest_match(self, text: bytes, kind: int):
+        ln, tid = C.c_uint32(), C.c_int32()
+        _check(self._L.wp_debug_longest_match(self._h, text, len(text), kind, C.byref(ln), C.byref(tid)))
+        return int(ln.value), int(tid.value)
+
+    # ---- encode ---------------------------------------------------------
+    def encode(self, text) -> np.ndarray:
+        """Host text (str / bytes / uint8 array / mmap) -> int32 ids (numpy).  ``wp_encode``."""
+        if isinstance(text, str):
+            text = text.encode("utf-8")
+        addr, n, keep = _buffer_address(text)
+        ids = C.POINTER(C.c_int32)()
+        cnt = C.c_size_t()
+        _check(self._L.wp_encode(self._h, addr, n, C.byref(ids), C.byref(cnt)))
+        del keep
+        if cnt.value == 0:
+            if ids:
+                self._L.wp_free(ids)
+            return np.zeros(0, np.int32)
+        out = np.ctypeslib.as_array(ids, shape=(cnt.value,)).copy()
+        self._L.wp_free(ids)
+        return out
+
+    def encode_into(self, text, out: np.ndarray) -> int:
+        """Host text -> caller's int32 numpy buffer; returns the id count.  ``wp_encode_into``."""
+        assert out.dtype == np.int32 and out.flags.c_contiguous
+        addr, n, keep = _buffer_address(text)
+        cnt = C.c_size_t()
+        _check(self._L.wp_encode_into(self._h, addr, n, out.ctypes.data, out.size, C.byref(cnt)))
+        del keep
+        return int(cnt.value)
+
+    def encode_device(self, d_text, d_ids=None, stream=None):
+        """Device text (torch uint8 CUDA tensor) -> (torch int32 CUDA tensor of ids, count).
+
+        ``wp_encode_device``.  ``d_ids`` may be a preallocated int32 tensor (capacity = numel);
+        otherwise one id per byte is allocated (always enough).  Synchronises the stream.
+        """
+        import torch
+
+        assert d_text.is_cuda and d_text.dtype == torch.uint8 and d_text.is_contiguous()
+        n = d_text.numel()
+        if d_ids is None:
+            d_ids = torch.empty(max(n, 1), dtype=torch.int32, device=d_text.device)
+        assert d_ids.is_cuda and d_ids.dtype == torch.int32 and d_ids.is_contiguous()
+        if stream is None:
+            stream = torch.cuda.current_stream(d_text.device).cuda_stream
+        cnt = C.c_size_t()
+        st = self._L.wp_encode_device(self._h, d_text.data_ptr(), n, d_ids.data_ptr(), d_ids.numel(), C.byref(cnt),
+                                      stream)
+        _check(st)
+        return d_ids, int(cnt.value)
+
+    def encode_device_async(self, d_text, d_ids, d_count, stream=None) -> None:
+        """Fully asynchronous variant: count lands in the int64 CUDA tensor ``d_count`` (1 element)."""
+        import torch
+
+        assert d_text.is_cuda and d_text.dtype == torch.uint8 and d_text.is_contiguous()
+        assert d_ids.is_cuda and d_ids.dtype == torch.int32 and d_ids.is_contiguous()
+        assert d_count.is_cuda and d_count.dtype == torch.int64 and d_count.numel() >= 1
+        if stream is None:
+            stream = torch.cuda.current_stream(d_text.device).cuda_stream
+        _check(self._L.wp_encode_device_async(self._h, d_text.data_ptr(), d_text.numel(), d_ids.data_ptr(),
+                                              d_ids.numel(), d_count.data_ptr(), stream))
+
+    def stats(self) -> Stats:
+        s = _StatsStruct()
+        _check(self._L.wp_last_stats(self._h, C.byref(s)))
+        return Stats(s.n_bytes, s.n_ids, s.n_tiles, s.dirty_tiles, s.long_segments, s.kernel_launches)
+
+    # ---- decode ---------------------------------------------------------
+    def decode(self, ids: Iterable[int]) -> List[bytes]:
+        """``word_piece::fast::decode`` (fast.cpp:165-187) -> list of token byte strings."""
+        a = np.ascontiguousarray(np.asarray(list(ids) if not isinstance(ids, np.ndarray) else ids, dtype=np.int32))
+        buf, offs = C.c_void_p(), C.c_void_p()
+        n, skipped = C.c_size_t(), C.c_size_t()
+        _check(self._L.wp_decode(self._h, a.ctypes.data, a.size, C.byref(buf), C.byref(offs), C.byref(n),
+                                 C.byref(skipped)))
+        o = np.ctypeslib.as_array(C.cast(offs, C.POINTER(C.c_size_t)), shape=(n.value + 1,)).copy()
+        raw = C.string_at(buf, int(o[-1]))
+        self._L.wp_free(buf)
+        self._L.wp_free(offs)
+        return [raw[int(o[i]):int(o[i + 1])] for i in range(n.value)]
+
+
+# ---- the reference's stateless entry points ---------------------------------
+
+_cache: dict = {}
+
+
+def _default_device() -> int:
+    return int(os.environ.get("WORDPIECE_B200_DEVICE", "0"))
+
+
+def _cached_vocab(tokens: Sequence[Union[str, bytes]], device: Optional[int]) -> Vocab:
+    dev = _default_device() if device is None else device
+    key = (dev, hash(tuple(_as_bytes(t) for t in tokens)), len(tokens))
+    v = _cache.get(key)
+    if v is None:
+        if len(_cache) >= 4:
+            _cache.pop(next(iter(_cache))).close()
+        v = Vocab(tokens, device=dev)
+        _cache[key] = v
+    return v
+
+
+def _read_vocab_lines(vocab_file: str) -> List[bytes]:
+    # std::getline semantics (utils.cpp:123-137): split at '\n'; no trailing empty token; '\r' stays
+    with open(vocab_file, "rb") as f:
+        data = f.read()
+    lines = data.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    return lines
+
+
+def encode(text, vocab: Sequence[Union[str, bytes]], device: Optional[int] = None) -> np.ndarray:
+    """``word_piece::fast::encode(text, vocab)`` (fast.cpp:154-157)."""
+    return _cached_vocab(vocab, device).encode(text)
+
+
+def encode_files(text_file: str, vocab_file: str, device: Optional[int] = None) -> np.ndarray:
+    """``word_piece::fast::encode(text_file, vocab_file)`` (fast.cpp:159-163)."""
+    v = _cached_vocab(_read_vocab_lines(vocab_file), device)
+    if os.path.getsize(text_file) == 0:
+        return np.zeros(0, np.int32)
+    with open(text_file, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as m:
+        a = np.frombuffer(m, dtype=np.uint8)
+        try:
+            return v.encode(a)
+        finally:
+            del a
+
+
+def decode(vocab_file: str, ids: Iterable[int], device: Optional[int] = -1) -> List[bytes]:
+    """``word_piece::fast::decode(vocab_file, ids)`` (fast.cpp:165-187)."""
+    return _cached_vocab(_read_vocab_lines(vocab_file), device).decode(ids)
+
+
+def _starts_with_space(b: bytes, pos: int, size_arg: int) -> bool:
+    # utf8.cpp:92-96 via :54-90, with the reference's (pointer, remaining) arguments
+    c = b[pos]
+    if c < 0x80:
+        return 0x09 <= c <= 0x0D or c == 0x20
+    return size_arg >= 3 and b[pos:pos + 3] == b"\xe2\x96\x81"
+
+
+def encode_external(text_file: str, vocab_file: str, out_file: str, memory_limit: int,
+                    device: Optional[int] = None) -> None:
+    """``word_piece::fast::encodeExternal`` (fast.cpp:189-220): batches of at most
+    ``memory_limit // 2`` bytes, each extended until its last byte starts a space,
+    ids appended to ``out_file`` as ``"id id id "``."""
+    v = _cached_vocab(_read_vocab_lines(vocab_file), device)
+    max_batch = memory_limit // 2
+    size = os.path.getsize(text_file)
+    with open(out_file, "w") as fout:
+        if size == 0:
+            return
+        with open(text_file, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as m:
+            begin = 0
+            while size > 0:
+                if size > max_batch:
+                    batch = max(max_batch, 1)
+                    while batch < size and not _starts_with_space(m, begin + batch - 1, size - batch):
+                        batch += 1
+                else:
+                    batch = size
+                a = np.frombuffer(m, dtype=np.uint8, count=batch, offset=begin)
+                ids = v.encode(a)
+                del a
+                if ids.size:
+                    fout.write(" ".join(map(str, ids.tolist())) + " ")
+                begin += batch
+                size -= batch

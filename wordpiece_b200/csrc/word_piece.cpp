@@ -1,0 +1,298 @@
+// Host shim: the reference's C++ entry points (include/word_piece.hpp) on top of
+// the C ABI (include/wordpiece_b200.h).  Mirrors src/fast.cpp:143-220 of
+// gleb-kov/wordpiece; the encoding itself happens on the GPU.
+//
+// The reference is stateless — it re-parses the vocabulary and rebuilds both hash
+// maps on every call (fast.cpp:154-157, :21-35; ~14 ms for a 29k vocabulary).
+// Here the device table is built once per distinct vocabulary and cached by a
+// content hash, so repeated calls with the same vocabulary only pay for the text.
+#include "word_piece.hpp"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <list>
+#include <mutex>
+#include <stdexcept>
+#include <thread>
+
+#include "word_piece_utils.hpp"
+#include "wordpiece_b200.h"
+
+namespace {
+
+int shim_device() {
+  const char *e = std::getenv("WORDPIECE_B200_DEVICE");
+  return e ? std::atoi(e) : 0;
+}
+
+[[noreturn]] void raise(wp_status st) {
+  // utils.cpp:100 throws exactly this text; everything else is a runtime_error too (fast path has no other throws
+  // except Boost's mmap failure).
+  if (st == WP_ERR_EMPTY_VOCAB_WORD) throw std::runtime_error("Vocab word is empty");
+  if (st == WP_ERR_ID_RANGE) throw std::out_of_range(wp_last_error());
+  throw std::runtime_error(std::string("wordpiece_b200: ") + wp_last_error());
+}
+
+uint64_t fnv1a(const void *p, size_t n, uint64_t h) {
+  const unsigned char *b = static_cast<const unsigned char *>(p);
+  for (size_t i = 0; i < n; i++) {
+    h ^= b[i];
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+struct CacheEntry {
+  uint64_t key;
+  size_t n_tokens;
+  size_t n_bytes;
+  wp_vocab *handle;
+};
+
+// Small LRU of device vocabularies.  Guarded by one mutex which is also held
+// while a handle is in use: the reference's API is not re-entrant either
+// (one process-global pool whose waitCompletion waits for all tasks,
+// thread_pool.hpp:72-77).
+class VocabCache {
+ public:
+  ~VocabCache() {
+    for (auto &e : entries_) wp_vocab_destroy(e.handle);
+  }
+  std::mutex mu;
+
+  wp_vocab *get(const std::vector<std::string> &vocab) {
+    uint64_t h = 14695981039346656037ull;
+    size_t bytes = 0;
+    for (const std::string &t : vocab) {
+      const uint64_t len = t.size();
+      h = fnv1a(&len, sizeof(len), h);
+      h = fnv1a(t.data(), t.size(), h);
+      bytes += t.size();
+    }
+    for (auto it = entries_.begin(); it != entries_.end(); ++it) {
+      if (it->key == h && it->n_tokens == vocab.size() && it->n_bytes == bytes) {
+        entries_.splice(entries_.begin(), entries_, it);
+        return entries_.front().handle;
+      }
+    }
+    std::vector<const char *> ptrs(vocab.size());
+    std::vector<size_t> lens(vocab.size());
+    for (size_t i = 0; i < vocab.size(); i++) {
+      ptrs[i] = vocab[i].data();
+      lens[i] = vocab[i].size();
+    }
+    wp_vocab *handle = nullptr;
+    const wp_status st = wp_vocab_create(ptrs.data(), lens.data(), vocab.size(), shim_device(), &handle);
+    if (st != WP_OK) raise(st);
+    for (size_t i = 0; i < vocab.size(); i++) {
+      const int fl = wp_vocab_token_flags(handle, i);
+      if (fl & 4) std::cerr << "Vocab word is malformed: " << vocab[i] << std::endl;  // utils.cpp:104
+    }
+    entries_.push_front(CacheEntry{h, vocab.size(), bytes, handle});
+    if (entries_.size() > kMaxEntries) {
+      wp_vocab_destroy(entries_.back().handle);
+      entries_.pop_back();
+    }
+    return handle;
+  }
+
+ private:
+  static constexpr size_t kMaxEntries = 4;
+  std::list<CacheEntry> entries_;
+};
+
+VocabCache &cache() {
+  static VocabCache c;
+  return c;
+}
+
+// utils.cpp:123-137: std::getline over the file; no check that it opened.
+std::vector<std::string> read_vocab_lines(const std::string &file) {
+  std::vector<std::string> lines;
+  std::ifstream fin(file);
+  std::string word;
+  while (std::getline(fin, word)) lines.push_back(word);
+  return lines;
+}
+
+// Read-only mapping of a text file (the reference uses boost::iostreams::mapped_file, fast.cpp:161,196).
+class MappedFile {
+ public:
+  explicit MappedFile(const std::string &path) {
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw std::runtime_error("cannot open file: " + path);
+    struct stat st;
+    if (::fstat(fd, &st) != 0) {
+      ::close(fd);
+      throw std::runtime_error("cannot stat file: " + path);
+    }
+    size_ = static_cast<size_t>(st.st_size);
+    if (size_ > 0) {
+      void *p = ::mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (p == MAP_FAILED) {
+        ::close(fd);
+        throw std::runtime_error("cannot map file: " + path);
+      }
+      data_ = static_cast<const char *>(p);
+    }
+    ::close(fd);
+  }
+  MappedFile(const MappedFile &) = delete;
+  MappedFile &operator=(const MappedFile &) = delete;
+  ~MappedFile() {
+    if (data_) ::munmap(const_cast<char *>(data_), size_);
+  }
+  const char *data() const { return data_; }
+  size_t size() const { return size_; }
+
+ private:
+  const char *data_ = nullptr;
+  size_t size_ = 0;
+};
+
+// fast.cpp:143-150
+std::vector<int> encode_buffer(wp_vocab *v, const char *text, size_t size) {
+  if (size == 0) return {};
+  int32_t *ids = nullptr;
+  size_t n = 0;
+  const wp_status st = wp_encode(v, text, size, &ids, &n);
+  if (st != WP_OK) raise(st);
+  wp_stats stats{};
+  wp_last_stats(v, &stats);
+  if (stats.dirty_tiles > 0)  // utf8.cpp:143-145
+    std::cerr << "WARNING Input contains invalid unicode characters." << std::endl;
+  std::vector<int> out(ids, ids + n);
+  wp_free(ids);
+  return out;
+}
+
+// utf8.cpp:92-96 with :54-90 — does the sequence at `p` decode to an is_space char?
+bool starts_with_space(const char *p, size_t size) {
+  if (size == 0) return false;
+  const unsigned char c = static_cast<unsigned char>(p[0]);
+  if (c < 0x80) return (c >= 0x09 && c <= 0x0D) || c == 0x20;
+  return size >= 3 && c == 0xE2 && static_cast<unsigned char>(p[1]) == 0x96 &&
+         static_cast<unsigned char>(p[2]) == 0x81;  // U+2581
+}
+
+}  // namespace
+
+namespace word_piece {
+namespace fast {
+
+std::vector<int> encode(const std::string &text, const std::vector<std::string> &vocab) {
+  std::lock_guard<std::mutex> lock(cache().mu);
+  wp_vocab *v = cache().get(vocab);
+  return encode_buffer(v, text.data(), text.size());
+}
+
+std::vector<int> encode(const std::string &text_file, const std::string &vocab_file) {
+  std::lock_guard<std::mutex> lock(cache().mu);
+  wp_vocab *v = cache().get(read_vocab_lines(vocab_file));
+  MappedFile map(text_file);
+  return encode_buffer(v, map.data(), map.size());
+}
+
+std::vector<std::string> decode(const std::string vocab_file, const std::vector<int> &ids) {
+  std::lock_guard<std::mutex> lock(cache().mu);
+  wp_vocab *v = cache().get(read_vocab_lines(vocab_file));
+  const size_t size = wp_vocab_size(v);
+  for (int id : ids) {  // fast.cpp:171-178 diagnostics
+    if (id < 0 || static_cast<size_t>(id) > size) {
+      std::cerr << "no token " << id << std::endl;
+    } else if (static_cast<size_t>(id) < size && (wp_vocab_token_flags(v, static_cast<size_t>(id)) & 4)) {
+      std::cerr << "trying to access malformed token" << std::endl;
+    }
+  }
+  char *buf = nullptr;
+  size_t *offs = nullptr;
+  size_t n = 0;
+  static_assert(sizeof(int) == sizeof(int32_t), "ids are 32-bit");
+  const wp_status st = wp_decode(v, reinterpret_cast<const int32_t *>(ids.data()), ids.size(), &buf, &offs, &n, nullptr);
+  if (st != WP_OK) raise(st);
+  std::vector<std::string> result;
+  result.reserve(n);
+  for (size_t i = 0; i < n; i++) result.emplace_back(buf + offs[i], offs[i + 1] - offs[i]);
+  wp_free(buf);
+  wp_free(offs);
+  return result;
+}
+
+void encodeExternal(const std::string &text_file,
+                    const std::string &vocab_file,
+                    const std::string &out_file,
+                    size_t memory_limit) {
+  std::lock_guard<std::mutex> lock(cache().mu);
+  wp_vocab *v = cache().get(read_vocab_lines(vocab_file));
+  const size_t max_text_batch = memory_limit / 2;  // fast.cpp:194
+  MappedFile map(text_file);
+  const char *begin = map.data();
+  size_t size = map.size();
+  std::ofstream fout(out_file);
+  std::string line;
+  while (size > 0) {
+    size_t batch;
+    if (size > max_text_batch) {  // fast.cpp:202-211: extend until the last byte of the batch starts a space
+      batch = max_text_batch;
+      if (batch == 0) batch = 1;
+      while (batch < size && !starts_with_space(begin + batch - 1, size - batch)) batch++;
+    } else {
+      batch = size;
+    }
+    const std::vector<int> ids = encode_buffer(v, begin, batch);
+    line.clear();
+    for (int id : ids) {  // fast.cpp:214-216
+      line += std::to_string(id);
+      line.push_back(' ');
+    }
+    fout << line;
+    begin += batch;
+    size -= batch;
+  }
+}
+
+}  // namespace fast
+}  // namespace word_piece
+
+namespace utils {
+
+ThreadPool::ThreadPool(size_t n_threads) : n_threads_(n_threads) {
+  if (n_threads_ == 0) {
+    n_threads_ = std::thread::hardware_concurrency();
+    if (n_threads_ == 0) n_threads_ = 8;  // thread_pool.hpp:24-29
+  }
+}
+
+ThreadPool &globalThreadPool(size_t n_threads) {
+  static ThreadPool pool(n_threads);  // frozen by the first caller, utils.cpp:25-28
+  return pool;
+}
+
+void writeToFile(const std::string &file, const std::vector<int> &ids) {
+  std::ofstream fout(file);
+  std::string line;
+  for (int id : ids) {
+    line += std::to_string(id);
+    line.push_back(' ');
+    if (line.size() > (1u << 16)) {
+      fout << line;
+      line.clear();
+    }
+  }
+  fout << line;
+}
+
+int64_t currentTs() {
+  return std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::system_clock::now().time_since_epoch())
+      .count();
+}
+
+}  // namespace utils

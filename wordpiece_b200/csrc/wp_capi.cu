@@ -1,0 +1,485 @@
+// C ABI of the B200-native fast WordPiece encoder (include/wordpiece_b200.h).
+// Host logic only: handle lifetime, device buffers, streams, error reporting.
+// All tokenisation work happens in the CUDA kernels of wp_encode.cu; there is no
+// CPU fallback — without a usable CUDA device every call fails loudly.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/wordpiece_b200.h"
+#include "wp_encode.h"
+#include "wp_vocab.h"
+
+namespace {
+
+thread_local std::string g_error;
+const char *const kHostOnly = "host-only vocabulary handle (device -1): encoding needs a CUDA device; there is no CPU path";
+std::atomic<uint64_t> g_launches{0};
+
+wp_status fail(wp_status st, const std::string &msg) {
+  g_error = msg;
+  return st;
+}
+
+#define WP_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(WP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorName(_e) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// scratch header at the start of the workspace (all zeroed before a launch)
+struct ScratchHeader {
+  unsigned int ticket;
+  unsigned int pad;
+  unsigned long long n_ids;
+  unsigned long long dirty_tiles;
+  unsigned long long long_segments;
+};
+
+}  // namespace
+
+struct wp_vocab {
+  wp::HostVocab host;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  // device table
+  wp::Slot *d_slots = nullptr;
+  uint32_t *d_long_ref = nullptr;
+  uint32_t *d_long_entries = nullptr;
+  uint8_t *d_long_bytes = nullptr;
+  size_t device_bytes = 0;
+  // scratch, grown on demand
+  uint8_t *d_work = nullptr;
+  size_t work_bytes = 0;
+  uint8_t *d_text = nullptr;  // staging for the host-buffer entry points
+  size_t text_cap = 0;
+  int32_t *d_ids = nullptr;
+  size_t ids_cap = 0;
+  ScratchHeader *h_header = nullptr;  // pinned
+  wp_stats stats{};
+};
+
+namespace {
+
+wp::DeviceVocab device_view(const wp_vocab *v) {
+  wp::DeviceVocab d{};
+  d.slots = v->d_slots;
+  d.slot_mask = static_cast<uint32_t>(v->host.slots.size() - 1);
+  d.long_ref = v->d_long_ref;
+  d.long_entries = v->d_long_entries;
+  d.long_bytes = v->d_long_bytes;
+  d.unk_id = v->host.unk_id;
+  d.han_swallow = v->host.max_len >= 2 ? 1u : 0u;
+  return d;
+}
+
+wp_status upload(wp_vocab *v) {
+  const wp::HostVocab &h = v->host;
+  const size_t b_slots = h.slots.size() * sizeof(wp::Slot);
+  const size_t b_ref = h.long_ref.size() * sizeof(uint32_t);
+  const size_t b_ent = h.long_entries.size() * sizeof(uint32_t);
+  const size_t b_bytes = h.long_bytes.size();
+  WP_CUDA(cudaMalloc(&v->d_slots, b_slots));
+  WP_CUDA(cudaMalloc(&v->d_long_ref, b_ref));
+  WP_CUDA(cudaMalloc(&v->d_long_entries, b_ent));
+  WP_CUDA(cudaMalloc(&v->d_long_bytes, b_bytes));
+  WP_CUDA(cudaMemcpy(v->d_slots, h.slots.data(), b_slots, cudaMemcpyHostToDevice));
+  WP_CUDA(cudaMemcpy(v->d_long_ref, h.long_ref.data(), b_ref, cudaMemcpyHostToDevice));
+  WP_CUDA(cudaMemcpy(v->d_long_entries, h.long_entries.data(), b_ent, cudaMemcpyHostToDevice));
+  WP_CUDA(cudaMemcpy(v->d_long_bytes, h.long_bytes.data(), b_bytes, cudaMemcpyHostToDevice));
+  v->device_bytes = b_slots + b_ref + b_ent + b_bytes;
+  WP_CUDA(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
+  WP_CUDA(cudaMallocHost(&v->h_header, sizeof(ScratchHeader)));
+  return WP_OK;
+}
+
+wp_status ensure_work(wp_vocab *v, size_t n_tiles) {
+  const size_t need = sizeof(ScratchHeader) + n_tiles * sizeof(unsigned long long);
+  if (need > v->work_bytes) {
+    if (v->d_work) cudaFree(v->d_work);
+    v->d_work = nullptr;
+    v->work_bytes = 0;
+    const size_t cap = need + need / 2 + 4096;
+    WP_CUDA(cudaMalloc(&v->d_work, cap));
+    v->work_bytes = cap;
+  }
+  return WP_OK;
+}
+
+// Enqueue scratch reset + kernel on `stream`.  No synchronisation.
+wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_t *d_ids, size_t capacity,
+                         cudaStream_t stream, uint32_t *n_tiles_out) {
+  const uint32_t tile = wp::encode_tile_bytes();
+  const size_t n_tiles = (n_bytes + tile - 1) / tile;
+  if (n_tiles > 0x7FFFFFFFull) return fail(WP_ERR_INVALID_ARG, "text too large for one call (> 2^31 tiles)");
+  wp_status st = ensure_work(v, n_tiles);
+  if (st != WP_OK) return st;
+  const size_t reset = sizeof(ScratchHeader) + n_tiles * sizeof(unsigned long long);
+  WP_CUDA(cudaMemsetAsync(v->d_work, 0, reset, stream));
+  ScratchHeader *hdr = reinterpret_cast<ScratchHeader *>(v->d_work);
+  wp::EncodeParams P{};
+  P.vocab = device_view(v);
+  P.text = static_cast<const uint8_t *>(d_text);
+  P.n_bytes = n_bytes;
+  P.ids = d_ids;
+  P.capacity = capacity;
+  P.n_tiles = static_cast<uint32_t>(n_tiles);
+  P.ticket = &hdr->ticket;
+  P.n_ids_out = &hdr->n_ids;
+  P.stat_dirty_tiles = &hdr->dirty_tiles;
+  P.stat_long_segments = &hdr->long_segments;
+  P.tile_state = reinterpret_cast<unsigned long long *>(v->d_work + sizeof(ScratchHeader));
+  WP_CUDA(wp::launch_encode(P, stream));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  *n_tiles_out = static_cast<uint32_t>(n_tiles);
+  return WP_OK;
+}
+
+wp_status finish_stats(wp_vocab *v, size_t n_bytes, uint32_t n_tiles, cudaStream_t stream) {
+  WP_CUDA(cudaMemcpyAsync(v->h_header, v->d_work, sizeof(ScratchHeader), cudaMemcpyDeviceToHost, stream));
+  WP_CUDA(cudaStreamSynchronize(stream));
+  v->stats.n_bytes = n_bytes;
+  v->stats.n_ids = v->h_header->n_ids;
+  v->stats.n_tiles = n_tiles;
+  v->stats.dirty_tiles = v->h_header->dirty_tiles;
+  v->stats.long_segments = v->h_header->long_segments;
+  v->stats.kernel_launches = 1;
+  return WP_OK;
+}
+
+wp_status create_common(wp_vocab *v, const char *const *tokens, const size_t *lens, size_t n, int device,
+                        wp_vocab **out) {
+  std::string err;
+  if (!wp::build_host_vocab(tokens, lens, n, &v->host, &err)) {
+    delete v;
+    return fail(WP_ERR_EMPTY_VOCAB_WORD, err);
+  }
+  if (device == -1) {  // host-only handle: vocabulary queries and decode work, every encode call fails
+    v->device = -1;
+    *out = v;
+    return WP_OK;
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+    delete v;
+    return fail(WP_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+  }
+  if (device < 0 || device >= count) {
+    delete v;
+    return fail(WP_ERR_INVALID_ARG, "device ordinal out of range");
+  }
+  v->device = device;
+  DeviceGuard g(device);
+  if (!g.ok) {
+    delete v;
+    return fail(WP_ERR_CUDA, "cudaSetDevice failed");
+  }
+  wp_status st = upload(v);
+  if (st != WP_OK) {
+    std::string keep = g_error;
+    wp_vocab_destroy(v);
+    g_error = keep;
+    return st;
+  }
+  *out = v;
+  return WP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *wp_last_error(void) { return g_error.c_str(); }
+
+uint64_t wp_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void wp_free(void *p) { std::free(p); }
+
+wp_status wp_vocab_create(const char *const *tokens, const size_t *token_lens, size_t n_tokens, int device,
+                          wp_vocab **out) {
+  if (out == nullptr || (n_tokens > 0 && (tokens == nullptr || token_lens == nullptr)))
+    return fail(WP_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  wp_vocab *v = new (std::nothrow) wp_vocab();
+  if (!v) return fail(WP_ERR_NOMEM, "out of memory");
+  return create_common(v, tokens, token_lens, n_tokens, device, out);
+}
+
+wp_status wp_vocab_create_from_file(const char *vocab_file, int device, wp_vocab **out) {
+  if (out == nullptr || vocab_file == nullptr) return fail(WP_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  std::ifstream fin(vocab_file, std::ios::binary);
+  // utils.cpp:123-137 never checks the stream: an unreadable file is an empty vocabulary there.
+  // We report it, since silently encoding everything to UNK helps nobody.
+  if (!fin) return fail(WP_ERR_IO, std::string("cannot open vocab file: ") + vocab_file);
+  std::vector<std::string> lines;
+  std::string line;
+  while (std::getline(fin, line)) lines.push_back(line);  // '\r' stays, as with the reference's getline
+  std::vector<const char *> ptrs(lines.size());
+  std::vector<size_t> lens(lines.size());
+  for (size_t i = 0; i < lines.size(); i++) {
+    ptrs[i] = lines[i].data();
+    lens[i] = lines[i].size();
+  }
+  wp_vocab *v = new (std::nothrow) wp_vocab();
+  if (!v) return fail(WP_ERR_NOMEM, "out of memory");
+  return create_common(v, ptrs.data(), lens.data(), lines.size(), device, out);
+}
+
+void wp_vocab_destroy(wp_vocab *v) {
+  if (!v) return;
+  if (v->device >= 0) {
+    DeviceGuard g(v->device);
+    if (v->stream) cudaStreamSynchronize(v->stream);
+    cudaFree(v->d_slots);
+    cudaFree(v->d_long_ref);
+    cudaFree(v->d_long_entries);
+    cudaFree(v->d_long_bytes);
+    cudaFree(v->d_work);
+    cudaFree(v->d_text);
+    cudaFree(v->d_ids);
+    if (v->h_header) cudaFreeHost(v->h_header);
+    if (v->stream) cudaStreamDestroy(v->stream);
+  }
+  delete v;
+}
+
+size_t wp_vocab_size(const wp_vocab *v) { return v ? v->host.tokens.size() : 0; }
+int32_t wp_vocab_unk_id(const wp_vocab *v) { return v ? v->host.unk_id : -1; }
+size_t wp_vocab_max_len(const wp_vocab *v) { return v ? v->host.max_len : 0; }
+int wp_vocab_device(const wp_vocab *v) { return v ? v->device : -1; }
+size_t wp_vocab_device_bytes(const wp_vocab *v) { return v ? v->device_bytes : 0; }
+
+int wp_vocab_token_flags(const wp_vocab *v, size_t index) {
+  if (!v || index >= v->host.tokens.size()) return -1;
+  const wp::HostToken &t = v->host.tokens[index];
+  return (t.is_prefix ? 1 : 0) | (t.is_special ? 2 : 0) | (t.is_malformed ? 4 : 0) | (t.had_invalid ? 8 : 0);
+}
+
+wp_status wp_encode_device_async(wp_vocab *v, const void *d_text, size_t n_bytes, int32_t *d_ids, size_t capacity,
+                                 uint64_t *d_n_ids, void *stream) {
+  if (!v || (n_bytes > 0 && d_text == nullptr) || (capacity > 0 && d_ids == nullptr))
+    return fail(WP_ERR_INVALID_ARG, "null argument");
+  if (v->device < 0) return fail(WP_ERR_NO_DEVICE, kHostOnly);
+  DeviceGuard g(v->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : v->stream;
+  if (n_bytes == 0) {  // fast.cpp:145
+    if (d_n_ids) WP_CUDA(cudaMemsetAsync(d_n_ids, 0, sizeof(uint64_t), s));
+    return WP_OK;
+  }
+  uint32_t n_tiles = 0;
+  wp_status st = enqueue_encode(v, d_text, n_bytes, d_ids, capacity, s, &n_tiles);
+  if (st != WP_OK) return st;
+  if (d_n_ids) {
+    ScratchHeader *hdr = reinterpret_cast<ScratchHeader *>(v->d_work);
+    WP_CUDA(cudaMemcpyAsync(d_n_ids, &hdr->n_ids, sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+  }
+  return WP_OK;
+}
+
+wp_status wp_encode_device(wp_vocab *v, const void *d_text, size_t n_bytes, int32_t *d_ids, size_t capacity,
+                           size_t *n_ids, void *stream) {
+  if (!v || n_ids == nullptr || (n_bytes > 0 && d_text == nullptr) || (capacity > 0 && d_ids == nullptr))
+    return fail(WP_ERR_INVALID_ARG, "null argument");
+  *n_ids = 0;
+  if (v->device < 0) return fail(WP_ERR_NO_DEVICE, kHostOnly);
+  DeviceGuard g(v->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : v->stream;
+  if (n_bytes == 0) {
+    v->stats = wp_stats{};
+    return WP_OK;
+  }
+  uint32_t n_tiles = 0;
+  wp_status st = enqueue_encode(v, d_text, n_bytes, d_ids, capacity, s, &n_tiles);
+  if (st != WP_OK) return st;
+  st = finish_stats(v, n_bytes, n_tiles, s);
+  if (st != WP_OK) return st;
+  *n_ids = static_cast<size_t>(v->stats.n_ids);
+  if (v->stats.n_ids > capacity) return fail(WP_ERR_CAPACITY, "id buffer too small");
+  return WP_OK;
+}
+
+wp_status wp_encode_into(wp_vocab *v, const char *text, size_t n_bytes, int32_t *ids, size_t capacity,
+                         size_t *n_ids) {
+  if (!v || n_ids == nullptr || (n_bytes > 0 && text == nullptr)) return fail(WP_ERR_INVALID_ARG, "null argument");
+  *n_ids = 0;
+  if (v->device < 0) return fail(WP_ERR_NO_DEVICE, kHostOnly);
+  if (n_bytes == 0) {
+    v->stats = wp_stats{};
+    return WP_OK;
+  }
+  DeviceGuard g(v->device);
+  if (n_bytes > v->text_cap) {
+    cudaFree(v->d_text);
+    v->d_text = nullptr;
+    v->text_cap = 0;
+    const size_t cap = n_bytes + n_bytes / 8 + 256;
+    WP_CUDA(cudaMalloc(&v->d_text, cap));
+    v->text_cap = cap;
+  }
+  // One id per byte is the worst case (a run of single-byte tokens); allocate what the caller can take,
+  // bounded by that, and retry once with the exact count if the guess was short.
+  size_t want = capacity < n_bytes ? capacity : n_bytes;
+  if (want == 0) want = 1;
+  if (want > v->ids_cap) {
+    cudaFree(v->d_ids);
+    v->d_ids = nullptr;
+    v->ids_cap = 0;
+    WP_CUDA(cudaMalloc(&v->d_ids, want * sizeof(int32_t)));
+    v->ids_cap = want;
+  }
+  WP_CUDA(cudaMemcpyAsync(v->d_text, text, n_bytes, cudaMemcpyHostToDevice, v->stream));
+  uint32_t n_tiles = 0;
+  wp_status st = enqueue_encode(v, v->d_text, n_bytes, v->d_ids, v->ids_cap, v->stream, &n_tiles);
+  if (st != WP_OK) return st;
+  st = finish_stats(v, n_bytes, n_tiles, v->stream);
+  if (st != WP_OK) return st;
+  *n_ids = static_cast<size_t>(v->stats.n_ids);
+  if (v->stats.n_ids > capacity) return fail(WP_ERR_CAPACITY, "id buffer too small");
+  if (*n_ids > 0) {
+    WP_CUDA(cudaMemcpyAsync(ids, v->d_ids, *n_ids * sizeof(int32_t), cudaMemcpyDeviceToHost, v->stream));
+    WP_CUDA(cudaStreamSynchronize(v->stream));
+  }
+  return WP_OK;
+}
+
+wp_status wp_encode(wp_vocab *v, const char *text, size_t n_bytes, int32_t **ids_out, size_t *n_ids) {
+  if (!v || ids_out == nullptr || n_ids == nullptr || (n_bytes > 0 && text == nullptr))
+    return fail(WP_ERR_INVALID_ARG, "null argument");
+  *ids_out = nullptr;
+  *n_ids = 0;
+  if (v->device < 0) return fail(WP_ERR_NO_DEVICE, kHostOnly);
+  if (n_bytes == 0) {
+    v->stats = wp_stats{};
+    return WP_OK;
+  }
+  DeviceGuard g(v->device);
+  if (n_bytes > v->text_cap) {
+    cudaFree(v->d_text);
+    v->d_text = nullptr;
+    v->text_cap = 0;
+    const size_t cap = n_bytes + n_bytes / 8 + 256;
+    WP_CUDA(cudaMalloc(&v->d_text, cap));
+    v->text_cap = cap;
+  }
+  // first guess: half an id per byte (English-like text needs ~0.25); exact retry if short
+  size_t guess = n_bytes / 2 + 1024;
+  if (guess > n_bytes) guess = n_bytes;
+  WP_CUDA(cudaMemcpyAsync(v->d_text, text, n_bytes, cudaMemcpyHostToDevice, v->stream));
+  for (int attempt = 0; attempt < 2; attempt++) {
+    if (guess > v->ids_cap) {
+      cudaFree(v->d_ids);
+      v->d_ids = nullptr;
+      v->ids_cap = 0;
+      WP_CUDA(cudaMalloc(&v->d_ids, guess * sizeof(int32_t)));
+      v->ids_cap = guess;
+    }
+    uint32_t n_tiles = 0;
+    wp_status st = enqueue_encode(v, v->d_text, n_bytes, v->d_ids, v->ids_cap, v->stream, &n_tiles);
+    if (st != WP_OK) return st;
+    st = finish_stats(v, n_bytes, n_tiles, v->stream);
+    if (st != WP_OK) return st;
+    if (v->stats.n_ids <= v->ids_cap) break;
+    guess = static_cast<size_t>(v->stats.n_ids);
+    v->stats.kernel_launches += 1;
+  }
+  const size_t cnt = static_cast<size_t>(v->stats.n_ids);
+  int32_t *host = static_cast<int32_t *>(std::malloc(cnt ? cnt * sizeof(int32_t) : 1));
+  if (!host) return fail(WP_ERR_NOMEM, "out of memory");
+  if (cnt > 0) {
+    cudaError_t e = cudaMemcpyAsync(host, v->d_ids, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, v->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(v->stream);
+    if (e != cudaSuccess) {
+      std::free(host);
+      return fail(WP_ERR_CUDA, std::string("copy ids: ") + cudaGetErrorString(e));
+    }
+  }
+  *ids_out = host;
+  *n_ids = cnt;
+  return WP_OK;
+}
+
+wp_status wp_last_stats(wp_vocab *v, wp_stats *out) {
+  if (!v || !out) return fail(WP_ERR_INVALID_ARG, "null argument");
+  *out = v->stats;
+  return WP_OK;
+}
+
+wp_status wp_decode(const wp_vocab *v, const int32_t *ids, size_t n_ids, char **out, size_t **offsets_out,
+                    size_t *n_tokens, size_t *n_skipped) {
+  if (!v || !out || !offsets_out || !n_tokens || (n_ids > 0 && !ids)) return fail(WP_ERR_INVALID_ARG, "null argument");
+  std::string joined;
+  std::vector<size_t> offs;
+  offs.push_back(0);
+  size_t skipped = 0;
+  const size_t size = v->host.tokens.size();
+  for (size_t i = 0; i < n_ids; i++) {
+    const int32_t id = ids[i];
+    if (id < 0 || static_cast<size_t>(id) > size) {  // fast.cpp:171-174 (note the reference's `>`)
+      skipped++;
+      continue;
+    }
+    if (static_cast<size_t>(id) == size) return fail(WP_ERR_ID_RANGE, "token id equals vocabulary size");  // :175 .at()
+    const wp::HostToken &t = v->host.tokens[static_cast<size_t>(id)];
+    if (t.is_malformed) {  // fast.cpp:176-177
+      skipped++;
+      continue;
+    }
+    if (!t.is_prefix) joined += "##";  // fast.cpp:180-183
+    joined += t.word;
+    offs.push_back(joined.size());
+  }
+  char *buf = static_cast<char *>(std::malloc(joined.size() + 1));
+  size_t *ob = static_cast<size_t *>(std::malloc(offs.size() * sizeof(size_t)));
+  if (!buf || !ob) {
+    std::free(buf);
+    std::free(ob);
+    return fail(WP_ERR_NOMEM, "out of memory");
+  }
+  std::memcpy(buf, joined.data(), joined.size());
+  buf[joined.size()] = 0;
+  std::memcpy(ob, offs.data(), offs.size() * sizeof(size_t));
+  *out = buf;
+  *offsets_out = ob;
+  *n_tokens = offs.size() - 1;
+  if (n_skipped) *n_skipped = skipped;
+  return WP_OK;
+}
+
+// Test hook: the host mirror of the device longest-match query (wp_vocab.cpp), so that the table
+// image can be unit-tested without a GPU.  Nothing on the encode path calls it.
+wp_status wp_debug_longest_match(const wp_vocab *v, const char *text, size_t window_bytes, int kind,
+                                 uint32_t *len_out, int32_t *id_out) {
+  if (!v || !text || !len_out || !id_out) return fail(WP_ERR_INVALID_ARG, "null argument");
+  const wp::MatchResult r =
+      wp::host_longest_match(v->host, reinterpret_cast<const uint8_t *>(text), window_bytes, kind ? 1u : 0u);
+  *len_out = r.len;
+  *id_out = r.id;
+  return WP_OK;
+}
+
+size_t wp_debug_table_slots(const wp_vocab *v) { return v ? v->host.slots.size() : 0; }
+size_t wp_debug_table_nodes(const wp_vocab *v) { return v ? v->host.n_nodes : 0; }
+size_t wp_debug_long_tokens(const wp_vocab *v) { return v ? v->host.n_long : 0; }
+
+}  // extern "C"

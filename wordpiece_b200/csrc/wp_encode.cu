@@ -1,0 +1,859 @@
+// Fused WordPiece encode kernel for sm_100a: word split -> longest match ->
+// scan + scatter, one text tile per CTA, nothing but the text is read from HBM
+// and nothing but the ids is written to it.
+//
+// What it reproduces (gleb-kov/wordpiece):
+//   utils.cpp:37-79 / utf8.cpp:130-147   strict UTF-8 decode, invalid bytes dropped
+//   utf8.cpp:10-29                       space / punctuation / Han classes
+//   fast.cpp:38-41                       word-initial positions
+//   fast.cpp:43-99                       the greedy longest-match worker with
+//                                        whole-word UNK roll-back
+//   fast.cpp:101-138                     chunk + concat (here: tiles + one
+//                                        decoupled look-back scan)
+//
+// Stages inside the kernel (DESIGN.md has the full account):
+//   S1 split   : a tile (8 KB + halo) is staged in shared memory with 16-byte
+//                loads; each thread classifies a 32-byte chunk into bit masks
+//                (valid lead / space / punct / Han), tiles holding invalid UTF-8
+//                are compacted in shared memory, and segment starts ("safe
+//                starts") fall out of a few mask operations.
+//   S2 match   : the thread that owns a chunk runs the greedy matcher over the
+//                segments that start in it, probing the hashed-trie table
+//                (wp_table.h): whole window first, then binary search.
+//   S3 scatter : per-thread token counts -> block scan -> decoupled look-back
+//                across tiles -> ids copied from the shared staging area to
+//                their final positions.
+//   A segment that does not end inside the tile's window (at most one per tile)
+//   is walked straight from global memory by one thread (count, then emit).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "wp_encode.h"
+#include "wp_table.h"
+
+namespace wp {
+
+// ------------------------------------------------------------------ geometry
+constexpr int TILE = 8192;                       // text bytes owned by one CTA
+constexpr int CHUNK = 32;                        // bytes classified by one thread at a time
+constexpr int THREADS = TILE / CHUNK;            // 256
+constexpr int HALO = 256;                        // classified bytes past the tile (segment completion)
+constexpr int LOOKAHEAD = 32;                    // loaded, not classified (UTF-8 validation look-ahead)
+constexpr int LEFT = 16;                         // bytes before the tile (ownership of leading continuation bytes)
+constexpr int WINDOW = TILE + HALO;              // classified window
+constexpr int NCHUNK = WINDOW / CHUNK;           // 264
+constexpr int OWNED_CHUNKS = TILE / CHUNK;       // 256
+constexpr int RAW_BYTES = LEFT + WINDOW + LOOKAHEAD;  // 8496
+constexpr int WARPS = THREADS / 32;
+constexpr int32_t LONG_NONE = -1;
+
+static_assert(RAW_BYTES % 16 == 0, "raw buffer is loaded in 16-byte units");
+static_assert(WP_KEY_BYTES + 4 <= LOOKAHEAD, "key window reads stay inside the loaded bytes");
+
+struct __align__(16) TileSmem {
+  uint8_t raw[RAW_BYTES];              // [0,LEFT) left halo, then the window, then look-ahead
+  uint8_t packed[WINDOW + LOOKAHEAD + 16];  // compacted copy (only for tiles with invalid UTF-8)
+  int32_t stage[WINDOW + 8];           // ids of a segment starting at byte s live at stage[s..s+cnt)
+  uint16_t segcnt[TILE];               // token count of the segment starting at byte s
+  uint32_t m_lead[NCHUNK + 1];         // valid lead bytes
+  uint32_t m_space[NCHUNK + 1];
+  uint32_t m_punct[NCHUNK + 1];
+  uint32_t m_han[NCHUNK + 1];
+  uint32_t m_cover[NCHUNK + 1];        // bytes covered by a valid sequence that starts in this chunk
+  uint32_t m_kept[NCHUNK + 1];         // bytes of the RAW window that survive the strict decoder (dirty tiles)
+  uint32_t kept_scan[NCHUNK + 2];      // exclusive scan of kept bytes per chunk (dirty tiles)
+  uint8_t spill[NCHUNK + 1];           // bytes by which the chunk's last sequence runs into the next chunk
+  uint32_t warp_sums[WARPS];
+  uint32_t tile_index;
+  uint32_t prev_class;                 // class of the last valid char before the tile
+  uint32_t left_spill;                 // bytes of the tile start covered by a sequence that began before it
+  int32_t long_start;                  // window position of the segment that leaves the window, or LONG_NONE
+  uint32_t long_count;
+  int32_t long_unk_at;
+  unsigned long long tile_base;        // ids produced by all earlier tiles
+};
+
+// ------------------------------------------------------------------- helpers
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
+
+// 0x80 in every byte lane whose (7-bit) value lies in [lo, hi]; lanes must be < 0x80.
+__device__ __forceinline__ uint32_t swar_range(uint32_t w, uint32_t lo, uint32_t hi) {
+  const uint32_t ge_lo = w + (0x80808080u - lo * 0x01010101u);
+  const uint32_t gt_hi = w + (0x80808080u - (hi + 1u) * 0x01010101u);
+  return ge_lo & ~gt_hi & 0x80808080u;
+}
+
+// gather the four 0x80 flags of a word into a nibble (lane 0 -> bit 0)
+__device__ __forceinline__ uint32_t swar_nibble(uint32_t flags) { return (((flags >> 7) * 0x01020408u) >> 24) & 0xFu; }
+
+// Class of a decoded char from its UTF-8 bytes (valid sequence of length len).
+__device__ __forceinline__ uint32_t class_of(uint32_t cp) { return cp_class(cp); }
+
+// ---------------------------------------------------------------- table probe
+
+struct NodeHit {
+  uint32_t w5;
+  int32_t term_id;
+  int32_t best_id;
+  uint32_t slot;
+};
+
+__device__ __forceinline__ bool probe_node(const DeviceVocab &V, const uint32_t kw[6], NodeHit *hit) {
+  uint32_t idx = key_hash(kw[0], kw[1], kw[2], kw[3], kw[4], kw[5]) & V.slot_mask;
+  const uint4 *tab = reinterpret_cast<const uint4 *>(V.slots);
+  for (;;) {
+    const uint4 a = __ldg(tab + 2 * idx);
+    const uint4 b = __ldg(tab + 2 * idx + 1);
+    if (slot_len(b.y) == 0) return false;
+    if (a.x == kw[0] && a.y == kw[1] && a.z == kw[2] && a.w == kw[3] && b.x == kw[4] &&
+        ((b.y ^ kw[5]) & WP_W5_KEYMASK) == 0) {
+      hit->w5 = b.y;
+      hit->term_id = static_cast<int32_t>(b.z);
+      hit->best_id = static_cast<int32_t>(b.w);
+      hit->slot = idx;
+      return true;
+    }
+    idx = (idx + 1) & V.slot_mask;
+  }
+}
+
+// Key words for the first k (1..22) bytes of the 24 raw window bytes r[0..5].
+__device__ __forceinline__ void make_key(const uint32_t r[6], uint32_t k, uint32_t kind, uint32_t kw[6]) {
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    const int nb = static_cast<int>(k) - 4 * i;
+    kw[i] = nb >= 4 ? r[i] : (nb <= 0 ? 0u : (r[i] & ((1u << (8 * nb)) - 1u)));
+  }
+  const int nb5 = static_cast<int>(k) - 20;
+  const uint32_t tail = nb5 <= 0 ? 0u : (r[5] & ((1u << (8 * nb5)) - 1u));
+  kw[5] = make_w5(tail, k, kind);
+}
+
+// Deepest trie node along the window whose first min(window,22) bytes are r[];
+// returns its depth (0 = none).  Node existence is monotone in the depth, so
+// after the whole-window probe a binary search suffices.
+__device__ __forceinline__ uint32_t deepest_node(const DeviceVocab &V, const uint32_t r[6], uint32_t k0, uint32_t kind,
+                                                 NodeHit *node) {
+  uint32_t kw[6];
+  make_key(r, k0, kind, kw);
+  if (probe_node(V, kw, node)) return k0;
+  uint32_t lo = 0, hi = k0;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    NodeHit h;
+    make_key(r, mid, kind, kw);
+    if (probe_node(V, kw, &h)) {
+      lo = mid;
+      *node = h;
+    } else {
+      hi = mid;
+    }
+  }
+  return lo;
+}
+
+// ------------------------------------------------- longest match, shared memory
+
+// Longest token of `kind` that is a prefix of buf[p, p+window).  Bytes are clean
+// (valid UTF-8, nothing to drop) and at least 28 bytes past p are readable.
+__device__ __forceinline__ uint32_t longest_match_smem(const DeviceVocab &V, const uint8_t *buf, int p, int window,
+                                                       uint32_t kind, int32_t *id) {
+  const int a = p & ~3;
+  const uint32_t sh = (p & 3) * 8;
+  uint32_t x[7];
+#pragma unroll
+  for (int i = 0; i < 7; i++) x[i] = ld_u32(buf + a + 4 * i);
+  uint32_t r[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) r[i] = __funnelshift_r(x[i], x[i + 1], sh);
+
+  const uint32_t k0 = window < static_cast<int>(WP_KEY_BYTES) ? window : WP_KEY_BYTES;
+  NodeHit node;
+  const uint32_t d = deepest_node(V, r, k0, kind, &node);
+  if (d == 0) return 0;
+  if (d == WP_KEY_BYTES && slot_has_long(node.w5) && window > static_cast<int>(WP_KEY_BYTES)) {
+    const uint32_t ref = V.long_ref[node.slot];
+    const uint32_t cnt = V.long_entries[ref];
+    for (uint32_t e = 0; e < cnt; e++) {
+      const uint32_t len = V.long_entries[ref + 1 + 3 * e];
+      if (len > static_cast<uint32_t>(window)) continue;
+      const uint8_t *tok = V.long_bytes + V.long_entries[ref + 3 + 3 * e];
+      uint32_t o = WP_KEY_BYTES;
+      while (o < len && buf[p + o] == tok[o]) o++;
+      if (o == len) {
+        *id = static_cast<int32_t>(V.long_entries[ref + 2 + 3 * e]);
+        return len;
+      }
+    }
+  }
+  if (node.term_id != WP_NO_ID) {
+    *id = node.term_id;
+    return d;
+  }
+  const uint32_t bl = slot_best_len(node.w5);
+  if (bl != 0) {
+    *id = node.best_id;
+    return bl;
+  }
+  return 0;
+}
+
+// One segment [s, e) of clean bytes in shared memory: a single
+// punctuation char, a run of ordinary chars, or a Han char followed by such a
+// run.  Writes the ids to stage[s..] and returns how many.
+__device__ __forceinline__ uint32_t match_segment_smem(const DeviceVocab &V, const uint8_t *buf, int s, int e,
+                                                       uint32_t first_class, int first_len, int32_t *stage) {
+  int32_t id = 0;
+  if (first_class == CLS_PUNCT) {  // fast.cpp:55: window of a punctuation char is 1
+    const uint32_t k = longest_match_smem(V, buf, s, first_len, WP_KIND_PREFIX, &id);
+    stage[s] = (k == static_cast<uint32_t>(first_len)) ? id : V.unk_id;
+    return 1;
+  }
+  int p = s;
+  uint32_t n = 0;           // ids written so far
+  uint32_t word_first = 0;  // index of the current word's first id (fast.cpp:53 tokens_since_prefix)
+  uint32_t kind = WP_KIND_PREFIX;
+  if (first_class == CLS_HAN) {
+    const uint32_t k = longest_match_smem(V, buf, p, e - p, WP_KIND_PREFIX, &id);
+    if (k == 0) {
+      stage[s] = V.unk_id;
+      if (V.han_swallow) return 1;  // fast.cpp:85-88: begin += word_len swallows the run
+      n = 1;
+      word_first = 1;
+      p += first_len;
+    } else {
+      stage[s] = id;
+      n = 1;
+      p += k;
+      if (k == static_cast<uint32_t>(first_len)) {
+        word_first = 1;  // fast.cpp:89-91: the next position follows a spacing char => new word
+      } else {
+        kind = WP_KIND_SUFFIX;
+      }
+    }
+  }
+  while (p < e) {
+    const uint32_t k = longest_match_smem(V, buf, p, e - p, kind, &id);
+    if (k == 0) {  // fast.cpp:79-88
+      stage[s + word_first] = V.unk_id;
+      return word_first + 1;
+    }
+    stage[s + n++] = id;
+    p += k;
+    kind = WP_KIND_SUFFIX;
+  }
+  return n;
+}
+
+// --------------------------------------------- global-memory walker (slow lane)
+// Walks ONE segment straight from the text in global memory, dropping invalid
+// bytes on the fly.  Used for the (at most one per tile) segment that does not
+// end inside the tile's window.  Single thread; two passes: count, then emit.
+
+struct TextView {
+  const uint8_t *t;
+  size_t n;
+};
+
+// Decode the char at pos; returns its length (0 = invalid byte) and class.
+__device__ uint32_t gdecode(const TextView &tv, size_t pos, uint32_t *cls) {
+  const size_t rem = tv.n - pos;
+  const uint32_t b0 = tv.t[pos];
+  if (b0 < 0x80u) {
+    *cls = cp_class(b0);
+    return 1;
+  }
+  const uint32_t b1 = rem > 1 ? tv.t[pos + 1] : 0u;
+  const uint32_t b2 = rem > 2 ? tv.t[pos + 2] : 0u;
+  const uint32_t b3 = rem > 3 ? tv.t[pos + 3] : 0u;
+  uint32_t cp = 0;
+  const uint32_t len = utf8_decode(b0, b1, b2, b3, rem > 4 ? 4u : static_cast<uint32_t>(rem), &cp);
+  if (len) *cls = cp_class(cp);
+  return len;
+}
+
+// First valid lead at or after pos (n if none); returns its length and class.
+__device__ size_t gnext(const TextView &tv, size_t pos, uint32_t *len, uint32_t *cls) {
+  while (pos < tv.n) {
+    const uint32_t l = gdecode(tv, pos, cls);
+    if (l) {
+      *len = l;
+      return pos;
+    }
+    pos++;
+  }
+  *len = 0;
+  *cls = CLS_SPACE;
+  return tv.n;
+}
+
+// Class of the last valid char that starts before pos (SPACE at the text start).
+__device__ uint32_t gprev_class(const TextView &tv, size_t pos) {
+  size_t p = pos;
+  while (p > 0) {
+    size_t q = p - 1;
+    while (q > 0 && is_cont_byte(tv.t[q])) q--;
+    if (!is_cont_byte(tv.t[q])) {
+      uint32_t cls;
+      if (gdecode(tv, q, &cls)) return cls;
+    }
+    p = q;
+  }
+  return CLS_SPACE;
+}
+
+// Longest match for the window that starts at the valid lead `p` (first char of
+// any non-space class, then ordinary chars only).
+__device__ uint32_t longest_match_global(const DeviceVocab &V, const TextView &tv, size_t p, uint32_t kind,
+                                         int32_t *id) {
+  uint8_t kb[24];
+#pragma unroll
+  for (int i = 0; i < 24; i++) kb[i] = 0;
+  uint32_t klen = 0;
+  bool more = false;
+  {
+    size_t q = p;
+    bool first = true;
+    while (q < tv.n) {
+      uint32_t len, cls;
+      q = gnext(tv, q, &len, &cls);
+      if (q >= tv.n) break;
+      if (!first && cls != CLS_OTHER) break;
+      for (uint32_t i = 0; i < len; i++) {
+        if (klen < WP_KEY_BYTES) {
+          kb[klen++] = tv.t[q + i];
+        } else {
+          more = true;
+        }
+      }
+      if (more) break;
+      if (first && cls == CLS_PUNCT) break;
+      first = false;
+      q += len;
+    }
+    if (!more && klen == WP_KEY_BYTES && q < tv.n) {
+      // exactly 22 bytes gathered: does the window go on?
+      uint32_t len, cls;
+      const size_t q2 = gnext(tv, q, &len, &cls);
+      more = q2 < tv.n && cls == CLS_OTHER;
+    }
+  }
+  uint32_t r[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+    r[i] = uint32_t(kb[4 * i]) | (uint32_t(kb[4 * i + 1]) << 8) | (uint32_t(kb[4 * i + 2]) << 16) |
+           (uint32_t(kb[4 * i + 3]) << 24);
+  NodeHit node;
+  const uint32_t d = deepest_node(V, r, klen, kind, &node);
+  if (d == 0) return 0;
+  if (d == WP_KEY_BYTES && slot_has_long(node.w5) && more) {
+    const uint32_t ref = V.long_ref[node.slot];
+    const uint32_t cnt = V.long_entries[ref];
+    for (uint32_t e = 0; e < cnt; e++) {
+      const uint32_t len = V.long_entries[ref + 1 + 3 * e];
+      const uint8_t *tok = V.long_bytes + V.long_entries[ref + 3 + 3 * e];
+      // compare clean bytes [0,len) of the window with the token
+      uint32_t o = 0;
+      size_t q = p;
+      bool ok = true, first = true;
+      while (o < len) {
+        uint32_t clen, cls;
+        q = gnext(tv, q, &clen, &cls);
+        if (q >= tv.n || (!first && cls != CLS_OTHER)) {
+          ok = false;
+          break;
+        }
+        for (uint32_t i = 0; i < clen && ok; i++) {
+          if (o >= len || tv.t[q + i] != tok[o]) ok = false;
+          o++;
+        }
+        if (!ok) break;
+        first = false;
+        q += clen;
+      }
+      if (ok && o == len) {
+        *id = static_cast<int32_t>(V.long_entries[ref + 2 + 3 * e]);
+        return len;
+      }
+    }
+  }
+  if (node.term_id != WP_NO_ID) {
+    *id = node.term_id;
+    return d;
+  }
+  const uint32_t bl = slot_best_len(node.w5);
+  if (bl != 0) {
+    *id = node.best_id;
+    return bl;
+  }
+  return 0;
+}
+
+// Walk the segment that starts at the valid, non-space lead gs.  out == nullptr:
+// count only.  Otherwise ids go to out[0..) (bounded by cap_left); ids at
+// indices >= unk_at are not written (they are rolled back, fast.cpp:80-84) and
+// the UNK id is written at unk_at.  Returns the id count; *unk_at_out = index
+// of the final UNK or -1.
+__device__ uint32_t walk_segment(const DeviceVocab &V, const TextView &tv, size_t gs, int32_t *out,
+                                 unsigned long long cap_left, int32_t unk_at, int32_t *unk_at_out) {
+  uint32_t len0, cls0;
+  gnext(tv, gs, &len0, &cls0);
+  int32_t id = 0;
+  auto emit = [&](uint32_t index, int32_t v, bool is_unk) {
+    if (out == nullptr) return;
+    if (!is_unk && unk_at >= 0 && index >= static_cast<uint32_t>(unk_at)) return;
+    if (index < cap_left) out[index] = v;
+  };
+  *unk_at_out = -1;
+  if (cls0 == CLS_PUNCT) {
+    const uint32_t k = longest_match_global(V, tv, gs, WP_KIND_PREFIX, &id);
+    if (k == len0) {
+      emit(0, id, false);
+    } else {
+      *unk_at_out = 0;
+      emit(0, V.unk_id, true);
+    }
+    return 1;
+  }
+  size_t p = gs;
+  uint32_t n = 0, word_first = 0, kind = WP_KIND_PREFIX;
+  bool at_han = (cls0 == CLS_HAN);
+  for (;;) {
+    const uint32_t k = longest_match_global(V, tv, p, kind, &id);
+    if (k == 0) {
+      if (at_han && !V.han_swallow) {
+        // max_len < 2: the Han char alone is UNK, the run after it is a new word
+        emit(n, V.unk_id, true);  // not rolled back later: word_first moves past it
+        n += 1;
+        word_first = n;
+        at_han = false;
+        uint32_t l, c;
+        p = gnext(tv, p + len0, &l, &c);
+        if (p >= tv.n || c != CLS_OTHER) return n;
+        continue;
+      }
+      *unk_at_out = static_cast<int32_t>(word_first);
+      emit(word_first, V.unk_id, true);
+      return word_first + 1;
+    }
+    emit(n, id, false);
+    n += 1;
+    // advance k clean bytes
+    uint32_t o = 0, l = 0, c = CLS_SPACE;
+    while (o < k) {
+      p = gnext(tv, p, &l, &c);
+      o += l;
+      p += l;
+    }
+    p = gnext(tv, p, &l, &c);
+    if (p >= tv.n || c != CLS_OTHER) return n;
+    if (at_han && k == len0) {
+      word_first = n;
+      kind = WP_KIND_PREFIX;
+    } else {
+      kind = WP_KIND_SUFFIX;
+    }
+    at_han = false;
+  }
+}
+
+// ------------------------------------------------------------- classification
+
+// Classify chunk c of `buf` (window coordinates) into the mask arrays.  `limit`
+// is the number of meaningful bytes in buf (positions >= limit are ignored).
+__device__ __forceinline__ void classify_chunk(TileSmem &sm, const uint8_t *buf, int c, int limit) {
+  const uint8_t *cb = buf + c * CHUNK;
+  uint32_t w[8];
+  {
+    const uint4 a = *reinterpret_cast<const uint4 *>(cb);
+    const uint4 b = *reinterpret_cast<const uint4 *>(cb + 16);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+  }
+  uint32_t lead = 0, sp = 0, pu = 0, ha = 0, cover = 0, spill = 0;
+  const uint32_t any_high = (w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) & 0x80808080u;
+  if (any_high == 0) {
+    lead = 0xFFFFFFFFu;
+    cover = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const uint32_t s = swar_range(w[i], 0x09, 0x0D) | swar_range(w[i], 0x20, 0x20);
+      const uint32_t q = swar_range(w[i], 0x21, 0x2F) | swar_range(w[i], 0x3A, 0x40) | swar_range(w[i], 0x5B, 0x60) |
+                         swar_range(w[i], 0x7B, 0x7E);
+      sp |= swar_nibble(s) << (4 * i);
+      pu |= swar_nibble(q) << (4 * i);
+    }
+  } else {
+    for (int j = 0; j < CHUNK; j++) {
+      const uint32_t b0 = cb[j];
+      if (is_cont_byte(b0)) continue;
+      uint32_t cp = 0;
+      const uint32_t len = b0 < 0x80u ? (cp = b0, 1u) : utf8_decode(b0, cb[j + 1], cb[j + 2], cb[j + 3], 4u, &cp);
+      if (len == 0) continue;
+      lead |= 1u << j;
+      const uint32_t span = (len == 1 ? 1u : (1u << len) - 1u);
+      cover |= span << j;
+      if (j + static_cast<int>(len) > CHUNK) spill = j + len - CHUNK;
+      const uint32_t cls = cp_class(cp);
+      sp |= (cls == CLS_SPACE ? 1u : 0u) << j;
+      pu |= (cls == CLS_PUNCT ? 1u : 0u) << j;
+      ha |= (cls == CLS_HAN ? 1u : 0u) << j;
+    }
+  }
+  // ignore everything at or past `limit`
+  const int left = limit - c * CHUNK;
+  const uint32_t in = left >= CHUNK ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+  sm.m_lead[c] = lead & in;
+  sm.m_space[c] = sp & in;
+  sm.m_punct[c] = pu & in;
+  sm.m_han[c] = ha & in;
+  sm.m_cover[c] = cover;
+  sm.spill[c] = static_cast<uint8_t>(spill);
+}
+
+// Position of the first spacing-char lead (space / punct / Han) at or after pos,
+// or -1 if there is none before `limit`.
+__device__ __forceinline__ int find_break(const TileSmem &sm, int pos, int limit) {
+  int c = pos >> 5;
+  const int last = (limit + CHUNK - 1) >> 5;
+  if (c >= last) return -1;
+  uint32_t m = (sm.m_space[c] | sm.m_punct[c] | sm.m_han[c]) & (0xFFFFFFFFu << (pos & 31));
+  while (m == 0) {
+    if (++c >= last) return -1;
+    m = sm.m_space[c] | sm.m_punct[c] | sm.m_han[c];
+  }
+  return c * CHUNK + __ffs(m) - 1;
+}
+
+// ------------------------------------------------------------------ the kernel
+
+__global__ void __launch_bounds__(THREADS) wp_encode_kernel(EncodeParams P) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const DeviceVocab &V = P.vocab;
+
+  // tiles are handed out in launch order so that a tile's predecessors are
+  // always already running (decoupled look-back needs forward progress)
+  if (tid == 0) {
+    sm.tile_index = atomicAdd(P.ticket, 1u);
+    sm.long_start = LONG_NONE;
+    sm.long_count = 0;
+    sm.long_unk_at = -1;
+    sm.left_spill = 0;
+  }
+  __syncthreads();
+  const uint32_t tile = sm.tile_index;
+  const size_t t0 = static_cast<size_t>(tile) * TILE;
+  const size_t n = P.n_bytes;
+  const size_t avail = n - t0;  // > 0
+  const bool more_text = avail > static_cast<size_t>(WINDOW);
+  const TextView tv{P.text, n};
+
+  // ---- S1a: stage raw bytes [t0-LEFT, t0+WINDOW+LOOKAHEAD) in shared memory
+  {
+    const bool aligned = (reinterpret_cast<uintptr_t>(P.text) & 15u) == 0;
+    for (int u = tid; u < RAW_BYTES / 16; u += THREADS) {
+      const long long g = static_cast<long long>(t0) - LEFT + 16ll * u;  // text offset of this unit
+      uint4 v;
+      if (aligned && g >= 0 && static_cast<size_t>(g) + 16 <= n) {
+        v = ldg_stream(reinterpret_cast<const uint4 *>(P.text + g));
+      } else {
+        uint32_t q[4] = {0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u};
+        for (int i = 0; i < 16; i++) {
+          const long long gi = g + i;
+          if (gi >= 0 && static_cast<size_t>(gi) < n) {
+            q[i >> 2] = (q[i >> 2] & ~(0xFFu << (8 * (i & 3)))) | (uint32_t(P.text[gi]) << (8 * (i & 3)));
+          }
+        }
+        v = make_uint4(q[0], q[1], q[2], q[3]);
+      }
+      *reinterpret_cast<uint4 *>(sm.raw + 16 * u) = v;
+    }
+    if (tid == THREADS - 1) sm.prev_class = gprev_class(tv, t0);
+  }
+  __syncthreads();
+
+  // ---- S1b: classify the window; find bytes that the strict decoder drops
+  const uint8_t *buf = sm.raw + LEFT;
+  int limit = WINDOW;
+  for (int c = tid; c < NCHUNK; c += THREADS) classify_chunk(sm, buf, c, WINDOW);
+  if (tid == THREADS - 2) {
+    // a sequence that starts in the last 3 bytes before the tile may own its first bytes
+    uint32_t ls = 0;
+    for (int j = -3; j < 0; j++) {
+      const uint32_t b0 = buf[j];
+      if (is_cont_byte(b0) || b0 < 0x80u) continue;
+      uint32_t cp;
+      const uint32_t len = utf8_decode(b0, buf[j + 1], buf[j + 2], buf[j + 3], 4u, &cp);
+      if (len && j + static_cast<int>(len) > 0) ls = j + len;
+    }
+    sm.left_spill = ls;
+  }
+  __syncthreads();
+  bool dirty_here = false;
+  for (int c = tid; c < NCHUNK; c += THREADS) {
+    const uint32_t sp_in = c == 0 ? sm.left_spill : sm.spill[c - 1];
+    const uint32_t kept = sm.m_cover[c] | ((1u << sp_in) - 1u);
+    dirty_here |= (kept != 0xFFFFFFFFu);
+  }
+  const bool dirty = __syncthreads_or(dirty_here);
+
+  if (dirty) {
+    // ---- S1c (rare): drop the invalid bytes by compacting the window in shared
+    // memory, then classify the compacted copy.  utf8.cpp:130-147.
+    // chunk NCHUNK (look-ahead) keeps only the tail of a sequence begun before it.
+    uint32_t my_cnt = 0;  // thread t scans chunks t and t+THREADS
+    uint32_t kept0 = 0, kept1 = 0;
+    {
+      const int c = tid;
+      const uint32_t sp_in = c == 0 ? sm.left_spill : sm.spill[c - 1];
+      kept0 = sm.m_cover[c] | ((1u << sp_in) - 1u);
+      my_cnt = __popc(kept0);
+      sm.m_kept[c] = kept0;
+    }
+    const int c2 = tid + THREADS;
+    if (c2 <= NCHUNK) {
+      const uint32_t sp_in = sm.spill[c2 - 1];
+      kept1 = (c2 < NCHUNK ? sm.m_cover[c2] : 0u) | ((1u << sp_in) - 1u);
+      sm.m_kept[c2] = kept1;
+    }
+    // exclusive scan over chunks 0..THREADS-1 (thread order), then the tail chunks serially
+    uint32_t incl = my_cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) sm.warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int wi = 0; wi < warp; wi++) wbase += sm.warp_sums[wi];
+    sm.kept_scan[tid] = wbase + incl - my_cnt;
+    if (tid == THREADS - 1) sm.kept_scan[THREADS] = wbase + incl;
+    __syncthreads();
+    if (tid == 0) {
+      // chunks THREADS..NCHUNK: few (HALO/32 + 1); serial
+      uint32_t run = sm.kept_scan[THREADS];
+      for (int c = THREADS; c <= NCHUNK; c++) {
+        const uint32_t sp_in = sm.spill[c - 1];
+        const uint32_t k = (c < NCHUNK ? sm.m_cover[c] : 0u) | ((1u << sp_in) - 1u);
+        sm.kept_scan[c] = run;
+        run += __popc(k);
+      }
+      sm.kept_scan[NCHUNK + 1] = run;
+    }
+    __syncthreads();
+    {
+      uint32_t dst = sm.kept_scan[tid];
+      uint32_t m = kept0;
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        sm.packed[dst++] = buf[tid * CHUNK + j];
+      }
+      if (c2 <= NCHUNK) {
+        dst = sm.kept_scan[c2];
+        m = kept1;
+        while (m) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1;
+          sm.packed[dst++] = buf[c2 * CHUNK + j];
+        }
+      }
+    }
+    const int packed_len = static_cast<int>(sm.kept_scan[NCHUNK + 1]);
+    for (int i = packed_len + tid; i < WINDOW + LOOKAHEAD + 16; i += THREADS) sm.packed[i] = 0x20;
+    __syncthreads();
+    buf = sm.packed;
+    limit = packed_len < WINDOW ? packed_len : WINDOW;
+    for (int c = tid; c < NCHUNK; c += THREADS) classify_chunk(sm, buf, c, limit);
+    __syncthreads();
+  }
+  // owned range in buffer coordinates: segments that start in [0, own_end)
+  const int own_end = dirty ? static_cast<int>(sm.kept_scan[OWNED_CHUNKS]) : TILE;
+
+  // ---- S1d: segment starts of my chunk (SURVEY A.2 safe starts)
+  uint32_t starts = 0;
+  const int c = tid;
+  const uint32_t lead = sm.m_lead[c], sp = sm.m_space[c], pu = sm.m_punct[c], ha = sm.m_han[c];
+  {
+    uint32_t carry_s, carry_p;
+    if (c == 0) {
+      carry_s = sm.prev_class == CLS_SPACE;
+      carry_p = sm.prev_class == CLS_PUNCT;
+    } else {
+      const uint32_t pl = sm.m_lead[c - 1];
+      uint32_t xs = sm.m_space[c - 1], xp = sm.m_punct[c - 1];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        xs |= (xs << 1) & ~pl;
+        xp |= (xp << 1) & ~pl;
+      }
+      carry_s = xs >> 31;
+      carry_p = xp >> 31;
+    }
+    uint32_t xs = sp | (carry_s & ~lead & 1u), xp = pu | (carry_p & ~lead & 1u);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      xs |= (xs << 1) & ~lead;
+      xp |= (xp << 1) & ~lead;
+    }
+    const uint32_t prev_s = (xs << 1) | carry_s;
+    const uint32_t prev_p = (xp << 1) | carry_p;
+    starts = lead & ~sp & (pu | ha | prev_s | prev_p);
+    const int left = own_end - c * CHUNK;
+    starts &= left >= CHUNK ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+  }
+
+  // ---- S2: match the segments that start in my chunk
+  uint32_t my_total = 0;
+  {
+    uint32_t m = starts;
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const int s = c * CHUNK + j;
+      const uint32_t bit = 1u << j;
+      const uint32_t cls = (pu & bit) ? CLS_PUNCT : ((ha & bit) ? CLS_HAN : CLS_OTHER);
+      const int first_len = static_cast<int>(utf8_lead_len(buf[s]));
+      int e;
+      if (cls == CLS_PUNCT) {
+        e = s + first_len;
+      } else {
+        e = find_break(sm, s + first_len, limit);
+        if (e < 0) {
+          if (more_text) {  // leaves the window: walked from global memory below
+            sm.long_start = s;
+            continue;
+          }
+          e = limit;
+        }
+      }
+      const uint32_t cnt = match_segment_smem(V, buf, s, e, cls, first_len, sm.stage);
+      sm.segcnt[s] = static_cast<uint16_t>(cnt);
+      my_total += cnt;
+    }
+  }
+
+  // ---- S3a: block scan of the per-thread counts
+  uint32_t incl = my_total;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  __syncthreads();  // warp_sums may have been used by the dirty path
+  if (lane == 31) sm.warp_sums[warp] = incl;
+  __syncthreads();
+  uint32_t wbase = 0, tile_normal = 0;
+  for (int wi = 0; wi < WARPS; wi++) {
+    const uint32_t ws = sm.warp_sums[wi];
+    if (wi < warp) wbase += ws;
+    tile_normal += ws;
+  }
+  const uint32_t my_off = wbase + incl - my_total;
+
+  // ---- S3b: the long segment (count pass) and the look-back across tiles
+  if (tid == 0) {
+    size_t long_gs = 0;
+    if (sm.long_start != LONG_NONE) {
+      // window position -> text position (compacted windows: undo the compaction)
+      int wpos = sm.long_start;
+      if (dirty) {
+        int cc = 0;
+        while (cc + 1 <= NCHUNK && sm.kept_scan[cc + 1] <= static_cast<uint32_t>(wpos)) cc++;
+        // position of the (k+1)-th surviving byte of raw chunk cc
+        const uint32_t k = static_cast<uint32_t>(wpos) - sm.kept_scan[cc];
+        const int pos_in = static_cast<int>(__fns(sm.m_kept[cc], 0, static_cast<int>(k) + 1));
+        wpos = cc * CHUNK + pos_in;
+      }
+      long_gs = t0 + static_cast<size_t>(wpos);
+      int32_t unk_at;
+      sm.long_count = walk_segment(V, tv, long_gs, nullptr, 0, -1, &unk_at);
+      sm.long_unk_at = unk_at;
+      atomicAdd(P.stat_long_segments, 1ull);
+    }
+    if (dirty) atomicAdd(P.stat_dirty_tiles, 1ull);
+    const unsigned long long total = static_cast<unsigned long long>(tile_normal) + sm.long_count;
+
+    // decoupled look-back: state = flag << 62 | value; flag 1 = tile aggregate, 2 = inclusive prefix
+    volatile unsigned long long *state = P.tile_state;
+    unsigned long long base = 0;
+    if (tile == 0) {
+      state[0] = (2ull << 62) | total;
+    } else {
+      state[tile] = (1ull << 62) | total;
+      __threadfence();
+      long long pred = static_cast<long long>(tile) - 1;
+      for (;;) {
+        unsigned long long sv;
+        do {
+          sv = state[pred];
+        } while ((sv >> 62) == 0);
+        base += sv & ((1ull << 62) - 1);
+        if ((sv >> 62) == 2) break;
+        pred--;
+      }
+      state[tile] = (2ull << 62) | (base + total);
+    }
+    sm.tile_base = base;
+    if (tile == P.n_tiles - 1) *P.n_ids_out = base + total;
+
+    if (sm.long_start != LONG_NONE) {
+      const unsigned long long at = base + tile_normal;
+      int32_t unk_at;
+      walk_segment(V, tv, long_gs, P.ids + at, at < P.capacity ? P.capacity - at : 0ull, sm.long_unk_at, &unk_at);
+    }
+  }
+  __syncthreads();
+
+  // ---- S3c: scatter my ids to their final positions
+  {
+    unsigned long long at = sm.tile_base + my_off;
+    uint32_t m = starts;
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const int s = c * CHUNK + j;
+      if (s == sm.long_start) continue;
+      const uint32_t cnt = sm.segcnt[s];
+      for (uint32_t i = 0; i < cnt; i++) {
+        if (at < P.capacity) P.ids[at] = sm.stage[s + i];
+        at++;
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------- launch
+
+size_t encode_smem_bytes() { return sizeof(TileSmem); }
+uint32_t encode_tile_bytes() { return TILE; }
+
+cudaError_t launch_encode(const EncodeParams &P, cudaStream_t stream) {
+  // the opt-in to > 48 KB of dynamic shared memory is per device
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    e = cudaFuncSetAttribute(wp_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(sizeof(TileSmem)));
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  wp_encode_kernel<<<P.n_tiles, THREADS, sizeof(TileSmem), stream>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace wp
