@@ -1,0 +1,194 @@
+"""CPU tests of the product's host side: the C ABI surface, the vocabulary builder and its
+table image (through the host mirror of the device probe), decode, the synthetic corpora
+and the sharding plan.  No encode call is made here — that needs a GPU (tests -m gpu)."""
+from __future__ import annotations
+
+import ctypes
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+import cases
+import textgen
+from _model import model_encode
+from _oracle import EmptyVocabWord, Oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import wordpiece_b200
+    from wordpiece_b200._capi import EXPORTED_SYMBOLS
+
+    header = open(os.path.join(ROOT, "include", "wordpiece_b200.h")).read()
+    declared = set(re.findall(r"\b(wp_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(EXPORTED_SYMBOLS), declared ^ set(EXPORTED_SYMBOLS)
+    lib = wordpiece_b200.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_cpp_entry_points_are_exported():
+    """The reference's C++ signatures (src/word_piece.hpp:25-34) exist in the shared library."""
+    import subprocess
+
+    out = subprocess.check_output(["nm", "-DC", "--defined-only", os.path.join(ROOT, "wordpiece_b200", "lib",
+                                                                              "libwordpiece_b200.so")], text=True)
+    for sig in ("word_piece::fast::encode(std::__cxx11::basic_string", "word_piece::fast::decode(",
+                "word_piece::fast::encodeExternal(", "utils::writeToFile(", "utils::globalThreadPool("):
+        assert sig in out, sig
+
+
+def test_no_device_fails_loudly():
+    """Without a CUDA device (this container) creation on device 0 must fail — never fall back to a CPU path."""
+    import torch
+
+    import wordpiece_b200
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(wordpiece_b200.WordPieceError) as ei:
+        wordpiece_b200.Vocab(["a", "[UNK]"], device=0)
+    assert ei.value.status == 4
+    v = wordpiece_b200.Vocab(["a", "[UNK]"], device=-1)
+    with pytest.raises(wordpiece_b200.WordPieceError) as ei:
+        v.encode(b"a")
+    assert ei.value.status == 4 and "no CPU path" in str(ei.value)
+
+
+def test_vocab_builder_matches_oracle_classification():
+    from wordpiece_b200 import Vocab, WordPieceError
+
+    rng = random.Random(7)
+    for _ in range(400):
+        _, vocab = cases.fuzz_case(rng)
+        try:
+            o = Oracle(vocab)
+        except EmptyVocabWord:
+            with pytest.raises(WordPieceError) as ei:
+                Vocab(vocab, device=-1)
+            assert ei.value.status == 2 and str(ei.value) == "Vocab word is empty"
+            continue
+        v = Vocab(vocab, device=-1)
+        assert (v.unk_id, v.max_len, len(v)) == (o.unk_id, o.max_len, len(vocab))
+        for i in range(len(vocab)):
+            assert (v.token_flags(i) & 7) == o.token_flags(i)
+
+
+def test_table_image_against_oracle_through_the_model():
+    """The byte-domain plan of the kernel (tests/_model.py) over the table image == oracle."""
+    from wordpiece_b200 import Vocab
+
+    for text, vocab, expected in cases.REFERENCE_GOLDEN:
+        assert model_encode(Vocab(vocab, device=-1), text.encode()) == expected
+    for name, text, vocab in cases.QUIRKS:
+        assert model_encode(Vocab(vocab, device=-1), text) == Oracle(vocab).encode(text).tolist(), name
+    rng = random.Random(31)
+    for _ in range(3000):
+        text, vocab = cases.fuzz_case(rng)
+        try:
+            o = Oracle(vocab)
+        except EmptyVocabWord:
+            continue
+        assert model_encode(Vocab(vocab, device=-1), text) == o.encode(text).tolist(), (text, vocab)
+    for i in range(60):  # long tokens (> 22 bytes) hang off depth-22 nodes
+        s, vocab = cases.random_split_case(rng, rng.randint(40, 600), rng.randint(2, 14), i % 3 != 0)
+        v = Vocab(vocab, device=-1)
+        assert model_encode(v, s.encode()) == Oracle(vocab).encode(s).tolist()
+    text, vocab = textgen.case(3, 20000, long_run_rate=0.05, long_tokens=20)
+    v = Vocab(vocab, device=-1)
+    assert v.table_info["long_tokens"] >= 20
+    assert model_encode(v, text) == Oracle(vocab).encode(text).tolist()
+
+
+def test_table_image_shape():
+    from wordpiece_b200 import Vocab
+
+    v = Vocab(["ab", "abc", "##abc", "b", "[UNK]", "x" * 30, "x" * 40, "x" * 30], device=-1)
+    info = v.table_info
+    assert info["slots"] >= 2 * info["nodes"] and info["slots"] & (info["slots"] - 1) == 0
+    assert info["long_tokens"] == 2  # the duplicate long token is stored once
+    assert v.debug_longest_match(b"abcd", 0) == (3, 1)
+    assert v.debug_longest_match(b"abcd", 1) == (3, 2)
+    assert v.debug_longest_match(b"ab", 0) == (2, 0)
+    assert v.debug_longest_match(b"a", 0) == (0, -2)
+    assert v.debug_longest_match(b"x" * 50, 0) == (40, 6)
+    assert v.debug_longest_match(b"x" * 39, 0) == (30, 7)  # last duplicate wins
+    assert v.debug_longest_match(b"x" * 29, 0) == (0, -2)
+
+
+def test_decode_matches_reference_rules(tmp_path):
+    """fast.cpp:165-187."""
+    import wordpiece_b200
+
+    vocab = ["[PAD]", "a", "##b", "--", "[UNK]", "中", "##かな"]
+    v = wordpiece_b200.Vocab(vocab, device=-1)
+    assert v.decode([1, 2, 5, 6, 0, 4]) == [b"a", b"##b", "中".encode(), "##かな".encode(), b"[PAD]", b"[UNK]"]
+    assert v.decode([-1, 1, 3, 8, 2]) == [b"a", b"##b"]  # negative, malformed and > size are skipped
+    with pytest.raises(wordpiece_b200.WordPieceError) as ei:
+        v.decode([7])  # id == size: the reference's .at() throws
+    assert ei.value.status == 8
+    p = tmp_path / "vocab.txt"
+    p.write_bytes(b"\n".join(t.encode() for t in vocab) + b"\n")
+    assert wordpiece_b200.decode(str(p), [1, 2]) == [b"a", b"##b"]
+
+
+def test_vocab_file_reader_semantics(tmp_path):
+    """utils.cpp:123-137: getline — '\\r' stays, blank line throws, last line need not end in '\\n'."""
+    import wordpiece_b200
+
+    p = tmp_path / "v.txt"
+    p.write_bytes(b"a\r\n[UNK]\nb")
+    v = wordpiece_b200.Vocab.from_file(str(p), device=-1)
+    assert len(v) == 3 and v.unk_id == 1
+    assert v.decode([0, 2]) == [b"a\r", b"b"]
+    p.write_bytes(b"a\n\nb\n")
+    with pytest.raises(wordpiece_b200.WordPieceError) as ei:
+        wordpiece_b200.Vocab.from_file(str(p), device=-1)
+    assert ei.value.status == 2
+    with pytest.raises(wordpiece_b200.WordPieceError) as ei:
+        wordpiece_b200.Vocab.from_file(str(tmp_path / "missing.txt"), device=-1)
+    assert ei.value.status == 6
+
+
+def test_synthetic_corpus_is_deterministic_and_shardable():
+    from wordpiece_b200 import synth
+
+    g = synth.generator("en")
+    whole = g.generate(3 * synth.BLOCK + 12345, seed=4, n_threads=3)
+    again = g.generate(3 * synth.BLOCK + 12345, seed=4, n_threads=1)
+    assert np.array_equal(whole, again)
+    part = g.generate(synth.BLOCK + 12345, seed=4, first_block=2)
+    assert np.array_equal(whole[2 * synth.BLOCK:], part)
+    assert not np.array_equal(whole[:1000], g.generate(1000, seed=5))
+    vocab = g.spec.vocab
+    assert len(vocab) == 28996 and len(set(vocab)) == 28996 and vocab[100] == b"[UNK]"
+    o = Oracle(vocab)
+    ids = o.encode(whole[: 1 << 20])
+    ratio = ids.size / (1 << 20)
+    assert 0.2 < ratio < 0.35, ratio
+    assert 0.002 < float((ids == o.unk_id).mean()) < 0.05
+
+
+def test_shard_plan_preserves_ids():
+    """Cuts after a space leave the concatenated ids unchanged (fast.cpp:113-115)."""
+    from wordpiece_b200.sharding import global_offsets, plan_shards
+
+    for seed, kw in ((51, {}), (52, dict(invalid_rate=0.02)), (53, dict(long_run_rate=0.05, long_tokens=10))):
+        text, vocab = textgen.case(seed, 70000, **kw)
+        o = Oracle(vocab)
+        whole = o.encode(text)
+        arr = np.frombuffer(text, dtype=np.uint8)
+        for n_shards in (2, 3, 8):
+            plan = plan_shards(arr, n_shards)
+            assert plan[0][0] == 0 and plan[-1][1] == arr.size
+            assert all(plan[i][1] == plan[i + 1][0] for i in range(n_shards - 1))
+            parts = [o.encode(text[a:b]) for a, b in plan]
+            offs = global_offsets([p.size for p in parts])
+            out = np.empty(sum(p.size for p in parts), np.int32)
+            for off, p in zip(offs, parts):
+                out[off:off + p.size] = p
+            assert np.array_equal(out, whole), (seed, n_shards)
