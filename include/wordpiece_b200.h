@@ -101,7 +101,7 @@ wp_status wp_encode_into(wp_vocab *v, const char *text, size_t n_bytes, int32_t 
                          size_t *n_ids);
 
 /* Device text -> device ids, both resident on the handle's device.  Enqueues
- * the kernels on `stream` (a cudaStream_t; NULL = the handle's own stream),
+ * the kernels on `stream` (a cudaStream_t; NULL = the CUDA default stream),
  * then synchronises that stream to return the count.  At most `capacity` ids
  * are written; if more were produced the status is WP_ERR_CAPACITY and *n_ids
  * is the count needed (n_bytes ids always suffice). */

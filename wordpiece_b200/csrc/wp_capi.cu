@@ -282,7 +282,7 @@ wp_status wp_encode_device_async(wp_vocab *v, const void *d_text, size_t n_bytes
     return fail(WP_ERR_INVALID_ARG, "null argument");
   if (v->device < 0) return fail(WP_ERR_NO_DEVICE, kHostOnly);
   DeviceGuard g(v->device);
-  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : v->stream;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);  // NULL = the default stream, as everywhere in CUDA
   if (n_bytes == 0) {  // fast.cpp:145
     if (d_n_ids) WP_CUDA(cudaMemsetAsync(d_n_ids, 0, sizeof(uint64_t), s));
     return WP_OK;
@@ -304,7 +304,7 @@ wp_status wp_encode_device(wp_vocab *v, const void *d_text, size_t n_bytes, int3
   *n_ids = 0;
   if (v->device < 0) return fail(WP_ERR_NO_DEVICE, kHostOnly);
   DeviceGuard g(v->device);
-  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : v->stream;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);  // NULL = the default stream, as everywhere in CUDA
   if (n_bytes == 0) {
     v->stats = wp_stats{};
     return WP_OK;

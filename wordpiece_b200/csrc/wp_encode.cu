@@ -17,12 +17,16 @@
 //                (valid lead / space / punct / Han), tiles holding invalid UTF-8
 //                are compacted in shared memory, and segment starts ("safe
 //                starts") fall out of a few mask operations.
-//   S2 match   : the thread that owns a chunk runs the greedy matcher over the
-//                segments that start in it, probing the hashed-trie table
-//                (wp_table.h): whole window first, then binary search.
-//   S3 scatter : per-thread token counts -> block scan -> decoupled look-back
-//                across tiles -> ids copied from the shared staging area to
-//                their final positions.
+//   S2 match   : segment starts are compacted into a list; every lane pulls
+//                segments from it and runs the greedy matcher as a FLATTENED
+//                state machine — one table probe per loop iteration, whatever
+//                the lane is doing (first whole-window probe, binary-search
+//                step, next piece, collision) — so a warp stays converged on
+//                the probe.  Table: hashed trie of wp_table.h.
+//   S3 scatter : per-segment id counts -> warp/block scan -> decoupled
+//                look-back across tiles -> ids copied from the shared staging
+//                area to their final positions, one segment per lane so that a
+//                warp's stores land in a few adjacent sectors.
 //   A segment that does not end inside the tile's window (at most one per tile)
 //   is walked straight from global memory by one thread (count, then emit).
 #include <cuda_runtime.h>
@@ -35,8 +39,8 @@ namespace wp {
 
 // ------------------------------------------------------------------ geometry
 constexpr int TILE = 8192;                       // text bytes owned by one CTA
-constexpr int CHUNK = 32;                        // bytes classified by one thread at a time
-constexpr int THREADS = TILE / CHUNK;            // 256
+constexpr int CHUNK = 32;                        // bytes classified by one thread
+constexpr int THREADS = 512;                     // 16 warps; 2 CTAs per SM
 constexpr int HALO = 256;                        // classified bytes past the tile (segment completion)
 constexpr int LOOKAHEAD = 32;                    // loaded, not classified (UTF-8 validation look-ahead)
 constexpr int LEFT = 16;                         // bytes before the tile (ownership of leading continuation bytes)
@@ -46,15 +50,17 @@ constexpr int OWNED_CHUNKS = TILE / CHUNK;       // 256
 constexpr int RAW_BYTES = LEFT + WINDOW + LOOKAHEAD;  // 8496
 constexpr int WARPS = THREADS / 32;
 constexpr int32_t LONG_NONE = -1;
+constexpr uint32_t FULL = 0xFFFFFFFFu;
 
 static_assert(RAW_BYTES % 16 == 0, "raw buffer is loaded in 16-byte units");
 static_assert(WP_KEY_BYTES + 4 <= LOOKAHEAD, "key window reads stay inside the loaded bytes");
+static_assert(NCHUNK + 1 <= THREADS, "one thread per chunk in the compaction pass");
 
 struct __align__(16) TileSmem {
   uint8_t raw[RAW_BYTES];              // [0,LEFT) left halo, then the window, then look-ahead
-  uint8_t packed[WINDOW + LOOKAHEAD + 16];  // compacted copy (only for tiles with invalid UTF-8)
-  int32_t stage[WINDOW + 8];           // ids of a segment starting at byte s live at stage[s..s+cnt)
-  uint16_t segcnt[TILE];               // token count of the segment starting at byte s
+  int32_t stage[WINDOW + 8];           // ids of the segment starting at byte s live at stage[s..s+cnt)
+  uint16_t seg_start[TILE];            // window position of owned segment k (text order)
+  uint16_t seg_cnt[TILE];              // id count of owned segment k
   uint32_t m_lead[NCHUNK + 1];         // valid lead bytes
   uint32_t m_space[NCHUNK + 1];
   uint32_t m_punct[NCHUNK + 1];
@@ -64,9 +70,12 @@ struct __align__(16) TileSmem {
   uint32_t kept_scan[NCHUNK + 2];      // exclusive scan of kept bytes per chunk (dirty tiles)
   uint8_t spill[NCHUNK + 1];           // bytes by which the chunk's last sequence runs into the next chunk
   uint32_t warp_sums[WARPS];
+  uint32_t warp_tot[WARPS];
   uint32_t tile_index;
   uint32_t prev_class;                 // class of the last valid char before the tile
   uint32_t left_spill;                 // bytes of the tile start covered by a sequence that began before it
+  uint32_t n_segs;                     // owned segments in this tile
+  uint32_t next_seg;                   // work dispenser of the match loop
   int32_t long_start;                  // window position of the segment that leaves the window, or LONG_NONE
   uint32_t long_count;
   int32_t long_unk_at;
@@ -159,99 +168,6 @@ __device__ __forceinline__ uint32_t deepest_node(const DeviceVocab &V, const uin
     }
   }
   return lo;
-}
-
-// ------------------------------------------------- longest match, shared memory
-
-// Longest token of `kind` that is a prefix of buf[p, p+window).  Bytes are clean
-// (valid UTF-8, nothing to drop) and at least 28 bytes past p are readable.
-__device__ __forceinline__ uint32_t longest_match_smem(const DeviceVocab &V, const uint8_t *buf, int p, int window,
-                                                       uint32_t kind, int32_t *id) {
-  const int a = p & ~3;
-  const uint32_t sh = (p & 3) * 8;
-  uint32_t x[7];
-#pragma unroll
-  for (int i = 0; i < 7; i++) x[i] = ld_u32(buf + a + 4 * i);
-  uint32_t r[6];
-#pragma unroll
-  for (int i = 0; i < 6; i++) r[i] = __funnelshift_r(x[i], x[i + 1], sh);
-
-  const uint32_t k0 = window < static_cast<int>(WP_KEY_BYTES) ? window : WP_KEY_BYTES;
-  NodeHit node;
-  const uint32_t d = deepest_node(V, r, k0, kind, &node);
-  if (d == 0) return 0;
-  if (d == WP_KEY_BYTES && slot_has_long(node.w5) && window > static_cast<int>(WP_KEY_BYTES)) {
-    const uint32_t ref = V.long_ref[node.slot];
-    const uint32_t cnt = V.long_entries[ref];
-    for (uint32_t e = 0; e < cnt; e++) {
-      const uint32_t len = V.long_entries[ref + 1 + 3 * e];
-      if (len > static_cast<uint32_t>(window)) continue;
-      const uint8_t *tok = V.long_bytes + V.long_entries[ref + 3 + 3 * e];
-      uint32_t o = WP_KEY_BYTES;
-      while (o < len && buf[p + o] == tok[o]) o++;
-      if (o == len) {
-        *id = static_cast<int32_t>(V.long_entries[ref + 2 + 3 * e]);
-        return len;
-      }
-    }
-  }
-  if (node.term_id != WP_NO_ID) {
-    *id = node.term_id;
-    return d;
-  }
-  const uint32_t bl = slot_best_len(node.w5);
-  if (bl != 0) {
-    *id = node.best_id;
-    return bl;
-  }
-  return 0;
-}
-
-// One segment [s, e) of clean bytes in shared memory: a single
-// punctuation char, a run of ordinary chars, or a Han char followed by such a
-// run.  Writes the ids to stage[s..] and returns how many.
-__device__ __forceinline__ uint32_t match_segment_smem(const DeviceVocab &V, const uint8_t *buf, int s, int e,
-                                                       uint32_t first_class, int first_len, int32_t *stage) {
-  int32_t id = 0;
-  if (first_class == CLS_PUNCT) {  // fast.cpp:55: window of a punctuation char is 1
-    const uint32_t k = longest_match_smem(V, buf, s, first_len, WP_KIND_PREFIX, &id);
-    stage[s] = (k == static_cast<uint32_t>(first_len)) ? id : V.unk_id;
-    return 1;
-  }
-  int p = s;
-  uint32_t n = 0;           // ids written so far
-  uint32_t word_first = 0;  // index of the current word's first id (fast.cpp:53 tokens_since_prefix)
-  uint32_t kind = WP_KIND_PREFIX;
-  if (first_class == CLS_HAN) {
-    const uint32_t k = longest_match_smem(V, buf, p, e - p, WP_KIND_PREFIX, &id);
-    if (k == 0) {
-      stage[s] = V.unk_id;
-      if (V.han_swallow) return 1;  // fast.cpp:85-88: begin += word_len swallows the run
-      n = 1;
-      word_first = 1;
-      p += first_len;
-    } else {
-      stage[s] = id;
-      n = 1;
-      p += k;
-      if (k == static_cast<uint32_t>(first_len)) {
-        word_first = 1;  // fast.cpp:89-91: the next position follows a spacing char => new word
-      } else {
-        kind = WP_KIND_SUFFIX;
-      }
-    }
-  }
-  while (p < e) {
-    const uint32_t k = longest_match_smem(V, buf, p, e - p, kind, &id);
-    if (k == 0) {  // fast.cpp:79-88
-      stage[s + word_first] = V.unk_id;
-      return word_first + 1;
-    }
-    stage[s + n++] = id;
-    p += k;
-    kind = WP_KIND_SUFFIX;
-  }
-  return n;
 }
 
 // --------------------------------------------- global-memory walker (slow lane)
@@ -534,9 +450,36 @@ __device__ __forceinline__ int find_break(const TileSmem &sm, int pos, int limit
   return c * CHUNK + __ffs(m) - 1;
 }
 
+// block-wide exclusive scan of one value per thread; returns the exclusive prefix, *total = sum
+__device__ __forceinline__ uint32_t block_exclusive_scan(TileSmem &sm, uint32_t v, uint32_t *total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += y;
+  }
+  __syncthreads();  // warp_sums may still be in use by an earlier scan
+  if (lane == 31) sm.warp_sums[warp] = incl;
+  __syncthreads();
+  uint32_t wbase = 0, tot = 0;
+#pragma unroll
+  for (int wi = 0; wi < WARPS; wi++) {
+    const uint32_t ws = sm.warp_sums[wi];
+    if (wi < warp) wbase += ws;
+    tot += ws;
+  }
+  *total = tot;
+  return wbase + incl - v;
+}
+
 // ------------------------------------------------------------------ the kernel
 
-__global__ void __launch_bounds__(THREADS) wp_encode_kernel(EncodeParams P) {
+// flags of a segment being matched
+constexpr uint32_t SEG_PUNCT = 1u;      // single punctuation char (window 1, fast.cpp:55)
+constexpr uint32_t SEG_HAN_FIRST = 2u;  // about to match the first piece of a Han-led segment
+
+__global__ void __launch_bounds__(THREADS, 2) wp_encode_kernel(EncodeParams P) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
   const int tid = threadIdx.x;
@@ -552,6 +495,7 @@ __global__ void __launch_bounds__(THREADS) wp_encode_kernel(EncodeParams P) {
     sm.long_count = 0;
     sm.long_unk_at = -1;
     sm.left_spill = 0;
+    sm.next_seg = 0;
   }
   __syncthreads();
   const uint32_t tile = sm.tile_index;
@@ -586,9 +530,9 @@ __global__ void __launch_bounds__(THREADS) wp_encode_kernel(EncodeParams P) {
   __syncthreads();
 
   // ---- S1b: classify the window; find bytes that the strict decoder drops
-  const uint8_t *buf = sm.raw + LEFT;
+  uint8_t *const buf = sm.raw + LEFT;
   int limit = WINDOW;
-  for (int c = tid; c < NCHUNK; c += THREADS) classify_chunk(sm, buf, c, WINDOW);
+  if (tid < NCHUNK) classify_chunk(sm, buf, tid, WINDOW);
   if (tid == THREADS - 2) {
     // a sequence that starts in the last 3 bytes before the tile may own its first bytes
     uint32_t ls = 0;
@@ -602,235 +546,383 @@ __global__ void __launch_bounds__(THREADS) wp_encode_kernel(EncodeParams P) {
     sm.left_spill = ls;
   }
   __syncthreads();
-  bool dirty_here = false;
-  for (int c = tid; c < NCHUNK; c += THREADS) {
-    const uint32_t sp_in = c == 0 ? sm.left_spill : sm.spill[c - 1];
-    const uint32_t kept = sm.m_cover[c] | ((1u << sp_in) - 1u);
-    dirty_here |= (kept != 0xFFFFFFFFu);
+  uint32_t kept = 0xFFFFFFFFu;  // surviving bytes of chunk `tid` (chunk NCHUNK = look-ahead: only a spilled tail)
+  if (tid <= NCHUNK) {
+    const uint32_t sp_in = tid == 0 ? sm.left_spill : sm.spill[tid - 1];
+    kept = (tid < NCHUNK ? sm.m_cover[tid] : 0u) | ((1u << sp_in) - 1u);
   }
-  const bool dirty = __syncthreads_or(dirty_here);
+  const bool dirty = __syncthreads_or(tid < NCHUNK && kept != 0xFFFFFFFFu);
 
   if (dirty) {
-    // ---- S1c (rare): drop the invalid bytes by compacting the window in shared
-    // memory, then classify the compacted copy.  utf8.cpp:130-147.
-    // chunk NCHUNK (look-ahead) keeps only the tail of a sequence begun before it.
-    uint32_t my_cnt = 0;  // thread t scans chunks t and t+THREADS
-    uint32_t kept0 = 0, kept1 = 0;
-    {
-      const int c = tid;
-      const uint32_t sp_in = c == 0 ? sm.left_spill : sm.spill[c - 1];
-      kept0 = sm.m_cover[c] | ((1u << sp_in) - 1u);
-      my_cnt = __popc(kept0);
-      sm.m_kept[c] = kept0;
+    // ---- S1c (rare): drop the invalid bytes by compacting the window IN PLACE
+    // (every thread first pulls its chunk into registers), then classify again.
+    // utf8.cpp:130-147.
+    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t my_cnt = 0;
+    if (tid <= NCHUNK) {
+      const uint4 a = *reinterpret_cast<const uint4 *>(buf + tid * CHUNK);
+      const uint4 b = *reinterpret_cast<const uint4 *>(buf + tid * CHUNK + 16);
+      w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+      w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+      my_cnt = __popc(kept);
+      sm.m_kept[tid] = kept;
     }
-    const int c2 = tid + THREADS;
-    if (c2 <= NCHUNK) {
-      const uint32_t sp_in = sm.spill[c2 - 1];
-      kept1 = (c2 < NCHUNK ? sm.m_cover[c2] : 0u) | ((1u << sp_in) - 1u);
-      sm.m_kept[c2] = kept1;
-    }
-    // exclusive scan over chunks 0..THREADS-1 (thread order), then the tail chunks serially
-    uint32_t incl = my_cnt;
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if (lane >= o) incl += y;
-    }
-    if (lane == 31) sm.warp_sums[warp] = incl;
-    __syncthreads();
-    uint32_t wbase = 0;
-    for (int wi = 0; wi < warp; wi++) wbase += sm.warp_sums[wi];
-    sm.kept_scan[tid] = wbase + incl - my_cnt;
-    if (tid == THREADS - 1) sm.kept_scan[THREADS] = wbase + incl;
-    __syncthreads();
-    if (tid == 0) {
-      // chunks THREADS..NCHUNK: few (HALO/32 + 1); serial
-      uint32_t run = sm.kept_scan[THREADS];
-      for (int c = THREADS; c <= NCHUNK; c++) {
-        const uint32_t sp_in = sm.spill[c - 1];
-        const uint32_t k = (c < NCHUNK ? sm.m_cover[c] : 0u) | ((1u << sp_in) - 1u);
-        sm.kept_scan[c] = run;
-        run += __popc(k);
-      }
-      sm.kept_scan[NCHUNK + 1] = run;
-    }
-    __syncthreads();
-    {
-      uint32_t dst = sm.kept_scan[tid];
-      uint32_t m = kept0;
+    uint32_t packed_len;
+    const uint32_t dst0 = block_exclusive_scan(sm, my_cnt, &packed_len);  // syncs: all chunks are in registers now
+    if (tid <= NCHUNK) {
+      sm.kept_scan[tid] = dst0;
+      if (tid == NCHUNK) sm.kept_scan[NCHUNK + 1] = packed_len;
+      uint32_t dst = dst0, m = kept;
       while (m) {
         const int j = __ffs(m) - 1;
         m &= m - 1;
-        sm.packed[dst++] = buf[tid * CHUNK + j];
-      }
-      if (c2 <= NCHUNK) {
-        dst = sm.kept_scan[c2];
-        m = kept1;
-        while (m) {
-          const int j = __ffs(m) - 1;
-          m &= m - 1;
-          sm.packed[dst++] = buf[c2 * CHUNK + j];
-        }
+        buf[dst++] = static_cast<uint8_t>(w[j >> 2] >> (8 * (j & 3)));
       }
     }
-    const int packed_len = static_cast<int>(sm.kept_scan[NCHUNK + 1]);
-    for (int i = packed_len + tid; i < WINDOW + LOOKAHEAD + 16; i += THREADS) sm.packed[i] = 0x20;
     __syncthreads();
-    buf = sm.packed;
-    limit = packed_len < WINDOW ? packed_len : WINDOW;
-    for (int c = tid; c < NCHUNK; c += THREADS) classify_chunk(sm, buf, c, limit);
+    for (int i = static_cast<int>(packed_len) + tid; i < WINDOW + LOOKAHEAD; i += THREADS) buf[i] = 0x20;
+    __syncthreads();
+    limit = static_cast<int>(packed_len) < WINDOW ? static_cast<int>(packed_len) : WINDOW;
+    if (tid < NCHUNK) classify_chunk(sm, buf, tid, limit);
     __syncthreads();
   }
   // owned range in buffer coordinates: segments that start in [0, own_end)
   const int own_end = dirty ? static_cast<int>(sm.kept_scan[OWNED_CHUNKS]) : TILE;
 
-  // ---- S1d: segment starts of my chunk (SURVEY A.2 safe starts)
-  uint32_t starts = 0;
-  const int c = tid;
-  const uint32_t lead = sm.m_lead[c], sp = sm.m_space[c], pu = sm.m_punct[c], ha = sm.m_han[c];
+  // ---- S1d: segment starts of my chunk (SURVEY A.2 safe starts), compacted into seg_start[]
   {
-    uint32_t carry_s, carry_p;
-    if (c == 0) {
-      carry_s = sm.prev_class == CLS_SPACE;
-      carry_p = sm.prev_class == CLS_PUNCT;
-    } else {
-      const uint32_t pl = sm.m_lead[c - 1];
-      uint32_t xs = sm.m_space[c - 1], xp = sm.m_punct[c - 1];
+    uint32_t starts = 0;
+    const int c = tid;
+    if (c < OWNED_CHUNKS) {
+      const uint32_t lead = sm.m_lead[c], sp = sm.m_space[c], pu = sm.m_punct[c], ha = sm.m_han[c];
+      uint32_t carry_s, carry_p;
+      if (c == 0) {
+        carry_s = sm.prev_class == CLS_SPACE;
+        carry_p = sm.prev_class == CLS_PUNCT;
+      } else {
+        const uint32_t pl = sm.m_lead[c - 1];
+        uint32_t xs = sm.m_space[c - 1], xp = sm.m_punct[c - 1];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          xs |= (xs << 1) & ~pl;
+          xp |= (xp << 1) & ~pl;
+        }
+        carry_s = xs >> 31;
+        carry_p = xp >> 31;
+      }
+      uint32_t xs = sp | (carry_s & ~lead & 1u), xp = pu | (carry_p & ~lead & 1u);
 #pragma unroll
       for (int i = 0; i < 3; i++) {
-        xs |= (xs << 1) & ~pl;
-        xp |= (xp << 1) & ~pl;
+        xs |= (xs << 1) & ~lead;
+        xp |= (xp << 1) & ~lead;
       }
-      carry_s = xs >> 31;
-      carry_p = xp >> 31;
+      const uint32_t prev_s = (xs << 1) | carry_s;
+      const uint32_t prev_p = (xp << 1) | carry_p;
+      starts = lead & ~sp & (pu | ha | prev_s | prev_p);
+      const int left = own_end - c * CHUNK;
+      starts &= left >= CHUNK ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
     }
-    uint32_t xs = sp | (carry_s & ~lead & 1u), xp = pu | (carry_p & ~lead & 1u);
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      xs |= (xs << 1) & ~lead;
-      xp |= (xp << 1) & ~lead;
+    uint32_t n_segs;
+    uint32_t at = block_exclusive_scan(sm, __popc(starts), &n_segs);
+    while (starts) {
+      const int j = __ffs(starts) - 1;
+      starts &= starts - 1;
+      sm.seg_start[at++] = static_cast<uint16_t>(c * CHUNK + j);
     }
-    const uint32_t prev_s = (xs << 1) | carry_s;
-    const uint32_t prev_p = (xp << 1) | carry_p;
-    starts = lead & ~sp & (pu | ha | prev_s | prev_p);
-    const int left = own_end - c * CHUNK;
-    starts &= left >= CHUNK ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+    if (tid == 0) sm.n_segs = n_segs;
   }
+  __syncthreads();
+  const uint32_t n_segs = sm.n_segs;
 
-  // ---- S2: match the segments that start in my chunk
-  uint32_t my_total = 0;
+  // ---- S2: match.  Flattened state machine: every iteration each active lane
+  // issues exactly ONE table probe for its current (piece start p, length k).
   {
-    uint32_t m = starts;
-    while (m) {
-      const int j = __ffs(m) - 1;
-      m &= m - 1;
-      const int s = c * CHUNK + j;
-      const uint32_t bit = 1u << j;
-      const uint32_t cls = (pu & bit) ? CLS_PUNCT : ((ha & bit) ? CLS_HAN : CLS_OTHER);
-      const int first_len = static_cast<int>(utf8_lead_len(buf[s]));
-      int e;
-      if (cls == CLS_PUNCT) {
-        e = s + first_len;
-      } else {
-        e = find_break(sm, s + first_len, limit);
-        if (e < 0) {
-          if (more_text) {  // leaves the window: walked from global memory below
-            sm.long_start = s;
-            continue;
+    bool active = false, exhausted = false, reload = false;
+    int s = 0, e = 0, p = 0;
+    uint32_t q = 0, nid = 0, word_first = 0, kind = WP_KIND_PREFIX, flags = 0, first_len = 0;
+    uint32_t k = 0, lo = 0, hi = 0, poff = 0;
+    uint32_t r[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t node_w5 = 0, node_slot = 0;
+    int32_t node_term = WP_NO_ID, node_best = WP_NO_ID;
+    const uint4 *tab = reinterpret_cast<const uint4 *>(V.slots);
+
+    for (;;) {
+      // -- refill idle lanes from the segment list (one shared-memory atomic per warp)
+      const bool need = !active && !exhausted;
+      const uint32_t needm = __ballot_sync(FULL, need);
+      if (needm) {
+        uint32_t base = 0;
+        const int leader = __ffs(needm) - 1;
+        if (lane == leader) base = atomicAdd(&sm.next_seg, static_cast<uint32_t>(__popc(needm)));
+        base = __shfl_sync(FULL, base, leader);
+        if (need) {
+          q = base + __popc(needm & ((1u << lane) - 1u));
+          if (q >= n_segs) {
+            exhausted = true;
+          } else {
+            s = sm.seg_start[q];
+            const uint32_t bit = 1u << (s & 31);
+            const uint32_t cls = (sm.m_punct[s >> 5] & bit) ? CLS_PUNCT : ((sm.m_han[s >> 5] & bit) ? CLS_HAN : CLS_OTHER);
+            first_len = utf8_lead_len(buf[s]);
+            bool ok = true;
+            if (cls == CLS_PUNCT) {
+              e = s + static_cast<int>(first_len);
+            } else {
+              e = find_break(sm, s + static_cast<int>(first_len), limit);
+              if (e < 0) {
+                if (more_text) {  // leaves the window: walked from global memory by thread 0 below
+                  sm.long_start = s;
+                  sm.seg_cnt[q] = 0;
+                  ok = false;
+                } else {
+                  e = limit;
+                }
+              }
+            }
+            if (ok) {
+              active = true;
+              p = s;
+              nid = 0;
+              word_first = 0;
+              kind = WP_KIND_PREFIX;
+              flags = cls == CLS_PUNCT ? SEG_PUNCT : (cls == CLS_HAN ? SEG_HAN_FIRST : 0u);
+              const uint32_t wlen = static_cast<uint32_t>(e - p);
+              k = wlen < WP_KEY_BYTES ? wlen : WP_KEY_BYTES;
+              lo = 0;
+              hi = k + 1;
+              poff = 0;
+              reload = true;
+            }
           }
-          e = limit;
         }
       }
-      const uint32_t cnt = match_segment_smem(V, buf, s, e, cls, first_len, sm.stage);
-      sm.segcnt[s] = static_cast<uint16_t>(cnt);
-      my_total += cnt;
+      if (!__any_sync(FULL, active || !exhausted)) break;
+      if (!active) continue;
+
+      // -- one probe
+      if (reload) {
+        const int a = p & ~3;
+        const uint32_t sh = (p & 3) * 8;
+        uint32_t x[7];
+#pragma unroll
+        for (int i = 0; i < 7; i++) x[i] = ld_u32(buf + a + 4 * i);
+#pragma unroll
+        for (int i = 0; i < 6; i++) r[i] = __funnelshift_r(x[i], x[i + 1], sh);
+        reload = false;
+      }
+      uint32_t kw[6];
+      make_key(r, k, kind, kw);
+      const uint32_t idx = (key_hash(kw[0], kw[1], kw[2], kw[3], kw[4], kw[5]) + poff) & V.slot_mask;
+      const uint4 sa = __ldg(tab + 2 * idx);
+      const uint4 sb = __ldg(tab + 2 * idx + 1);
+      const bool occupied = slot_len(sb.y) != 0;
+      const bool match = sa.x == kw[0] && sa.y == kw[1] && sa.z == kw[2] && sa.w == kw[3] && sb.x == kw[4] &&
+                         ((sb.y ^ kw[5]) & WP_W5_KEYMASK) == 0;
+      if (occupied && !match) {  // collision: next slot, same key
+        poff++;
+        continue;
+      }
+      poff = 0;
+      if (match) {
+        lo = k;
+        node_w5 = sb.y;
+        node_term = static_cast<int32_t>(sb.z);
+        node_best = static_cast<int32_t>(sb.w);
+        node_slot = idx;
+      } else {
+        hi = k;
+      }
+      if (hi - lo > 1) {  // binary search for the deepest node goes on
+        k = (lo + hi) >> 1;
+        continue;
+      }
+
+      // -- the deepest node along the window is at depth lo: read the longest match off it
+      uint32_t mlen = 0;
+      int32_t mid = WP_NO_ID;
+      if (lo != 0) {
+        if (node_term != WP_NO_ID) {
+          mlen = lo;
+          mid = node_term;
+        } else if (slot_best_len(node_w5) != 0) {
+          mlen = slot_best_len(node_w5);
+          mid = node_best;
+        }
+        if (lo == WP_KEY_BYTES && slot_has_long(node_w5) && e - p > static_cast<int>(WP_KEY_BYTES)) {
+          // tokens longer than the inline key hang off this node, longest first
+          const uint32_t ref = V.long_ref[node_slot];
+          const uint32_t cnt = V.long_entries[ref];
+          for (uint32_t li = 0; li < cnt; li++) {
+            const uint32_t len = V.long_entries[ref + 1 + 3 * li];
+            if (len > static_cast<uint32_t>(e - p)) continue;
+            const uint8_t *tok = V.long_bytes + V.long_entries[ref + 3 + 3 * li];
+            uint32_t o = WP_KEY_BYTES;
+            while (o < len && buf[p + o] == tok[o]) o++;
+            if (o == len) {
+              mlen = len;
+              mid = static_cast<int32_t>(V.long_entries[ref + 2 + 3 * li]);
+              break;
+            }
+          }
+        }
+      }
+
+      // -- apply the piece (fast.cpp:66-91)
+      bool done = false;
+      if (flags & SEG_PUNCT) {
+        sm.stage[s] = (mlen == first_len) ? mid : V.unk_id;
+        nid = 1;
+        done = true;
+      } else if (flags & SEG_HAN_FIRST) {
+        flags = 0;
+        nid = 1;
+        if (mlen == 0) {
+          sm.stage[s] = V.unk_id;
+          if (V.han_swallow) {
+            done = true;  // fast.cpp:85-88: begin += word_len swallows the run
+          } else {
+            word_first = 1;
+            p += static_cast<int>(first_len);
+          }
+        } else {
+          sm.stage[s] = mid;
+          p += static_cast<int>(mlen);
+          if (mlen == first_len) {
+            word_first = 1;  // fast.cpp:89-91: the next position follows a spacing char => new word
+          } else {
+            kind = WP_KIND_SUFFIX;
+          }
+        }
+      } else if (mlen == 0) {  // fast.cpp:79-88: whole-word UNK, earlier pieces rolled back
+        sm.stage[s + word_first] = V.unk_id;
+        nid = word_first + 1;
+        done = true;
+      } else {
+        sm.stage[s + nid] = mid;
+        nid++;
+        p += static_cast<int>(mlen);
+        kind = WP_KIND_SUFFIX;
+      }
+      if (done || p >= e) {
+        sm.seg_cnt[q] = static_cast<uint16_t>(nid);
+        active = false;
+      } else {
+        const uint32_t wlen = static_cast<uint32_t>(e - p);
+        k = wlen < WP_KEY_BYTES ? wlen : WP_KEY_BYTES;
+        lo = 0;
+        hi = k + 1;
+        reload = true;
+      }
     }
   }
-
-  // ---- S3a: block scan of the per-thread counts
-  uint32_t incl = my_total;
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if (lane >= o) incl += y;
-  }
-  __syncthreads();  // warp_sums may have been used by the dirty path
-  if (lane == 31) sm.warp_sums[warp] = incl;
   __syncthreads();
-  uint32_t wbase = 0, tile_normal = 0;
+
+  // ---- S3a: id counts -> per-warp totals.  Warp w scatters segments [w*R, (w+1)*R).
+  const uint32_t R = ((n_segs + WARPS - 1) / WARPS + 31u) & ~31u;
+  const uint32_t seg_lo = min(n_segs, static_cast<uint32_t>(warp) * R);
+  const uint32_t seg_hi = min(n_segs, seg_lo + R);
+  {
+    uint32_t sum = 0;
+    for (uint32_t i = seg_lo + lane; i < seg_hi; i += 32) sum += sm.seg_cnt[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+    if (lane == 0) sm.warp_tot[warp] = sum;
+  }
+  __syncthreads();
+  uint32_t warp_base = 0, tile_normal = 0;
+#pragma unroll
   for (int wi = 0; wi < WARPS; wi++) {
-    const uint32_t ws = sm.warp_sums[wi];
-    if (wi < warp) wbase += ws;
+    const uint32_t ws = sm.warp_tot[wi];
+    if (wi < warp) warp_base += ws;
     tile_normal += ws;
   }
-  const uint32_t my_off = wbase + incl - my_total;
 
-  // ---- S3b: the long segment (count pass) and the look-back across tiles
-  if (tid == 0) {
+  // ---- S3b: the long segment (count pass) and the look-back across tiles (warp 0)
+  if (warp == 0) {
     size_t long_gs = 0;
-    if (sm.long_start != LONG_NONE) {
-      // window position -> text position (compacted windows: undo the compaction)
-      int wpos = sm.long_start;
-      if (dirty) {
-        int cc = 0;
-        while (cc + 1 <= NCHUNK && sm.kept_scan[cc + 1] <= static_cast<uint32_t>(wpos)) cc++;
-        // position of the (k+1)-th surviving byte of raw chunk cc
-        const uint32_t k = static_cast<uint32_t>(wpos) - sm.kept_scan[cc];
-        const int pos_in = static_cast<int>(__fns(sm.m_kept[cc], 0, static_cast<int>(k) + 1));
-        wpos = cc * CHUNK + pos_in;
+    if (lane == 0) {
+      if (sm.long_start != LONG_NONE) {
+        // window position -> text position (compacted windows: undo the compaction)
+        int wpos = sm.long_start;
+        if (dirty) {
+          int cc = 0;
+          while (cc + 1 <= NCHUNK && sm.kept_scan[cc + 1] <= static_cast<uint32_t>(wpos)) cc++;
+          const uint32_t kk = static_cast<uint32_t>(wpos) - sm.kept_scan[cc];
+          wpos = cc * CHUNK + static_cast<int>(__fns(sm.m_kept[cc], 0, static_cast<int>(kk) + 1));
+        }
+        long_gs = t0 + static_cast<size_t>(wpos);
+        int32_t unk_at;
+        sm.long_count = walk_segment(V, tv, long_gs, nullptr, 0, -1, &unk_at);
+        sm.long_unk_at = unk_at;
+        atomicAdd(P.stat_long_segments, 1ull);
       }
-      long_gs = t0 + static_cast<size_t>(wpos);
-      int32_t unk_at;
-      sm.long_count = walk_segment(V, tv, long_gs, nullptr, 0, -1, &unk_at);
-      sm.long_unk_at = unk_at;
-      atomicAdd(P.stat_long_segments, 1ull);
+      if (dirty) atomicAdd(P.stat_dirty_tiles, 1ull);
     }
-    if (dirty) atomicAdd(P.stat_dirty_tiles, 1ull);
+    __syncwarp();
     const unsigned long long total = static_cast<unsigned long long>(tile_normal) + sm.long_count;
 
     // decoupled look-back: state = flag << 62 | value; flag 1 = tile aggregate, 2 = inclusive prefix
     volatile unsigned long long *state = P.tile_state;
+    constexpr unsigned long long VALUE_MASK = (1ull << 62) - 1;
     unsigned long long base = 0;
     if (tile == 0) {
-      state[0] = (2ull << 62) | total;
+      if (lane == 0) state[0] = (2ull << 62) | total;
     } else {
-      state[tile] = (1ull << 62) | total;
-      __threadfence();
-      long long pred = static_cast<long long>(tile) - 1;
+      if (lane == 0) state[tile] = (1ull << 62) | total;
+      long long pred = static_cast<long long>(tile) - 1 - lane;  // lane i looks at tile-1-i
       for (;;) {
-        unsigned long long sv;
-        do {
-          sv = state[pred];
-        } while ((sv >> 62) == 0);
-        base += sv & ((1ull << 62) - 1);
-        if ((sv >> 62) == 2) break;
-        pred--;
+        unsigned long long sv = 2ull << 62;  // tiles before 0 count as a zero prefix
+        if (pred >= 0) {
+          do {
+            sv = state[pred];
+          } while ((sv >> 62) == 0);
+        }
+        const uint32_t is_prefix = __ballot_sync(FULL, (sv >> 62) == 2);
+        // add the aggregates of the lanes before the first inclusive prefix, and that prefix
+        const int stop = is_prefix ? __ffs(is_prefix) - 1 : 31;
+        unsigned long long v = lane <= stop ? (sv & VALUE_MASK) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        base += v;
+        if (is_prefix) break;
+        pred -= 32;
       }
-      state[tile] = (2ull << 62) | (base + total);
+      if (lane == 0) state[tile] = (2ull << 62) | (base + total);
     }
-    sm.tile_base = base;
-    if (tile == P.n_tiles - 1) *P.n_ids_out = base + total;
-
-    if (sm.long_start != LONG_NONE) {
-      const unsigned long long at = base + tile_normal;
-      int32_t unk_at;
-      walk_segment(V, tv, long_gs, P.ids + at, at < P.capacity ? P.capacity - at : 0ull, sm.long_unk_at, &unk_at);
+    if (lane == 0) {
+      sm.tile_base = base;
+      if (tile == P.n_tiles - 1) *P.n_ids_out = base + total;
+      if (sm.long_start != LONG_NONE) {
+        const unsigned long long at = base + tile_normal;
+        int32_t unk_at;
+        walk_segment(V, tv, long_gs, P.ids + at, at < P.capacity ? P.capacity - at : 0ull, sm.long_unk_at, &unk_at);
+      }
     }
   }
   __syncthreads();
 
-  // ---- S3c: scatter my ids to their final positions
+  // ---- S3c: scatter.  One segment per lane, 32 consecutive segments per row, so
+  // the stores of a row fall into a few adjacent sectors.
   {
-    unsigned long long at = sm.tile_base + my_off;
-    uint32_t m = starts;
-    while (m) {
-      const int j = __ffs(m) - 1;
-      m &= m - 1;
-      const int s = c * CHUNK + j;
-      if (s == sm.long_start) continue;
-      const uint32_t cnt = sm.segcnt[s];
-      for (uint32_t i = 0; i < cnt; i++) {
-        if (at < P.capacity) P.ids[at] = sm.stage[s + i];
-        at++;
+    unsigned long long run = sm.tile_base + warp_base;
+    for (uint32_t row = seg_lo; row < seg_hi; row += 32) {
+      const uint32_t i = row + lane;
+      const uint32_t cnt = i < seg_hi ? sm.seg_cnt[i] : 0u;
+      const uint32_t s = i < seg_hi ? sm.seg_start[i] : 0u;
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += y;
       }
+      const unsigned long long at = run + incl - cnt;
+      uint32_t maxc = cnt;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(FULL, maxc, o));
+      for (uint32_t j = 0; j < maxc; j++) {
+        if (j < cnt && at + j < P.capacity) P.ids[at + j] = sm.stage[s + j];
+      }
+      run += __shfl_sync(FULL, incl, 31);
     }
   }
 }
