@@ -60,6 +60,9 @@ const char *wp_last_error(void);
 /* Number of CUDA kernels this library has launched in this process. */
 uint64_t wp_kernel_launch_count(void);
 
+/* Text bytes one thread block owns (the tile size of the encode kernel). */
+uint32_t wp_tile_bytes(void);
+
 /* ---- vocabulary ---------------------------------------------------------
  * Replaces utils::parseVocab (utils.cpp:108-121) + the WordPieceToken
  * constructor (utils.cpp:81-106) + the two-map build (fast.cpp:21-36), done

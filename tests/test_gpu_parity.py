@@ -124,11 +124,15 @@ def test_random_split_small(gpu_device):
                 _check(s, vocab, gpu_device, f"split L={text_len} parts={parts} pos={positive}")
 
 
-@pytest.mark.parametrize("seed,n_bytes", [(11, 5000), (12, 8192), (13, 8193), (14, 8191), (15, 40000), (16, 300000)])
+@pytest.mark.parametrize("seed,n_bytes", [(11, 5000), (12, 8192), (13, 8193), (14, 8191), (17, 4096), (18, 4097), (19, 4095),
+                                          (15, 40000), (16, 300000)])
 def test_multilingual_multi_tile(gpu_device, seed, n_bytes):
+    import wordpiece_b200
+
     text, vocab = textgen.case(seed, n_bytes)
     st = _check(text, vocab, gpu_device, f"mixed seed={seed}")
-    assert st.n_tiles == (len(text) + 8191) // 8192
+    tile = wordpiece_b200.tile_bytes()
+    assert st.n_tiles == (len(text) + tile - 1) // tile
 
 
 @pytest.mark.parametrize("seed,n_bytes,rate", [(21, 3000, 0.3), (22, 30000, 0.05), (23, 100000, 0.01), (24, 60000, 0.5)])
@@ -141,8 +145,11 @@ def test_invalid_utf8_is_dropped(gpu_device, seed, n_bytes, rate):
 
 def test_invalid_runs_across_tile_borders(gpu_device):
     vocab = ["ab", "##cd", "abcd", "x", "中", "[UNK]"]
+    import wordpiece_b200
+
+    tile = wordpiece_b200.tile_bytes()
     for junk in (b"\xff", b"\x80", b"\xe4\xb8", b"\xf0\x9f\x98"):
-        for pad in range(8180, 8200):
+        for pad in list(range(tile - 12, tile + 8)) + list(range(2 * tile - 12, 2 * tile + 8, 3)):
             text = b"x " * (pad // 2) + b"ab" + junk * 7 + b"cd" + junk * 40 + " 中".encode() + junk + b" x"
             _check(text, vocab, gpu_device, f"junk={junk!r} pad={pad}")
     # a run of invalid bytes longer than a whole tile between the halves of one word

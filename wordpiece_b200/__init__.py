@@ -33,6 +33,7 @@ from ._capi import (  # noqa: F401
     encode_files,
     kernel_launch_count,
     load_library,
+    tile_bytes,
 )
 
 __all__ = [
@@ -46,4 +47,5 @@ __all__ = [
     "encode_files",
     "kernel_launch_count",
     "load_library",
+    "tile_bytes",
 ]

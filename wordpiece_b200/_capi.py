@@ -57,6 +57,7 @@ class Stats:
 EXPORTED_SYMBOLS = [
     "wp_last_error",
     "wp_kernel_launch_count",
+    "wp_tile_bytes",
     "wp_vocab_create",
     "wp_vocab_create_from_file",
     "wp_vocab_destroy",
@@ -97,6 +98,7 @@ def load_library() -> C.CDLL:
     vp, sz, i32p = C.c_void_p, C.c_size_t, C.POINTER(C.c_int32)
     L.wp_last_error.restype = C.c_char_p
     L.wp_kernel_launch_count.restype = C.c_uint64
+    L.wp_tile_bytes.restype = C.c_uint32
     L.wp_vocab_create.argtypes = [C.POINTER(C.c_char_p), C.POINTER(sz), sz, C.c_int, C.POINTER(vp)]
     L.wp_vocab_create.restype = C.c_int
     L.wp_vocab_create_from_file.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
@@ -146,6 +148,10 @@ def _check(status: int) -> None:
 
 def kernel_launch_count() -> int:
     return int(load_library().wp_kernel_launch_count())
+
+
+def tile_bytes() -> int:
+    return int(load_library().wp_tile_bytes())
 
 
 def _as_bytes(x) -> bytes:

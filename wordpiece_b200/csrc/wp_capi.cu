@@ -213,6 +213,8 @@ const char *wp_last_error(void) { return g_error.c_str(); }
 
 uint64_t wp_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+uint32_t wp_tile_bytes(void) { return wp::encode_tile_bytes(); }
+
 void wp_free(void *p) { std::free(p); }
 
 wp_status wp_vocab_create(const char *const *tokens, const size_t *token_lens, size_t n_tokens, int device,

@@ -38,29 +38,33 @@
 namespace wp {
 
 // ------------------------------------------------------------------ geometry
-constexpr int TILE = 8192;                       // text bytes owned by one CTA
+constexpr int TILE = 4096;                       // text bytes owned by one CTA
 constexpr int CHUNK = 32;                        // bytes classified by one thread
-constexpr int THREADS = 512;                     // 16 warps; 2 CTAs per SM
+constexpr int THREADS = 192;                     // 6 warps; 4 CTAs per SM (shared memory bound)
 constexpr int HALO = 256;                        // classified bytes past the tile (segment completion)
 constexpr int LOOKAHEAD = 32;                    // loaded, not classified (UTF-8 validation look-ahead)
 constexpr int LEFT = 16;                         // bytes before the tile (ownership of leading continuation bytes)
 constexpr int WINDOW = TILE + HALO;              // classified window
-constexpr int NCHUNK = WINDOW / CHUNK;           // 264
-constexpr int OWNED_CHUNKS = TILE / CHUNK;       // 256
-constexpr int RAW_BYTES = LEFT + WINDOW + LOOKAHEAD;  // 8496
+constexpr int NCHUNK = WINDOW / CHUNK;           // 136
+constexpr int OWNED_CHUNKS = TILE / CHUNK;       // 128
+constexpr int RAW_BYTES = LEFT + WINDOW + LOOKAHEAD;  // 4400
 constexpr int WARPS = THREADS / 32;
 constexpr int32_t LONG_NONE = -1;
 constexpr uint32_t FULL = 0xFFFFFFFFu;
+constexpr uint32_t POS_MASK = 0x3FFFu;           // window positions fit 14 bits
+constexpr uint32_t SLOW_FIRST_MISSED = 0x8000u;  // slow-list flag: the whole-window probe already missed
 
 static_assert(RAW_BYTES % 16 == 0, "raw buffer is loaded in 16-byte units");
 static_assert(WP_KEY_BYTES + 4 <= LOOKAHEAD, "key window reads stay inside the loaded bytes");
-static_assert(NCHUNK + 1 <= THREADS, "one thread per chunk in the compaction pass");
+static_assert(NCHUNK + 1 <= THREADS, "one thread per chunk in the classification and compaction passes");
+static_assert(WINDOW <= static_cast<int>(POS_MASK), "positions must fit the packed list entries");
 
 struct __align__(16) TileSmem {
   uint8_t raw[RAW_BYTES];              // [0,LEFT) left halo, then the window, then look-ahead
   int32_t stage[WINDOW + 8];           // ids of the segment starting at byte s live at stage[s..s+cnt)
-  uint16_t seg_start[TILE];            // window position of owned segment k (text order)
-  uint16_t seg_cnt[TILE];              // id count of owned segment k
+  uint16_t seg_s[TILE];                // owned segment k (text order): start position | class << 14
+  uint16_t seg_e[WINDOW + 64];         // j-th segment end in the window; entry k+skip is reused as id count of segment k
+  uint16_t slow[TILE];                 // segments the whole-window probe did not settle
   uint32_t m_lead[NCHUNK + 1];         // valid lead bytes
   uint32_t m_space[NCHUNK + 1];
   uint32_t m_punct[NCHUNK + 1];
@@ -69,13 +73,16 @@ struct __align__(16) TileSmem {
   uint32_t m_kept[NCHUNK + 1];         // bytes of the RAW window that survive the strict decoder (dirty tiles)
   uint32_t kept_scan[NCHUNK + 2];      // exclusive scan of kept bytes per chunk (dirty tiles)
   uint8_t spill[NCHUNK + 1];           // bytes by which the chunk's last sequence runs into the next chunk
+  uint4 key_mask[2 * (WP_KEY_BYTES + 1)];  // row k: masks of the six key words for a k-byte key, then k << 16
   uint32_t warp_sums[WARPS];
   uint32_t warp_tot[WARPS];
   uint32_t tile_index;
   uint32_t prev_class;                 // class of the last valid char before the tile
   uint32_t left_spill;                 // bytes of the tile start covered by a sequence that began before it
   uint32_t n_segs;                     // owned segments in this tile
-  uint32_t next_seg;                   // work dispenser of the match loop
+  uint32_t n_ends;                     // segment ends found in the window
+  uint32_t n_slow;                     // entries of slow[]
+  uint32_t next_slow;                  // work dispenser of the slow lane
   int32_t long_start;                  // window position of the segment that leaves the window, or LONG_NONE
   uint32_t long_count;
   int32_t long_unk_at;
@@ -145,6 +152,20 @@ __device__ __forceinline__ void make_key(const uint32_t r[6], uint32_t k, uint32
   const int nb5 = static_cast<int>(k) - 20;
   const uint32_t tail = nb5 <= 0 ? 0u : (r[5] & ((1u << (8 * nb5)) - 1u));
   kw[5] = make_w5(tail, k, kind);
+}
+
+// Same, with the byte masks read from a 32-byte row of a shared-memory table
+// (two 16-byte loads and six ANDs instead of a compare/select chain per word).
+__device__ __forceinline__ void make_key_tab(const uint4 *key_mask, const uint32_t r[6], uint32_t k, uint32_t kind,
+                                             uint32_t kw[6]) {
+  const uint4 ma = key_mask[2 * k];
+  const uint4 mb = key_mask[2 * k + 1];
+  kw[0] = r[0] & ma.x;
+  kw[1] = r[1] & ma.y;
+  kw[2] = r[2] & ma.z;
+  kw[3] = r[3] & ma.w;
+  kw[4] = r[4] & mb.x;
+  kw[5] = (r[5] & mb.y) | mb.z | (kind << 24);
 }
 
 // Deepest trie node along the window whose first min(window,22) bytes are r[];
@@ -384,8 +405,48 @@ __device__ uint32_t walk_segment(const DeviceVocab &V, const TextView &tv, size_
 
 // ------------------------------------------------------------- classification
 
+// exact: 0x80 in every byte lane whose byte is zero
+__device__ __forceinline__ uint32_t swar_zero(uint32_t x) {
+  return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+}
+
+// flags of the byte lane d (1..3) positions earlier: lane j gets cur/prev lane j-d
+__device__ __forceinline__ uint32_t lanes_back(uint32_t prev, uint32_t cur, int d) {
+  return __funnelshift_l(prev, cur, 8 * d);
+}
+
+struct WordFlags {
+  uint32_t cont;     // 10xxxxxx
+  uint32_t m1;       // 11xxxxxx  (any multi-byte lead)
+  uint32_t m2;       // 111xxxxx
+  uint32_t m3;       // 1111xxxx
+  uint32_t suspect;  // leads whose validity depends on their value: C0 C1 E0 ED F0..FF
+};
+
+__device__ __forceinline__ WordFlags word_flags(uint32_t w) {
+  WordFlags f;
+  const uint32_t hi = w & 0x80808080u;
+  const uint32_t t1 = w << 1, t2 = w << 2, t3 = w << 3;
+  f.cont = hi & ~t1;
+  f.m1 = hi & t1;
+  f.m2 = f.m1 & t2;
+  f.m3 = f.m2 & t3;
+  const uint32_t lead2 = f.m1 & ~t2;
+  const uint32_t lead3 = f.m2 & ~t3;
+  const uint32_t low = w & 0x0F0F0F0Fu;
+  f.suspect = f.m3 | (lead2 & swar_zero(w & 0x1E1E1E1Eu)) | (lead3 & (swar_zero(low) | swar_zero(low ^ 0x0D0D0D0Du)));
+  return f;
+}
+
 // Classify chunk c of `buf` (window coordinates) into the mask arrays.  `limit`
 // is the number of meaningful bytes in buf (positions >= limit are ignored).
+//
+// Fast lane (no per-byte loop): ASCII classes by SWAR range tests; multi-byte
+// text is validated STRUCTURALLY (every lead followed by exactly its
+// continuation bytes) with byte-lane shifts; only leads that can be space /
+// punctuation / Han (C2, E2..E9, EF) are decoded.  Chunks holding a lead whose
+// validity depends on its value (overlong / surrogate / 4-byte forms) or any
+// structural error take the exact per-byte lane below.
 __device__ __forceinline__ void classify_chunk(TileSmem &sm, const uint8_t *buf, int c, int limit) {
   const uint8_t *cb = buf + c * CHUNK;
   uint32_t w[8];
@@ -395,34 +456,77 @@ __device__ __forceinline__ void classify_chunk(TileSmem &sm, const uint8_t *buf,
     w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
     w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
   }
-  uint32_t lead = 0, sp = 0, pu = 0, ha = 0, cover = 0, spill = 0;
-  const uint32_t any_high = (w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) & 0x80808080u;
-  if (any_high == 0) {
-    lead = 0xFFFFFFFFu;
-    cover = 0xFFFFFFFFu;
+  uint32_t lead = 0xFFFFFFFFu, sp = 0, pu = 0, ha = 0, cover = 0xFFFFFFFFu, spill = 0;
+  uint32_t any_high = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t w7 = w[i] & 0x7F7F7F7Fu;
+    const uint32_t asc = ~w[i] & 0x80808080u;
+    const uint32_t s = (swar_range(w7, 0x09, 0x0D) | swar_range(w7, 0x20, 0x20)) & asc;
+    const uint32_t q = (swar_range(w7, 0x21, 0x2F) | swar_range(w7, 0x3A, 0x40) | swar_range(w7, 0x5B, 0x60) |
+                        swar_range(w7, 0x7B, 0x7E)) & asc;
+    sp |= swar_nibble(s) << (4 * i);
+    pu |= swar_nibble(q) << (4 * i);
+    any_high |= w[i];
+  }
+  if (any_high & 0x80808080u) {
+    // ---- structural validation in the byte-lane domain
+    WordFlags prev = word_flags(ld_u32(cb - 4));
+    uint32_t bad = prev.suspect, contm = 0, cand = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      const uint32_t s = swar_range(w[i], 0x09, 0x0D) | swar_range(w[i], 0x20, 0x20);
-      const uint32_t q = swar_range(w[i], 0x21, 0x2F) | swar_range(w[i], 0x3A, 0x40) | swar_range(w[i], 0x5B, 0x60) |
-                         swar_range(w[i], 0x7B, 0x7E);
-      sp |= swar_nibble(s) << (4 * i);
-      pu |= swar_nibble(q) << (4 * i);
+      const WordFlags f = word_flags(w[i]);
+      const uint32_t expect = lanes_back(prev.m1, f.m1, 1) | lanes_back(prev.m2, f.m2, 2) | lanes_back(prev.m3, f.m3, 3);
+      bad |= (expect ^ f.cont) | f.suspect;
+      contm |= swar_nibble(f.cont) << (4 * i);
+      // leads that may be a spacing char: C2 (Latin-1 punctuation), E2 (U+2010.., U+2581), E3..E9, EF (Han)
+      const uint32_t low = w[i] & 0x0F0F0F0Fu;
+      const uint32_t lead3 = f.m2 & ~(w[i] << 3);
+      const uint32_t cf = swar_zero(w[i] ^ 0xC2C2C2C2u) | (lead3 & (swar_range(low, 2, 9) | swar_zero(low ^ 0x0F0F0F0Fu)));
+      cand |= swar_nibble(cf) << (4 * i);
+      prev = f;
     }
-  } else {
-    for (int j = 0; j < CHUNK; j++) {
-      const uint32_t b0 = cb[j];
-      if (is_cont_byte(b0)) continue;
-      uint32_t cp = 0;
-      const uint32_t len = b0 < 0x80u ? (cp = b0, 1u) : utf8_decode(b0, cb[j + 1], cb[j + 2], cb[j + 3], 4u, &cp);
-      if (len == 0) continue;
-      lead |= 1u << j;
-      const uint32_t span = (len == 1 ? 1u : (1u << len) - 1u);
-      cover |= span << j;
-      if (j + static_cast<int>(len) > CHUNK) spill = j + len - CHUNK;
-      const uint32_t cls = cp_class(cp);
-      sp |= (cls == CLS_SPACE ? 1u : 0u) << j;
-      pu |= (cls == CLS_PUNCT ? 1u : 0u) << j;
-      ha |= (cls == CLS_HAN ? 1u : 0u) << j;
+    {
+      // sequences that run past the chunk must find their continuation bytes in the next word
+      const WordFlags nx = word_flags(ld_u32(cb + CHUNK));
+      const uint32_t expect = lanes_back(prev.m1, 0u, 1) | lanes_back(prev.m2, 0u, 2) | lanes_back(prev.m3, 0u, 3);
+      bad |= expect & ~nx.cont;
+      spill = __popc(expect);
+    }
+    if (bad == 0) {
+      lead = ~contm;
+      while (cand) {
+        const int j = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const uint32_t b0 = cb[j], b1 = cb[j + 1], b2 = cb[j + 2];
+        const uint32_t cp = b0 < 0xE0u ? (((b0 & 0x1Fu) << 6) | (b1 & 0x3Fu))
+                                       : (((b0 & 0x0Fu) << 12) | ((b1 & 0x3Fu) << 6) | (b2 & 0x3Fu));
+        const uint32_t cls = cp_class(cp);
+        sp |= (cls == CLS_SPACE ? 1u : 0u) << j;
+        pu |= (cls == CLS_PUNCT ? 1u : 0u) << j;
+        ha |= (cls == CLS_HAN ? 1u : 0u) << j;
+      }
+    } else {
+      // ---- exact per-byte lane (utf8.cpp:54-90): overlongs, surrogates, 4-byte forms, stray bytes
+      lead = 0;
+      cover = 0;
+      spill = 0;
+      sp = 0;
+      pu = 0;
+      for (int j = 0; j < CHUNK; j++) {
+        const uint32_t b0 = cb[j];
+        if (is_cont_byte(b0)) continue;
+        uint32_t cp = 0;
+        const uint32_t len = b0 < 0x80u ? (cp = b0, 1u) : utf8_decode(b0, cb[j + 1], cb[j + 2], cb[j + 3], 4u, &cp);
+        if (len == 0) continue;
+        lead |= 1u << j;
+        cover |= ((1u << len) - 1u) << j;
+        if (j + static_cast<int>(len) > CHUNK) spill = j + len - CHUNK;
+        const uint32_t cls = cp_class(cp);
+        sp |= (cls == CLS_SPACE ? 1u : 0u) << j;
+        pu |= (cls == CLS_PUNCT ? 1u : 0u) << j;
+        ha |= (cls == CLS_HAN ? 1u : 0u) << j;
+      }
     }
   }
   // ignore everything at or past `limit`
@@ -434,20 +538,6 @@ __device__ __forceinline__ void classify_chunk(TileSmem &sm, const uint8_t *buf,
   sm.m_han[c] = ha & in;
   sm.m_cover[c] = cover;
   sm.spill[c] = static_cast<uint8_t>(spill);
-}
-
-// Position of the first spacing-char lead (space / punct / Han) at or after pos,
-// or -1 if there is none before `limit`.
-__device__ __forceinline__ int find_break(const TileSmem &sm, int pos, int limit) {
-  int c = pos >> 5;
-  const int last = (limit + CHUNK - 1) >> 5;
-  if (c >= last) return -1;
-  uint32_t m = (sm.m_space[c] | sm.m_punct[c] | sm.m_han[c]) & (0xFFFFFFFFu << (pos & 31));
-  while (m == 0) {
-    if (++c >= last) return -1;
-    m = sm.m_space[c] | sm.m_punct[c] | sm.m_han[c];
-  }
-  return c * CHUNK + __ffs(m) - 1;
 }
 
 // block-wide exclusive scan of one value per thread; returns the exclusive prefix, *total = sum
@@ -473,13 +563,22 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(TileSmem &sm, uint32_t 
   return wbase + incl - v;
 }
 
+// 24 window bytes starting at p (any alignment) as six little-endian words
+__device__ __forceinline__ void load_window(const uint8_t *buf, int p, uint32_t r[6]) {
+  const int a = p & ~3;
+  const uint32_t sh = (p & 3) * 8;
+  uint32_t x[7];
+#pragma unroll
+  for (int i = 0; i < 7; i++) x[i] = ld_u32(buf + a + 4 * i);
+#pragma unroll
+  for (int i = 0; i < 6; i++) r[i] = __funnelshift_r(x[i], x[i + 1], sh);
+}
+
 // ------------------------------------------------------------------ the kernel
 
-// flags of a segment being matched
-constexpr uint32_t SEG_PUNCT = 1u;      // single punctuation char (window 1, fast.cpp:55)
-constexpr uint32_t SEG_HAN_FIRST = 2u;  // about to match the first piece of a Han-led segment
+constexpr uint32_t SEG_HAN_FIRST = 1u;  // about to match the first piece of a Han-led segment
 
-__global__ void __launch_bounds__(THREADS, 2) wp_encode_kernel(EncodeParams P) {
+__global__ void __launch_bounds__(THREADS, 4) wp_encode_kernel(EncodeParams P) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
   const int tid = threadIdx.x;
@@ -495,7 +594,19 @@ __global__ void __launch_bounds__(THREADS, 2) wp_encode_kernel(EncodeParams P) {
     sm.long_count = 0;
     sm.long_unk_at = -1;
     sm.left_spill = 0;
-    sm.next_seg = 0;
+    sm.n_slow = 0;
+    sm.next_slow = 0;
+  }
+  if (tid <= static_cast<int>(WP_KEY_BYTES)) {
+    const uint32_t k = tid;  // row k of the key mask table
+    uint32_t m[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const int nb = static_cast<int>(k) - 4 * i;
+      m[i] = nb >= 4 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
+    }
+    sm.key_mask[2 * k] = make_uint4(m[0], m[1], m[2], m[3]);
+    sm.key_mask[2 * k + 1] = make_uint4(m[4], m[5] & 0xFFFFu, k << 16, 0u);
   }
   __syncthreads();
   const uint32_t tile = sm.tile_index;
@@ -589,12 +700,20 @@ __global__ void __launch_bounds__(THREADS, 2) wp_encode_kernel(EncodeParams P) {
   // owned range in buffer coordinates: segments that start in [0, own_end)
   const int own_end = dirty ? static_cast<int>(sm.kept_scan[OWNED_CHUNKS]) : TILE;
 
-  // ---- S1d: segment starts of my chunk (SURVEY A.2 safe starts), compacted into seg_start[]
+  // ---- S1d: segment starts (SURVEY A.2 safe starts) and segment ends, by mask
+  // arithmetic, compacted in text order into seg_s[] / seg_e[].  A segment ends
+  // at a lead p whose previous char is not a space and (is punctuation, or p
+  // itself is a spacing char).  Starts and ends alternate, so owned segment k
+  // pairs with end k + skip, skip = 1 iff a segment of the previous tile is
+  // still open at the tile border.
   {
-    uint32_t starts = 0;
+    uint32_t starts = 0, ends = 0, lead = 0, pu = 0, ha = 0;
     const int c = tid;
-    if (c < OWNED_CHUNKS) {
-      const uint32_t lead = sm.m_lead[c], sp = sm.m_space[c], pu = sm.m_punct[c], ha = sm.m_han[c];
+    if (c < NCHUNK) {
+      lead = sm.m_lead[c];
+      pu = sm.m_punct[c];
+      ha = sm.m_han[c];
+      const uint32_t sp = sm.m_space[c];
       uint32_t carry_s, carry_p;
       if (c == 0) {
         carry_s = sm.prev_class == CLS_SPACE;
@@ -618,100 +737,159 @@ __global__ void __launch_bounds__(THREADS, 2) wp_encode_kernel(EncodeParams P) {
       }
       const uint32_t prev_s = (xs << 1) | carry_s;
       const uint32_t prev_p = (xp << 1) | carry_p;
+      ends = lead & ~prev_s & (prev_p | sp | pu | ha);
       starts = lead & ~sp & (pu | ha | prev_s | prev_p);
       const int left = own_end - c * CHUNK;
       starts &= left >= CHUNK ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
     }
-    uint32_t n_segs;
-    uint32_t at = block_exclusive_scan(sm, __popc(starts), &n_segs);
+    uint32_t totals;
+    const uint32_t at = block_exclusive_scan(sm, __popc(starts) | (__popc(ends) << 16), &totals);
+    uint32_t at_s = at & 0xFFFFu, at_e = at >> 16;
     while (starts) {
       const int j = __ffs(starts) - 1;
       starts &= starts - 1;
-      sm.seg_start[at++] = static_cast<uint16_t>(c * CHUNK + j);
+      const uint32_t bit = 1u << j;
+      const uint32_t cls = (pu & bit) ? CLS_PUNCT : ((ha & bit) ? CLS_HAN : CLS_OTHER);
+      sm.seg_s[at_s++] = static_cast<uint16_t>((c * CHUNK + j) | (cls << 14));
     }
-    if (tid == 0) sm.n_segs = n_segs;
+    while (ends) {
+      const int j = __ffs(ends) - 1;
+      ends &= ends - 1;
+      sm.seg_e[at_e++] = static_cast<uint16_t>(c * CHUNK + j);
+    }
+    if (tid == 0) {
+      sm.n_segs = totals & 0xFFFFu;
+      sm.n_ends = totals >> 16;
+    }
   }
   __syncthreads();
   const uint32_t n_segs = sm.n_segs;
+  const uint32_t n_ends = sm.n_ends;
+  const uint32_t skip = sm.prev_class != CLS_SPACE ? 1u : 0u;
+  const uint4 *tab = reinterpret_cast<const uint4 *>(V.slots);
 
-  // ---- S2: match.  Flattened state machine: every iteration each active lane
-  // issues exactly ONE table probe for its current (piece start p, length k).
+  // ---- S2a: one whole-window probe per segment, statically assigned (uniform
+  // work: every lane does the same thing).  It settles every segment that is a
+  // single token (fast.cpp:66-72 hit on the first, longest candidate) and every
+  // single-char segment; the rest go to the slow list.
+  for (uint32_t base = 0; base < n_segs; base += THREADS) {
+    const uint32_t k = base + tid;
+    bool slow = false, found = false;
+    if (k < n_segs) {
+      const uint32_t sv = sm.seg_s[k];
+      const int s = static_cast<int>(sv & POS_MASK);
+      const uint32_t j = k + skip;
+      int e = limit;
+      bool is_long = false;
+      if (j < n_ends) {
+        e = sm.seg_e[j];
+      } else if (more_text) {  // leaves the window: walked from global memory by thread 0 below
+        is_long = true;
+        sm.long_start = s;
+        sm.seg_e[j] = 0;
+      }
+      if (!is_long) {
+        const uint32_t wlen = static_cast<uint32_t>(e - s);
+        const uint32_t first_len = utf8_lead_len(buf[s]);
+        const uint32_t k0 = wlen < WP_KEY_BYTES ? wlen : WP_KEY_BYTES;
+        uint32_t r[6], kw[6];
+        load_window(buf, s, r);
+        make_key_tab(sm.key_mask, r, k0, WP_KIND_PREFIX, kw);
+        uint32_t idx = key_hash(kw[0], kw[1], kw[2], kw[3], kw[4], kw[5]) & V.slot_mask;
+        int32_t term = WP_NO_ID;
+        for (;;) {
+          const uint4 sa = __ldg(tab + 2 * idx);
+          const uint4 sb = __ldg(tab + 2 * idx + 1);
+          if (slot_len(sb.y) == 0) break;
+          if (sa.x == kw[0] && sa.y == kw[1] && sa.z == kw[2] && sa.w == kw[3] && sb.x == kw[4] &&
+              ((sb.y ^ kw[5]) & WP_W5_KEYMASK) == 0) {
+            found = true;
+            term = static_cast<int32_t>(sb.z);
+            break;
+          }
+          idx = (idx + 1) & V.slot_mask;
+        }
+        const bool hit = found && term != WP_NO_ID && wlen <= WP_KEY_BYTES;
+        if (hit || wlen == first_len) {
+          sm.stage[s] = hit ? term : V.unk_id;
+          sm.seg_e[j] = 1;
+        } else {
+          slow = true;
+        }
+      }
+    }
+    const uint32_t slowm = __ballot_sync(FULL, slow);
+    if (slowm) {
+      uint32_t at = 0;
+      const int leader = __ffs(slowm) - 1;
+      if (lane == leader) at = atomicAdd(&sm.n_slow, static_cast<uint32_t>(__popc(slowm)));
+      at = __shfl_sync(FULL, at, leader);
+      if (slow) sm.slow[at + __popc(slowm & ((1u << lane) - 1u))] = static_cast<uint16_t>(k | (found ? 0u : SLOW_FIRST_MISSED));
+    }
+  }
+  __syncthreads();
+  const uint32_t n_slow = sm.n_slow;
+
+  // ---- S2b: the slow list.  Flattened state machine: every iteration each
+  // active lane issues exactly ONE table probe for its current (piece start p,
+  // length k) — binary-search step, next piece or collision alike — so a warp
+  // stays converged on the probe.  Lanes pull work dynamically.
   {
-    bool active = false, exhausted = false, reload = false;
+    bool active = false, exhausted = false;
     int s = 0, e = 0, p = 0;
-    uint32_t q = 0, nid = 0, word_first = 0, kind = WP_KIND_PREFIX, flags = 0, first_len = 0;
+    uint32_t cnt_at = 0, nid = 0, word_first = 0, kind = WP_KIND_PREFIX, flags = 0, first_len = 0;
     uint32_t k = 0, lo = 0, hi = 0, poff = 0;
-    uint32_t r[6] = {0, 0, 0, 0, 0, 0};
     uint32_t node_w5 = 0, node_slot = 0;
     int32_t node_term = WP_NO_ID, node_best = WP_NO_ID;
-    const uint4 *tab = reinterpret_cast<const uint4 *>(V.slots);
 
     for (;;) {
-      // -- refill idle lanes from the segment list (one shared-memory atomic per warp)
+      // -- refill idle lanes (one shared-memory atomic per warp and round)
       const bool need = !active && !exhausted;
       const uint32_t needm = __ballot_sync(FULL, need);
       if (needm) {
         uint32_t base = 0;
         const int leader = __ffs(needm) - 1;
-        if (lane == leader) base = atomicAdd(&sm.next_seg, static_cast<uint32_t>(__popc(needm)));
+        if (lane == leader) base = atomicAdd(&sm.next_slow, static_cast<uint32_t>(__popc(needm)));
         base = __shfl_sync(FULL, base, leader);
         if (need) {
-          q = base + __popc(needm & ((1u << lane) - 1u));
-          if (q >= n_segs) {
+          const uint32_t i = base + __popc(needm & ((1u << lane) - 1u));
+          if (i >= n_slow) {
             exhausted = true;
           } else {
-            s = sm.seg_start[q];
-            const uint32_t bit = 1u << (s & 31);
-            const uint32_t cls = (sm.m_punct[s >> 5] & bit) ? CLS_PUNCT : ((sm.m_han[s >> 5] & bit) ? CLS_HAN : CLS_OTHER);
+            const uint32_t ent = sm.slow[i];
+            const uint32_t q = ent & 0x1FFFu;
+            const uint32_t sv = sm.seg_s[q];
+            s = static_cast<int>(sv & POS_MASK);
+            cnt_at = q + skip;
+            e = cnt_at < n_ends ? static_cast<int>(sm.seg_e[cnt_at]) : limit;
             first_len = utf8_lead_len(buf[s]);
-            bool ok = true;
-            if (cls == CLS_PUNCT) {
-              e = s + static_cast<int>(first_len);
+            active = true;
+            p = s;
+            nid = 0;
+            word_first = 0;
+            kind = WP_KIND_PREFIX;
+            flags = (sv >> 14) == CLS_HAN ? SEG_HAN_FIRST : 0u;
+            const uint32_t wlen = static_cast<uint32_t>(e - p);
+            const uint32_t k0 = wlen < WP_KEY_BYTES ? wlen : WP_KEY_BYTES;
+            lo = 0;
+            poff = 0;
+            if (ent & SLOW_FIRST_MISSED) {  // the whole-window probe is known to miss (k0 >= 2 here)
+              hi = k0;
+              k = k0 >> 1;
             } else {
-              e = find_break(sm, s + static_cast<int>(first_len), limit);
-              if (e < 0) {
-                if (more_text) {  // leaves the window: walked from global memory by thread 0 below
-                  sm.long_start = s;
-                  sm.seg_cnt[q] = 0;
-                  ok = false;
-                } else {
-                  e = limit;
-                }
-              }
-            }
-            if (ok) {
-              active = true;
-              p = s;
-              nid = 0;
-              word_first = 0;
-              kind = WP_KIND_PREFIX;
-              flags = cls == CLS_PUNCT ? SEG_PUNCT : (cls == CLS_HAN ? SEG_HAN_FIRST : 0u);
-              const uint32_t wlen = static_cast<uint32_t>(e - p);
-              k = wlen < WP_KEY_BYTES ? wlen : WP_KEY_BYTES;
-              lo = 0;
-              hi = k + 1;
-              poff = 0;
-              reload = true;
+              hi = k0 + 1;
+              k = k0;
             }
           }
         }
       }
-      if (!__any_sync(FULL, active || !exhausted)) break;
+      if (!__any_sync(FULL, active)) break;
       if (!active) continue;
 
       // -- one probe
-      if (reload) {
-        const int a = p & ~3;
-        const uint32_t sh = (p & 3) * 8;
-        uint32_t x[7];
-#pragma unroll
-        for (int i = 0; i < 7; i++) x[i] = ld_u32(buf + a + 4 * i);
-#pragma unroll
-        for (int i = 0; i < 6; i++) r[i] = __funnelshift_r(x[i], x[i + 1], sh);
-        reload = false;
-      }
-      uint32_t kw[6];
-      make_key(r, k, kind, kw);
+      uint32_t r[6], kw[6];
+      load_window(buf, p, r);
+      make_key_tab(sm.key_mask, r, k, kind, kw);
       const uint32_t idx = (key_hash(kw[0], kw[1], kw[2], kw[3], kw[4], kw[5]) + poff) & V.slot_mask;
       const uint4 sa = __ldg(tab + 2 * idx);
       const uint4 sb = __ldg(tab + 2 * idx + 1);
@@ -769,11 +947,7 @@ __global__ void __launch_bounds__(THREADS, 2) wp_encode_kernel(EncodeParams P) {
 
       // -- apply the piece (fast.cpp:66-91)
       bool done = false;
-      if (flags & SEG_PUNCT) {
-        sm.stage[s] = (mlen == first_len) ? mid : V.unk_id;
-        nid = 1;
-        done = true;
-      } else if (flags & SEG_HAN_FIRST) {
+      if (flags & SEG_HAN_FIRST) {
         flags = 0;
         nid = 1;
         if (mlen == 0) {
@@ -804,14 +978,13 @@ __global__ void __launch_bounds__(THREADS, 2) wp_encode_kernel(EncodeParams P) {
         kind = WP_KIND_SUFFIX;
       }
       if (done || p >= e) {
-        sm.seg_cnt[q] = static_cast<uint16_t>(nid);
+        sm.seg_e[cnt_at] = static_cast<uint16_t>(nid);
         active = false;
       } else {
         const uint32_t wlen = static_cast<uint32_t>(e - p);
         k = wlen < WP_KEY_BYTES ? wlen : WP_KEY_BYTES;
         lo = 0;
         hi = k + 1;
-        reload = true;
       }
     }
   }
@@ -823,7 +996,7 @@ __global__ void __launch_bounds__(THREADS, 2) wp_encode_kernel(EncodeParams P) {
   const uint32_t seg_hi = min(n_segs, seg_lo + R);
   {
     uint32_t sum = 0;
-    for (uint32_t i = seg_lo + lane; i < seg_hi; i += 32) sum += sm.seg_cnt[i];
+    for (uint32_t i = seg_lo + lane; i < seg_hi; i += 32) sum += sm.seg_e[i + skip];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
     if (lane == 0) sm.warp_tot[warp] = sum;
@@ -907,8 +1080,8 @@ __global__ void __launch_bounds__(THREADS, 2) wp_encode_kernel(EncodeParams P) {
     unsigned long long run = sm.tile_base + warp_base;
     for (uint32_t row = seg_lo; row < seg_hi; row += 32) {
       const uint32_t i = row + lane;
-      const uint32_t cnt = i < seg_hi ? sm.seg_cnt[i] : 0u;
-      const uint32_t s = i < seg_hi ? sm.seg_start[i] : 0u;
+      const uint32_t cnt = i < seg_hi ? sm.seg_e[i + skip] : 0u;
+      const uint32_t s = i < seg_hi ? (sm.seg_s[i] & POS_MASK) : 0u;
       uint32_t incl = cnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
