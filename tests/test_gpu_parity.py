@@ -240,3 +240,22 @@ def test_handle_reuse_and_order_independence(gpu_device):
     for cut in (90000, 17, 8192, 50000, 1, 33333, 90000):
         assert np.array_equal(v.encode(text[:cut]), o.encode(text[:cut])), cut
     v.close()
+
+
+def test_several_ranges_per_call(gpu_device, monkeypatch):
+    """Large texts are encoded range by range (bounded scratch); force small ranges to cover the hand-over:
+    segments that straddle a range border, the running id offset, slow-list and look-back state resets."""
+    import wordpiece_b200
+
+    tile = wordpiece_b200.tile_bytes()
+    text, vocab = textgen.case(61, 30 * tile + 123, invalid_rate=0.004, long_run_rate=0.02, long_tokens=10)
+    exp = Oracle(vocab).encode(text)
+    v = _vocab(vocab, gpu_device)
+    for range_bytes in (tile, 3 * tile, 7 * tile + 1):
+        monkeypatch.setenv("WORDPIECE_B200_RANGE_BYTES", str(range_bytes))
+        got = v.encode(text)
+        assert np.array_equal(exp, got), range_bytes
+        assert v.stats().kernel_launches >= 3 * (len(text) // (range_bytes + tile))
+    monkeypatch.delenv("WORDPIECE_B200_RANGE_BYTES")
+    assert np.array_equal(exp, v.encode(text))
+    v.close()

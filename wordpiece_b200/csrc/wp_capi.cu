@@ -47,14 +47,7 @@ struct DeviceGuard {
   }
 };
 
-// scratch header at the start of the workspace (all zeroed before a launch)
-struct ScratchHeader {
-  unsigned int ticket;
-  unsigned int pad;
-  unsigned long long n_ids;
-  unsigned long long dirty_tiles;
-  unsigned long long long_segments;
-};
+constexpr size_t kRangeBytesMax = size_t(64) << 20;  // text bytes encoded per K1/K2/K3 round (bounds the scratch)
 
 }  // namespace
 
@@ -68,14 +61,16 @@ struct wp_vocab {
   uint32_t *d_long_entries = nullptr;
   uint8_t *d_long_bytes = nullptr;
   size_t device_bytes = 0;
-  // scratch, grown on demand
+  // scratch, grown on demand (layout: see Workspace below)
   uint8_t *d_work = nullptr;
   size_t work_bytes = 0;
+  wp::CallCounters *d_call = nullptr;
+  int sm_count = 0;
   uint8_t *d_text = nullptr;  // staging for the host-buffer entry points
   size_t text_cap = 0;
   int32_t *d_ids = nullptr;
   size_t ids_cap = 0;
-  ScratchHeader *h_header = nullptr;  // pinned
+  wp::CallCounters *h_call = nullptr;  // pinned
   wp_stats stats{};
 };
 
@@ -109,62 +104,148 @@ wp_status upload(wp_vocab *v) {
   WP_CUDA(cudaMemcpy(v->d_long_bytes, h.long_bytes.data(), b_bytes, cudaMemcpyHostToDevice));
   v->device_bytes = b_slots + b_ref + b_ent + b_bytes;
   WP_CUDA(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
-  WP_CUDA(cudaMallocHost(&v->h_header, sizeof(ScratchHeader)));
+  WP_CUDA(cudaMallocHost(&v->h_call, sizeof(wp::CallCounters)));
+  WP_CUDA(cudaMalloc(&v->d_call, sizeof(wp::CallCounters)));
+  WP_CUDA(cudaDeviceGetAttribute(&v->sm_count, cudaDevAttrMultiProcessorCount, v->device));
   return WP_OK;
 }
 
-wp_status ensure_work(wp_vocab *v, size_t n_tiles) {
-  const size_t need = sizeof(ScratchHeader) + n_tiles * sizeof(unsigned long long);
+// Scratch of one range of `range_bytes` text bytes.  Capacities are the exact worst cases, so the only
+// overflow that can happen is the id spill of segments walked from global memory (words longer than a
+// tile's window may be arbitrarily long); `spill_ids` bounds that part and the caller retries with more.
+struct Workspace {
+  size_t zero_bytes;     // counters + look-back words, zeroed before every range
+  size_t off_tile_state, off_block_state, off_seg, off_slow, off_tok, total;
+  uint32_t n_tiles, n_scatter_blocks, seg_cap, slow_cap, tok_cap;
+};
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+Workspace plan_workspace(size_t range_bytes, size_t spill_ids) {
+  Workspace w{};
+  const size_t tile = wp::encode_tile_bytes();
+  w.n_tiles = static_cast<uint32_t>((range_bytes + tile - 1) / tile);
+  const size_t padded = static_cast<size_t>(w.n_tiles) * tile;
+  w.seg_cap = static_cast<uint32_t>(padded);                  // a segment has at least one byte
+  w.slow_cap = static_cast<uint32_t>(padded / 2 + 1024);      // an unsettled segment has at least two
+  size_t tok = padded + 4096 + spill_ids;                     // ids <= bytes of the unsettled segments, + spill
+  if (tok > 0xFFFFFFF0ull) tok = 0xFFFFFFF0ull;
+  w.tok_cap = static_cast<uint32_t>(tok);
+  w.n_scatter_blocks = static_cast<uint32_t>((w.seg_cap + wp::scatter_block_segments() - 1) / wp::scatter_block_segments());
+  size_t off = align_up(sizeof(wp::RangeCounters), 256);
+  w.off_tile_state = off;
+  off += static_cast<size_t>(w.n_tiles) * 8;
+  w.off_block_state = off;
+  off += static_cast<size_t>(w.n_scatter_blocks) * 8;
+  w.zero_bytes = off;
+  off = align_up(off, 256);
+  w.off_seg = off;
+  off = align_up(off + static_cast<size_t>(w.seg_cap) * 4, 256);
+  w.off_slow = off;
+  off = align_up(off + static_cast<size_t>(w.slow_cap) * sizeof(wp::SlowEntry), 256);
+  w.off_tok = off;
+  off = align_up(off + static_cast<size_t>(w.tok_cap) * 4, 256);
+  w.total = off;
+  return w;
+}
+
+wp_status ensure_work(wp_vocab *v, size_t need) {
   if (need > v->work_bytes) {
     if (v->d_work) cudaFree(v->d_work);
     v->d_work = nullptr;
     v->work_bytes = 0;
-    const size_t cap = need + need / 2 + 4096;
-    WP_CUDA(cudaMalloc(&v->d_work, cap));
-    v->work_bytes = cap;
+    WP_CUDA(cudaMalloc(&v->d_work, need));
+    v->work_bytes = need;
   }
   return WP_OK;
 }
 
-// Enqueue scratch reset + kernel on `stream`.  No synchronisation.
+struct EnqueueInfo {
+  uint32_t n_tiles = 0;
+  uint32_t n_ranges = 0;
+  uint64_t launches = 0;
+};
+
+// Enqueue the kernels for a whole text on `stream`: K1/K2/K3 per range of at most kRangeBytesMax bytes.
+// No synchronisation.  The running id count ends up in d_call->ids_total[n_ranges & 1].
 wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_t *d_ids, size_t capacity,
-                         cudaStream_t stream, uint32_t *n_tiles_out) {
-  const uint32_t tile = wp::encode_tile_bytes();
+                         cudaStream_t stream, size_t spill_ids, EnqueueInfo *info) {
+  const size_t tile = wp::encode_tile_bytes();
   const size_t n_tiles = (n_bytes + tile - 1) / tile;
   if (n_tiles > 0x7FFFFFFFull) return fail(WP_ERR_INVALID_ARG, "text too large for one call (> 2^31 tiles)");
-  wp_status st = ensure_work(v, n_tiles);
+  size_t range_max = kRangeBytesMax;
+  if (const char *e = std::getenv("WORDPIECE_B200_RANGE_BYTES")) {  // test hook: force several ranges on small texts
+    const long long x = std::atoll(e);
+    if (x > 0) range_max = (static_cast<size_t>(x) + tile - 1) / tile * tile;
+  }
+  const size_t range_bytes = n_bytes < range_max ? n_bytes : range_max;
+  const Workspace w = plan_workspace(range_bytes, spill_ids ? spill_ids : range_bytes + tile);
+  wp_status st = ensure_work(v, w.total);
   if (st != WP_OK) return st;
-  const size_t reset = sizeof(ScratchHeader) + n_tiles * sizeof(unsigned long long);
-  WP_CUDA(cudaMemsetAsync(v->d_work, 0, reset, stream));
-  ScratchHeader *hdr = reinterpret_cast<ScratchHeader *>(v->d_work);
+  WP_CUDA(cudaMemsetAsync(v->d_call, 0, sizeof(wp::CallCounters), stream));
   wp::EncodeParams P{};
   P.vocab = device_view(v);
   P.text = static_cast<const uint8_t *>(d_text);
   P.n_bytes = n_bytes;
   P.ids = d_ids;
   P.capacity = capacity;
-  P.n_tiles = static_cast<uint32_t>(n_tiles);
-  P.ticket = &hdr->ticket;
-  P.n_ids_out = &hdr->n_ids;
-  P.stat_dirty_tiles = &hdr->dirty_tiles;
-  P.stat_long_segments = &hdr->long_segments;
-  P.tile_state = reinterpret_cast<unsigned long long *>(v->d_work + sizeof(ScratchHeader));
-  WP_CUDA(wp::launch_encode(P, stream));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  *n_tiles_out = static_cast<uint32_t>(n_tiles);
+  P.call = v->d_call;
+  P.counters = reinterpret_cast<wp::RangeCounters *>(v->d_work);
+  P.tile_state = reinterpret_cast<unsigned long long *>(v->d_work + w.off_tile_state);
+  P.block_state = reinterpret_cast<unsigned long long *>(v->d_work + w.off_block_state);
+  P.seg_result = reinterpret_cast<uint32_t *>(v->d_work + w.off_seg);
+  P.seg_capacity = w.seg_cap;
+  P.slow = reinterpret_cast<wp::SlowEntry *>(v->d_work + w.off_slow);
+  P.slow_capacity = w.slow_cap;
+  P.tok = reinterpret_cast<int32_t *>(v->d_work + w.off_tok);
+  P.tok_capacity = w.tok_cap;
+  P.n_scatter_blocks = w.n_scatter_blocks;
+  uint64_t launches = 0;
+  uint32_t range = 0;
+  for (size_t first = 0; first < n_tiles; first += w.n_tiles, range++) {
+    const size_t count = n_tiles - first < w.n_tiles ? n_tiles - first : w.n_tiles;
+    WP_CUDA(cudaMemsetAsync(v->d_work, 0, w.zero_bytes, stream));
+    P.first_tile = static_cast<uint32_t>(first);
+    P.n_tiles = static_cast<uint32_t>(count);
+    P.range_parity = range & 1u;
+    WP_CUDA(wp::launch_encode_range(P, v->sm_count, stream, &launches));
+  }
+  g_launches.fetch_add(launches, std::memory_order_relaxed);
+  info->n_tiles = static_cast<uint32_t>(n_tiles);
+  info->n_ranges = range;
+  info->launches = launches;
   return WP_OK;
 }
 
-wp_status finish_stats(wp_vocab *v, size_t n_bytes, uint32_t n_tiles, cudaStream_t stream) {
-  WP_CUDA(cudaMemcpyAsync(v->h_header, v->d_work, sizeof(ScratchHeader), cudaMemcpyDeviceToHost, stream));
+// Wait for the enqueued call and collect its counters.  *overflow tells the caller to retry with a larger spill.
+wp_status finish_stats(wp_vocab *v, size_t n_bytes, const EnqueueInfo &info, cudaStream_t stream, bool *overflow) {
+  WP_CUDA(cudaMemcpyAsync(v->h_call, v->d_call, sizeof(wp::CallCounters), cudaMemcpyDeviceToHost, stream));
   WP_CUDA(cudaStreamSynchronize(stream));
   v->stats.n_bytes = n_bytes;
-  v->stats.n_ids = v->h_header->n_ids;
-  v->stats.n_tiles = n_tiles;
-  v->stats.dirty_tiles = v->h_header->dirty_tiles;
-  v->stats.long_segments = v->h_header->long_segments;
-  v->stats.kernel_launches = 1;
+  v->stats.n_ids = v->h_call->ids_total[info.n_ranges & 1u];
+  v->stats.n_tiles = info.n_tiles;
+  v->stats.dirty_tiles = v->h_call->dirty_tiles;
+  v->stats.long_segments = v->h_call->long_segments;
+  v->stats.kernel_launches = info.launches;
+  *overflow = v->h_call->overflow != 0;
   return WP_OK;
+}
+
+// enqueue + wait, retrying once with a spill as large as the text if a walked segment outgrew the default
+wp_status run_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_t *d_ids, size_t capacity,
+                     cudaStream_t stream) {
+  size_t spill = 0;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    EnqueueInfo info;
+    wp_status st = enqueue_encode(v, d_text, n_bytes, d_ids, capacity, stream, spill, &info);
+    if (st != WP_OK) return st;
+    bool overflow = false;
+    st = finish_stats(v, n_bytes, info, stream, &overflow);
+    if (st != WP_OK) return st;
+    if (!overflow) return WP_OK;
+    spill = n_bytes + 4096;
+  }
+  return fail(WP_ERR_CUDA, "internal scratch overflow");
 }
 
 wp_status create_common(wp_vocab *v, const char *const *tokens, const size_t *lens, size_t n, int device,
@@ -260,7 +341,8 @@ void wp_vocab_destroy(wp_vocab *v) {
     cudaFree(v->d_work);
     cudaFree(v->d_text);
     cudaFree(v->d_ids);
-    if (v->h_header) cudaFreeHost(v->h_header);
+    if (v->h_call) cudaFreeHost(v->h_call);
+    cudaFree(v->d_call);
     if (v->stream) cudaStreamDestroy(v->stream);
   }
   delete v;
@@ -289,12 +371,12 @@ wp_status wp_encode_device_async(wp_vocab *v, const void *d_text, size_t n_bytes
     if (d_n_ids) WP_CUDA(cudaMemsetAsync(d_n_ids, 0, sizeof(uint64_t), s));
     return WP_OK;
   }
-  uint32_t n_tiles = 0;
-  wp_status st = enqueue_encode(v, d_text, n_bytes, d_ids, capacity, s, &n_tiles);
+  EnqueueInfo info;
+  wp_status st = enqueue_encode(v, d_text, n_bytes, d_ids, capacity, s, 0, &info);
   if (st != WP_OK) return st;
   if (d_n_ids) {
-    ScratchHeader *hdr = reinterpret_cast<ScratchHeader *>(v->d_work);
-    WP_CUDA(cudaMemcpyAsync(d_n_ids, &hdr->n_ids, sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+    WP_CUDA(cudaMemcpyAsync(d_n_ids, &v->d_call->ids_total[info.n_ranges & 1u], sizeof(uint64_t),
+                            cudaMemcpyDeviceToDevice, s));
   }
   return WP_OK;
 }
@@ -311,10 +393,7 @@ wp_status wp_encode_device(wp_vocab *v, const void *d_text, size_t n_bytes, int3
     v->stats = wp_stats{};
     return WP_OK;
   }
-  uint32_t n_tiles = 0;
-  wp_status st = enqueue_encode(v, d_text, n_bytes, d_ids, capacity, s, &n_tiles);
-  if (st != WP_OK) return st;
-  st = finish_stats(v, n_bytes, n_tiles, s);
+  wp_status st = run_encode(v, d_text, n_bytes, d_ids, capacity, s);
   if (st != WP_OK) return st;
   *n_ids = static_cast<size_t>(v->stats.n_ids);
   if (v->stats.n_ids > capacity) return fail(WP_ERR_CAPACITY, "id buffer too small");
@@ -351,10 +430,7 @@ wp_status wp_encode_into(wp_vocab *v, const char *text, size_t n_bytes, int32_t 
     v->ids_cap = want;
   }
   WP_CUDA(cudaMemcpyAsync(v->d_text, text, n_bytes, cudaMemcpyHostToDevice, v->stream));
-  uint32_t n_tiles = 0;
-  wp_status st = enqueue_encode(v, v->d_text, n_bytes, v->d_ids, v->ids_cap, v->stream, &n_tiles);
-  if (st != WP_OK) return st;
-  st = finish_stats(v, n_bytes, n_tiles, v->stream);
+  wp_status st = run_encode(v, v->d_text, n_bytes, v->d_ids, v->ids_cap, v->stream);
   if (st != WP_OK) return st;
   *n_ids = static_cast<size_t>(v->stats.n_ids);
   if (v->stats.n_ids > capacity) return fail(WP_ERR_CAPACITY, "id buffer too small");
@@ -396,14 +472,12 @@ wp_status wp_encode(wp_vocab *v, const char *text, size_t n_bytes, int32_t **ids
       WP_CUDA(cudaMalloc(&v->d_ids, guess * sizeof(int32_t)));
       v->ids_cap = guess;
     }
-    uint32_t n_tiles = 0;
-    wp_status st = enqueue_encode(v, v->d_text, n_bytes, v->d_ids, v->ids_cap, v->stream, &n_tiles);
+    const uint64_t before = v->stats.kernel_launches;
+    wp_status st = run_encode(v, v->d_text, n_bytes, v->d_ids, v->ids_cap, v->stream);
     if (st != WP_OK) return st;
-    st = finish_stats(v, n_bytes, n_tiles, v->stream);
-    if (st != WP_OK) return st;
+    if (attempt) v->stats.kernel_launches += before;
     if (v->stats.n_ids <= v->ids_cap) break;
     guess = static_cast<size_t>(v->stats.n_ids);
-    v->stats.kernel_launches += 1;
   }
   const size_t cnt = static_cast<size_t>(v->stats.n_ids);
   int32_t *host = static_cast<int32_t *>(std::malloc(cnt ? cnt * sizeof(int32_t) : 1));

@@ -1,34 +1,40 @@
-// Fused WordPiece encode kernel for sm_100a: word split -> longest match ->
-// scan + scatter, one text tile per CTA, nothing but the text is read from HBM
-// and nothing but the ids is written to it.
+// WordPiece encode kernels for sm_100a: word split -> longest match -> scan +
+// scatter.  Text is read from HBM once (plus the bytes of the ~20 % of words
+// that need more than one probe); ids are written once; the intermediates are a
+// 4-byte result per segment and a 16-byte entry per unsettled segment.
 //
-// What it reproduces (gleb-kov/wordpiece):
+// What they reproduce (gleb-kov/wordpiece):
 //   utils.cpp:37-79 / utf8.cpp:130-147   strict UTF-8 decode, invalid bytes dropped
 //   utf8.cpp:10-29                       space / punctuation / Han classes
 //   fast.cpp:38-41                       word-initial positions
 //   fast.cpp:43-99                       the greedy longest-match worker with
 //                                        whole-word UNK roll-back
-//   fast.cpp:101-138                     chunk + concat (here: tiles + one
-//                                        decoupled look-back scan)
+//   fast.cpp:101-138                     chunk + concat (here: tiles + decoupled
+//                                        look-back scans)
 //
-// Stages inside the kernel (DESIGN.md has the full account):
-//   S1 split   : a tile (8 KB + halo) is staged in shared memory with 16-byte
-//                loads; each thread classifies a 32-byte chunk into bit masks
-//                (valid lead / space / punct / Han), tiles holding invalid UTF-8
-//                are compacted in shared memory, and segment starts ("safe
-//                starts") fall out of a few mask operations.
-//   S2 match   : segment starts are compacted into a list; every lane pulls
-//                segments from it and runs the greedy matcher as a FLATTENED
-//                state machine — one table probe per loop iteration, whatever
-//                the lane is doing (first whole-window probe, binary-search
-//                step, next piece, collision) — so a warp stays converged on
-//                the probe.  Table: hashed trie of wp_table.h.
-//   S3 scatter : per-segment id counts -> warp/block scan -> decoupled
-//                look-back across tiles -> ids copied from the shared staging
-//                area to their final positions, one segment per lane so that a
-//                warp's stores land in a few adjacent sectors.
-//   A segment that does not end inside the tile's window (at most one per tile)
-//   is walked straight from global memory by one thread (count, then emit).
+// K1 wp_split_kernel (one 4 KB tile per CTA)
+//   S1 split : the tile + halo is staged in shared memory with 16-byte loads;
+//              each thread classifies a 32-byte chunk into bit masks (valid lead
+//              / space / punct / Han) with SWAR arithmetic; tiles holding invalid
+//              UTF-8 are compacted in shared memory; segment starts and ends
+//              ("safe starts") fall out of mask operations and are
+//              compacted into lists in text order.
+//   S2a probe: one whole-window probe per segment into the hashed-trie table
+//              (wp_table.h), uniform work for every lane.  It settles every
+//              segment that is a single token (~80 % of English words) — its id
+//              goes straight to seg_result[] — and appends the rest to the
+//              global slow list.
+// K2 wp_match_kernel (whole GPU, no tiles, no barriers)
+//   S2b match: every lane owns many slow segments and runs the greedy matcher as
+//              a FLATTENED state machine — one table probe per loop iteration,
+//              whatever the lane is doing (binary-search step, next piece,
+//              collision) — so a warp stays converged on the probe and chains of
+//              very different length average out over a lane's share.  Segments
+//              that left their tile's window or hold invalid UTF-8 are walked
+//              from global memory by the exact byte-wise lane (walk_segment).
+// K3 wp_scatter_kernel
+//   S3 scatter: per-segment id counts -> block scan -> decoupled look-back ->
+//              ids staged in shared memory and written out coalesced.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -38,9 +44,9 @@
 namespace wp {
 
 // ------------------------------------------------------------------ geometry
-constexpr int TILE = 4096;                       // text bytes owned by one CTA
+constexpr int TILE = 4096;                       // text bytes owned by one CTA of K1
 constexpr int CHUNK = 32;                        // bytes classified by one thread
-constexpr int THREADS = 192;                     // 6 warps; 4 CTAs per SM (shared memory bound)
+constexpr int THREADS = 160;                     // K1: 5 warps
 constexpr int HALO = 256;                        // classified bytes past the tile (segment completion)
 constexpr int LOOKAHEAD = 32;                    // loaded, not classified (UTF-8 validation look-ahead)
 constexpr int LEFT = 16;                         // bytes before the tile (ownership of leading continuation bytes)
@@ -49,22 +55,29 @@ constexpr int NCHUNK = WINDOW / CHUNK;           // 136
 constexpr int OWNED_CHUNKS = TILE / CHUNK;       // 128
 constexpr int RAW_BYTES = LEFT + WINDOW + LOOKAHEAD;  // 4400
 constexpr int WARPS = THREADS / 32;
-constexpr int32_t LONG_NONE = -1;
+constexpr int MAX_TILE_SLOW = TILE / 2 + 8;      // slow segments have >= 2 bytes
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 constexpr uint32_t POS_MASK = 0x3FFFu;           // window positions fit 14 bits
-constexpr uint32_t SLOW_FIRST_MISSED = 0x8000u;  // slow-list flag: the whole-window probe already missed
+constexpr uint32_t SLOW_FIRST_MISSED = 0x8000u;  // tile slow-list flag: the whole-window probe already missed
+constexpr uint32_t SLOW_WALK = 0x4000u;          // tile slow-list flag: segment leaves the window
+
+constexpr int MATCH_THREADS = 256;               // K2
+constexpr int SCATTER_THREADS = 256;             // K3
+constexpr int SCATTER_ITEMS = 8;                 // segments per thread and block iteration
+constexpr int SCATTER_SEGS = SCATTER_THREADS * SCATTER_ITEMS;  // 2048
+constexpr int SCATTER_STAGE = 6144;              // ids staged in shared memory per block iteration
 
 static_assert(RAW_BYTES % 16 == 0, "raw buffer is loaded in 16-byte units");
 static_assert(WP_KEY_BYTES + 4 <= LOOKAHEAD, "key window reads stay inside the loaded bytes");
 static_assert(NCHUNK + 1 <= THREADS, "one thread per chunk in the classification and compaction passes");
 static_assert(WINDOW <= static_cast<int>(POS_MASK), "positions must fit the packed list entries");
+static_assert(TILE <= 4096, "segment ordinals must fit 12 bits of the tile slow list");
 
 struct __align__(16) TileSmem {
   uint8_t raw[RAW_BYTES];              // [0,LEFT) left halo, then the window, then look-ahead
-  int32_t stage[WINDOW + 8];           // ids of the segment starting at byte s live at stage[s..s+cnt)
   uint16_t seg_s[TILE];                // owned segment k (text order): start position | class << 14
-  uint16_t seg_e[WINDOW + 64];         // j-th segment end in the window; entry k+skip is reused as id count of segment k
-  uint16_t slow[TILE];                 // segments the whole-window probe did not settle
+  uint16_t seg_e[WINDOW + 64];         // j-th segment end in the window
+  uint16_t slow[MAX_TILE_SLOW];        // segments the whole-window probe did not settle: ordinal | flags
   uint32_t m_lead[NCHUNK + 1];         // valid lead bytes
   uint32_t m_space[NCHUNK + 1];
   uint32_t m_punct[NCHUNK + 1];
@@ -75,18 +88,15 @@ struct __align__(16) TileSmem {
   uint8_t spill[NCHUNK + 1];           // bytes by which the chunk's last sequence runs into the next chunk
   uint4 key_mask[2 * (WP_KEY_BYTES + 1)];  // row k: masks of the six key words for a k-byte key, then k << 16
   uint32_t warp_sums[WARPS];
-  uint32_t warp_tot[WARPS];
   uint32_t tile_index;
   uint32_t prev_class;                 // class of the last valid char before the tile
   uint32_t left_spill;                 // bytes of the tile start covered by a sequence that began before it
   uint32_t n_segs;                     // owned segments in this tile
   uint32_t n_ends;                     // segment ends found in the window
   uint32_t n_slow;                     // entries of slow[]
-  uint32_t next_slow;                  // work dispenser of the slow lane
-  int32_t long_start;                  // window position of the segment that leaves the window, or LONG_NONE
-  uint32_t long_count;
-  int32_t long_unk_at;
-  unsigned long long tile_base;        // ids produced by all earlier tiles
+  uint32_t slow_base;                  // first global slow index of this tile
+  uint32_t tok_base;                   // first id-scratch slot reserved for this tile
+  unsigned long long seg_base;         // segments of all earlier tiles of the range
 };
 
 // ------------------------------------------------------------------- helpers
@@ -541,7 +551,8 @@ __device__ __forceinline__ void classify_chunk(TileSmem &sm, const uint8_t *buf,
 }
 
 // block-wide exclusive scan of one value per thread; returns the exclusive prefix, *total = sum
-__device__ __forceinline__ uint32_t block_exclusive_scan(TileSmem &sm, uint32_t v, uint32_t *total) {
+template <int NWARPS>
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t *warp_sums, uint32_t v, uint32_t *total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t incl = v;
 #pragma unroll
@@ -550,17 +561,53 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(TileSmem &sm, uint32_t 
     if (lane >= o) incl += y;
   }
   __syncthreads();  // warp_sums may still be in use by an earlier scan
-  if (lane == 31) sm.warp_sums[warp] = incl;
+  if (lane == 31) warp_sums[warp] = incl;
   __syncthreads();
   uint32_t wbase = 0, tot = 0;
 #pragma unroll
-  for (int wi = 0; wi < WARPS; wi++) {
-    const uint32_t ws = sm.warp_sums[wi];
+  for (int wi = 0; wi < NWARPS; wi++) {
+    const uint32_t ws = warp_sums[wi];
     if (wi < warp) wbase += ws;
     tot += ws;
   }
   *total = tot;
   return wbase + incl - v;
+}
+
+// Decoupled look-back over a chain of units (tiles of K1, blocks of K3), run by
+// one full warp.  state[i] = flag << 62 | value; flag 1 = the unit's own total,
+// 2 = inclusive prefix.  Publishes `total` for unit `index` and returns the sum
+// over all earlier units.  Units are handed out in launch order by a ticket, so
+// every predecessor is already running: the spin always ends.
+__device__ __forceinline__ unsigned long long lookback(volatile unsigned long long *state, uint32_t index,
+                                                       unsigned long long total, int lane) {
+  constexpr unsigned long long VALUE_MASK = (1ull << 62) - 1;
+  unsigned long long base = 0;
+  if (index == 0) {
+    if (lane == 0) state[0] = (2ull << 62) | total;
+    return 0;
+  }
+  if (lane == 0) state[index] = (1ull << 62) | total;
+  long long pred = static_cast<long long>(index) - 1 - lane;  // lane i looks at unit index-1-i
+  for (;;) {
+    unsigned long long sv = 2ull << 62;  // units before 0 count as a zero prefix
+    if (pred >= 0) {
+      do {
+        sv = state[pred];
+      } while ((sv >> 62) == 0);
+    }
+    const uint32_t is_prefix = __ballot_sync(FULL, (sv >> 62) == 2);
+    // add the totals of the lanes before the first inclusive prefix, and that prefix
+    const int stop = is_prefix ? __ffs(is_prefix) - 1 : 31;
+    unsigned long long v = lane <= stop ? (sv & VALUE_MASK) : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    base += v;
+    if (is_prefix) break;
+    pred -= 32;
+  }
+  if (lane == 0) state[index] = (2ull << 62) | (base + total);
+  return base;
 }
 
 // 24 window bytes starting at p (any alignment) as six little-endian words
@@ -574,11 +621,49 @@ __device__ __forceinline__ void load_window(const uint8_t *buf, int p, uint32_t 
   for (int i = 0; i < 6; i++) r[i] = __funnelshift_r(x[i], x[i + 1], sh);
 }
 
-// ------------------------------------------------------------------ the kernel
+// the same from the text in global memory (bytes past the end read as spaces)
+__device__ __forceinline__ void load_window_global(const uint8_t *text, size_t n_bytes, size_t pos, uint32_t r[6]) {
+  const uint8_t *addr = text + pos;
+  if (pos + 32 <= n_bytes) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(addr) & ~static_cast<uintptr_t>(3);
+    const uint32_t sh = (reinterpret_cast<uintptr_t>(addr) & 3u) * 8u;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a);
+    uint32_t x[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) x[i] = __ldg(w + i);
+#pragma unroll
+    for (int i = 0; i < 6; i++) r[i] = __funnelshift_r(x[i], x[i + 1], sh);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const size_t q = pos + 4 * i + b;
+        v |= (q < n_bytes ? static_cast<uint32_t>(text[q]) : 0x20u) << (8 * b);
+      }
+      r[i] = v;
+    }
+  }
+}
 
-constexpr uint32_t SEG_HAN_FIRST = 1u;  // about to match the first piece of a Han-led segment
+__device__ __forceinline__ void init_key_mask(uint4 *key_mask, int tid) {
+  if (tid <= static_cast<int>(WP_KEY_BYTES)) {
+    const uint32_t k = tid;  // row k of the key mask table
+    uint32_t m[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const int nb = static_cast<int>(k) - 4 * i;
+      m[i] = nb >= 4 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
+    }
+    key_mask[2 * k] = make_uint4(m[0], m[1], m[2], m[3]);
+    key_mask[2 * k + 1] = make_uint4(m[4], m[5] & 0xFFFFu, k << 16, 0u);
+  }
+}
 
-__global__ void __launch_bounds__(THREADS, 4) wp_encode_kernel(EncodeParams P) {
+// ================================================================ K1: split
+
+__global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
   const int tid = threadIdx.x;
@@ -589,28 +674,14 @@ __global__ void __launch_bounds__(THREADS, 4) wp_encode_kernel(EncodeParams P) {
   // tiles are handed out in launch order so that a tile's predecessors are
   // always already running (decoupled look-back needs forward progress)
   if (tid == 0) {
-    sm.tile_index = atomicAdd(P.ticket, 1u);
-    sm.long_start = LONG_NONE;
-    sm.long_count = 0;
-    sm.long_unk_at = -1;
+    sm.tile_index = atomicAdd(&P.counters->split_ticket, 1u);
     sm.left_spill = 0;
     sm.n_slow = 0;
-    sm.next_slow = 0;
   }
-  if (tid <= static_cast<int>(WP_KEY_BYTES)) {
-    const uint32_t k = tid;  // row k of the key mask table
-    uint32_t m[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-      const int nb = static_cast<int>(k) - 4 * i;
-      m[i] = nb >= 4 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
-    }
-    sm.key_mask[2 * k] = make_uint4(m[0], m[1], m[2], m[3]);
-    sm.key_mask[2 * k + 1] = make_uint4(m[4], m[5] & 0xFFFFu, k << 16, 0u);
-  }
+  init_key_mask(sm.key_mask, tid);
   __syncthreads();
-  const uint32_t tile = sm.tile_index;
-  const size_t t0 = static_cast<size_t>(tile) * TILE;
+  const uint32_t rel_tile = sm.tile_index;                 // within the range
+  const size_t t0 = (static_cast<size_t>(P.first_tile) + rel_tile) * TILE;
   const size_t n = P.n_bytes;
   const size_t avail = n - t0;  // > 0
   const bool more_text = avail > static_cast<size_t>(WINDOW);
@@ -679,7 +750,7 @@ __global__ void __launch_bounds__(THREADS, 4) wp_encode_kernel(EncodeParams P) {
       sm.m_kept[tid] = kept;
     }
     uint32_t packed_len;
-    const uint32_t dst0 = block_exclusive_scan(sm, my_cnt, &packed_len);  // syncs: all chunks are in registers now
+    const uint32_t dst0 = block_exclusive_scan<WARPS>(sm.warp_sums, my_cnt, &packed_len);  // syncs: chunks are in registers
     if (tid <= NCHUNK) {
       sm.kept_scan[tid] = dst0;
       if (tid == NCHUNK) sm.kept_scan[NCHUNK + 1] = packed_len;
@@ -707,10 +778,10 @@ __global__ void __launch_bounds__(THREADS, 4) wp_encode_kernel(EncodeParams P) {
   // pairs with end k + skip, skip = 1 iff a segment of the previous tile is
   // still open at the tile border.
   {
-    uint32_t starts = 0, ends = 0, lead = 0, pu = 0, ha = 0;
+    uint32_t starts = 0, ends = 0, pu = 0, ha = 0;
     const int c = tid;
     if (c < NCHUNK) {
-      lead = sm.m_lead[c];
+      const uint32_t lead = sm.m_lead[c];
       pu = sm.m_punct[c];
       ha = sm.m_han[c];
       const uint32_t sp = sm.m_space[c];
@@ -743,7 +814,7 @@ __global__ void __launch_bounds__(THREADS, 4) wp_encode_kernel(EncodeParams P) {
       starts &= left >= CHUNK ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
     }
     uint32_t totals;
-    const uint32_t at = block_exclusive_scan(sm, __popc(starts) | (__popc(ends) << 16), &totals);
+    const uint32_t at = block_exclusive_scan<WARPS>(sm.warp_sums, __popc(starts) | (__popc(ends) << 16), &totals);
     uint32_t at_s = at & 0xFFFFu, at_e = at >> 16;
     while (starts) {
       const int j = __ffs(starts) - 1;
@@ -766,6 +837,18 @@ __global__ void __launch_bounds__(THREADS, 4) wp_encode_kernel(EncodeParams P) {
   const uint32_t n_segs = sm.n_segs;
   const uint32_t n_ends = sm.n_ends;
   const uint32_t skip = sm.prev_class != CLS_SPACE ? 1u : 0u;
+
+  // ---- segment numbering across tiles: look-back on the segment counts (warp 0)
+  if (warp == 0) {
+    const unsigned long long base = lookback(P.tile_state, rel_tile, n_segs, lane);
+    if (lane == 0) {
+      sm.seg_base = base;
+      if (rel_tile == P.n_tiles - 1) P.counters->n_segs = base + n_segs;
+      if (dirty) atomicAdd(&P.call->dirty_tiles, 1ull);
+    }
+  }
+  __syncthreads();
+  const unsigned long long seg_base = sm.seg_base;
   const uint4 *tab = reinterpret_cast<const uint4 *>(V.slots);
 
   // ---- S2a: one whole-window probe per segment, statically assigned (uniform
@@ -774,21 +857,18 @@ __global__ void __launch_bounds__(THREADS, 4) wp_encode_kernel(EncodeParams P) {
   // single-char segment; the rest go to the slow list.
   for (uint32_t base = 0; base < n_segs; base += THREADS) {
     const uint32_t k = base + tid;
-    bool slow = false, found = false;
+    uint32_t slow = 0;  // 0 = settled, else the flags of the tile slow-list entry | 1
     if (k < n_segs) {
       const uint32_t sv = sm.seg_s[k];
       const int s = static_cast<int>(sv & POS_MASK);
       const uint32_t j = k + skip;
       int e = limit;
-      bool is_long = false;
       if (j < n_ends) {
         e = sm.seg_e[j];
-      } else if (more_text) {  // leaves the window: walked from global memory by thread 0 below
-        is_long = true;
-        sm.long_start = s;
-        sm.seg_e[j] = 0;
+      } else if (more_text) {  // leaves the window: walked from global memory in K2
+        slow = SLOW_WALK | 1u;
       }
-      if (!is_long) {
+      if (!slow) {
         const uint32_t wlen = static_cast<uint32_t>(e - s);
         const uint32_t first_len = utf8_lead_len(buf[s]);
         const uint32_t k0 = wlen < WP_KEY_BYTES ? wlen : WP_KEY_BYTES;
@@ -797,6 +877,7 @@ __global__ void __launch_bounds__(THREADS, 4) wp_encode_kernel(EncodeParams P) {
         make_key_tab(sm.key_mask, r, k0, WP_KIND_PREFIX, kw);
         uint32_t idx = key_hash(kw[0], kw[1], kw[2], kw[3], kw[4], kw[5]) & V.slot_mask;
         int32_t term = WP_NO_ID;
+        bool found = false;
         for (;;) {
           const uint4 sa = __ldg(tab + 2 * idx);
           const uint4 sb = __ldg(tab + 2 * idx + 1);
@@ -811,314 +892,432 @@ __global__ void __launch_bounds__(THREADS, 4) wp_encode_kernel(EncodeParams P) {
         }
         const bool hit = found && term != WP_NO_ID && wlen <= WP_KEY_BYTES;
         if (hit || wlen == first_len) {
-          sm.stage[s] = hit ? term : V.unk_id;
-          sm.seg_e[j] = 1;
+          const unsigned long long g = seg_base + k;
+          if (g < P.seg_capacity) {
+            P.seg_result[g] = static_cast<uint32_t>((hit ? term : V.unk_id) + 1);
+          } else {
+            P.call->overflow = 1u;
+          }
         } else {
-          slow = true;
+          slow = (found ? 0u : SLOW_FIRST_MISSED) | 1u;
         }
       }
     }
-    const uint32_t slowm = __ballot_sync(FULL, slow);
+    const uint32_t slowm = __ballot_sync(FULL, slow != 0);
     if (slowm) {
       uint32_t at = 0;
       const int leader = __ffs(slowm) - 1;
       if (lane == leader) at = atomicAdd(&sm.n_slow, static_cast<uint32_t>(__popc(slowm)));
       at = __shfl_sync(FULL, at, leader);
-      if (slow) sm.slow[at + __popc(slowm & ((1u << lane) - 1u))] = static_cast<uint16_t>(k | (found ? 0u : SLOW_FIRST_MISSED));
+      if (slow) sm.slow[at + __popc(slowm & ((1u << lane) - 1u))] = static_cast<uint16_t>(k | (slow & ~1u));
     }
   }
   __syncthreads();
+
+  // ---- hand the unsettled segments to K2: 16-byte entries in the global slow
+  // list (one reservation per tile), id-scratch space reserved by byte length
+  // (a segment never has more ids than bytes).
   const uint32_t n_slow = sm.n_slow;
-
-  // ---- S2b: the slow list.  Flattened state machine: every iteration each
-  // active lane issues exactly ONE table probe for its current (piece start p,
-  // length k) — binary-search step, next piece or collision alike — so a warp
-  // stays converged on the probe.  Lanes pull work dynamically.
+  if (n_slow == 0) return;  // uniform
   {
-    bool active = false, exhausted = false;
-    int s = 0, e = 0, p = 0;
-    uint32_t cnt_at = 0, nid = 0, word_first = 0, kind = WP_KIND_PREFIX, flags = 0, first_len = 0;
-    uint32_t k = 0, lo = 0, hi = 0, poff = 0;
-    uint32_t node_w5 = 0, node_slot = 0;
-    int32_t node_term = WP_NO_ID, node_best = WP_NO_ID;
-
-    for (;;) {
-      // -- refill idle lanes (one shared-memory atomic per warp and round)
-      const bool need = !active && !exhausted;
-      const uint32_t needm = __ballot_sync(FULL, need);
-      if (needm) {
-        uint32_t base = 0;
-        const int leader = __ffs(needm) - 1;
-        if (lane == leader) base = atomicAdd(&sm.next_slow, static_cast<uint32_t>(__popc(needm)));
-        base = __shfl_sync(FULL, base, leader);
-        if (need) {
-          const uint32_t i = base + __popc(needm & ((1u << lane) - 1u));
-          if (i >= n_slow) {
-            exhausted = true;
-          } else {
-            const uint32_t ent = sm.slow[i];
-            const uint32_t q = ent & 0x1FFFu;
-            const uint32_t sv = sm.seg_s[q];
-            s = static_cast<int>(sv & POS_MASK);
-            cnt_at = q + skip;
-            e = cnt_at < n_ends ? static_cast<int>(sm.seg_e[cnt_at]) : limit;
-            first_len = utf8_lead_len(buf[s]);
-            active = true;
-            p = s;
-            nid = 0;
-            word_first = 0;
-            kind = WP_KIND_PREFIX;
-            flags = (sv >> 14) == CLS_HAN ? SEG_HAN_FIRST : 0u;
-            const uint32_t wlen = static_cast<uint32_t>(e - p);
-            const uint32_t k0 = wlen < WP_KEY_BYTES ? wlen : WP_KEY_BYTES;
-            lo = 0;
-            poff = 0;
-            if (ent & SLOW_FIRST_MISSED) {  // the whole-window probe is known to miss (k0 >= 2 here)
-              hi = k0;
-              k = k0 >> 1;
-            } else {
-              hi = k0 + 1;
-              k = k0;
-            }
-          }
-        }
-      }
-      if (!__any_sync(FULL, active)) break;
-      if (!active) continue;
-
-      // -- one probe
-      uint32_t r[6], kw[6];
-      load_window(buf, p, r);
-      make_key_tab(sm.key_mask, r, k, kind, kw);
-      const uint32_t idx = (key_hash(kw[0], kw[1], kw[2], kw[3], kw[4], kw[5]) + poff) & V.slot_mask;
-      const uint4 sa = __ldg(tab + 2 * idx);
-      const uint4 sb = __ldg(tab + 2 * idx + 1);
-      const bool occupied = slot_len(sb.y) != 0;
-      const bool match = sa.x == kw[0] && sa.y == kw[1] && sa.z == kw[2] && sa.w == kw[3] && sb.x == kw[4] &&
-                         ((sb.y ^ kw[5]) & WP_W5_KEYMASK) == 0;
-      if (occupied && !match) {  // collision: next slot, same key
-        poff++;
+    const uint32_t per = (n_slow + THREADS - 1) / THREADS;
+    const uint32_t lo = min(n_slow, static_cast<uint32_t>(tid) * per);
+    const uint32_t hi = min(n_slow, lo + per);
+    uint32_t my_len = 0, n_walk = 0;
+    for (uint32_t i = lo; i < hi; i++) {
+      const uint32_t ent = sm.slow[i];
+      const uint32_t k = ent & 0xFFFu;
+      if (dirty || (ent & SLOW_WALK)) {
+        n_walk += (ent & SLOW_WALK) ? 1u : 0u;
         continue;
       }
-      poff = 0;
-      if (match) {
-        lo = k;
-        node_w5 = sb.y;
-        node_term = static_cast<int32_t>(sb.z);
-        node_best = static_cast<int32_t>(sb.w);
-        node_slot = idx;
-      } else {
-        hi = k;
+      const uint32_t j = k + skip;
+      const int e = j < n_ends ? static_cast<int>(sm.seg_e[j]) : limit;
+      my_len += static_cast<uint32_t>(e - static_cast<int>(sm.seg_s[k] & POS_MASK));
+    }
+    uint32_t total_len;
+    uint32_t run = block_exclusive_scan<WARPS>(sm.warp_sums, my_len, &total_len);
+    if (tid == 0) {
+      sm.slow_base = atomicAdd(&P.counters->n_slow, n_slow);
+      sm.tok_base = atomicAdd(&P.counters->tok_reserved, total_len);
+    }
+    if (n_walk) atomicAdd(&P.call->long_segments, static_cast<unsigned long long>(n_walk));
+    __syncthreads();
+    const uint32_t slow_base = sm.slow_base;
+    const uint32_t tok_base = sm.tok_base;
+    if (static_cast<unsigned long long>(slow_base) + n_slow > P.slow_capacity ||
+        static_cast<unsigned long long>(tok_base) + total_len > P.tok_capacity) {
+      if (tid == 0) P.call->overflow = 1u;
+      return;  // uniform
+    }
+    for (uint32_t i = lo; i < hi; i++) {
+      const uint32_t ent = sm.slow[i];
+      const uint32_t k = ent & 0xFFFu;
+      const uint32_t sv = sm.seg_s[k];
+      int wpos = static_cast<int>(sv & POS_MASK);
+      const bool walk = dirty || (ent & SLOW_WALK);
+      uint32_t len = 0;
+      if (!walk) {
+        const uint32_t j = k + skip;
+        const int e = j < n_ends ? static_cast<int>(sm.seg_e[j]) : limit;
+        len = static_cast<uint32_t>(e - wpos);
       }
-      if (hi - lo > 1) {  // binary search for the deepest node goes on
-        k = (lo + hi) >> 1;
-        continue;
-      }
-
-      // -- the deepest node along the window is at depth lo: read the longest match off it
-      uint32_t mlen = 0;
-      int32_t mid = WP_NO_ID;
-      if (lo != 0) {
-        if (node_term != WP_NO_ID) {
-          mlen = lo;
-          mid = node_term;
-        } else if (slot_best_len(node_w5) != 0) {
-          mlen = slot_best_len(node_w5);
-          mid = node_best;
+      if (dirty) {
+        // window position -> raw window position: undo the compaction
+        int a = 0, b = NCHUNK;  // last chunk whose first surviving byte is at or before wpos
+        while (a < b) {
+          const int m = (a + b + 1) >> 1;
+          if (sm.kept_scan[m] <= static_cast<uint32_t>(wpos)) a = m; else b = m - 1;
         }
-        if (lo == WP_KEY_BYTES && slot_has_long(node_w5) && e - p > static_cast<int>(WP_KEY_BYTES)) {
-          // tokens longer than the inline key hang off this node, longest first
-          const uint32_t ref = V.long_ref[node_slot];
-          const uint32_t cnt = V.long_entries[ref];
-          for (uint32_t li = 0; li < cnt; li++) {
-            const uint32_t len = V.long_entries[ref + 1 + 3 * li];
-            if (len > static_cast<uint32_t>(e - p)) continue;
-            const uint8_t *tok = V.long_bytes + V.long_entries[ref + 3 + 3 * li];
-            uint32_t o = WP_KEY_BYTES;
-            while (o < len && buf[p + o] == tok[o]) o++;
-            if (o == len) {
-              mlen = len;
-              mid = static_cast<int32_t>(V.long_entries[ref + 2 + 3 * li]);
-              break;
-            }
-          }
-        }
+        const uint32_t kk = static_cast<uint32_t>(wpos) - sm.kept_scan[a];
+        wpos = a * CHUNK + static_cast<int>(__fns(sm.m_kept[a], 0, static_cast<int>(kk) + 1));
       }
+      const size_t pos = t0 + static_cast<size_t>(wpos);
+      SlowEntry out;
+      out.pos_lo = static_cast<uint32_t>(pos);
+      out.meta = static_cast<uint32_t>((pos >> 32) & 0xFFu) | (len << 8) | ((sv >> 14) << 24) |
+                 ((ent & SLOW_FIRST_MISSED) ? SLOW_META_MISSED : 0u) | (walk ? SLOW_META_WALK : 0u);
+      out.tok_off = tok_base + run;
+      out.cnt = 0;
+      run += len;
+      *reinterpret_cast<uint4 *>(&P.slow[slow_base + i]) = *reinterpret_cast<const uint4 *>(&out);
+      const unsigned long long g = seg_base + k;
+      if (g < P.seg_capacity) P.seg_result[g] = SEG_RESULT_SLOW | (slow_base + i);
+    }
+  }
+}
 
-      // -- apply the piece (fast.cpp:66-91)
-      bool done = false;
-      if (flags & SEG_HAN_FIRST) {
-        flags = 0;
-        nid = 1;
-        if (mlen == 0) {
-          sm.stage[s] = V.unk_id;
-          if (V.han_swallow) {
-            done = true;  // fast.cpp:85-88: begin += word_len swallows the run
+// ================================================================ K2: match
+
+constexpr uint32_t SEG_HAN_FIRST = 1u;  // about to match the first piece of a Han-led segment
+
+__global__ void __launch_bounds__(MATCH_THREADS) wp_match_kernel(EncodeParams P) {
+  __shared__ uint4 key_mask[2 * (WP_KEY_BYTES + 1)];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const DeviceVocab &V = P.vocab;
+  init_key_mask(key_mask, tid);
+  __syncthreads();
+
+  const uint32_t n_slow = min(P.counters->n_slow, P.slow_capacity);
+  const uint32_t spill_base = min(P.counters->tok_reserved, P.tok_capacity);
+  const uint32_t n_warps = gridDim.x * (MATCH_THREADS / 32);
+  const uint32_t gw = blockIdx.x * (MATCH_THREADS / 32) + (tid >> 5);
+  const uint32_t per = ((n_slow + n_warps - 1) / n_warps + 31u) & ~31u;
+  uint32_t cursor = min(n_slow, gw * per);             // warp-uniform: next unassigned entry of this warp
+  const uint32_t cursor_end = min(n_slow, cursor + per);
+  const uint4 *tab = reinterpret_cast<const uint4 *>(V.slots);
+  const TextView tv{P.text, P.n_bytes};
+
+  bool active = false, reload = false;
+  size_t seg_pos = 0;
+  uint32_t ent_index = 0, seg_len = 0, p = 0, tok_off = 0;
+  uint32_t nid = 0, word_first = 0, kind = WP_KIND_PREFIX, flags = 0, first_len = 0;
+  uint32_t k = 0, lo = 0, hi = 0, poff = 0;
+  uint32_t r[6] = {0, 0, 0, 0, 0, 0};
+  uint32_t node_w5 = 0, node_slot = 0;
+  int32_t node_term = WP_NO_ID, node_best = WP_NO_ID;
+
+  for (;;) {
+    // -- refill idle lanes with the next entries of this warp's share
+    const uint32_t needm = __ballot_sync(FULL, !active);
+    if (needm && cursor < cursor_end) {
+      const uint32_t i = cursor + __popc(needm & ((1u << lane) - 1u));
+      cursor += __popc(needm);  // may pass cursor_end; entries beyond it are simply not taken
+      if (!active && i < cursor_end) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(&P.slow[i]));
+        const uint32_t meta = raw.y;
+        seg_pos = static_cast<size_t>(raw.x) | (static_cast<size_t>(meta & 0xFFu) << 32);
+        ent_index = i;
+        if (meta & SLOW_META_WALK) {
+          // exact byte-wise lane: the segment left its tile's window or holds invalid UTF-8
+          int32_t unk_at, tmp;
+          const uint32_t cnt = walk_segment(V, tv, seg_pos, nullptr, 0, -1, &unk_at);
+          const uint32_t off = spill_base + atomicAdd(&P.counters->tok_spill, cnt);
+          uint32_t written = 0;
+          if (static_cast<unsigned long long>(off) + cnt <= P.tok_capacity) {
+            walk_segment(V, tv, seg_pos, P.tok + off, cnt, unk_at, &tmp);
+            written = cnt;
           } else {
-            word_first = 1;
-            p += static_cast<int>(first_len);
+            P.call->overflow = 1u;
           }
+          P.slow[i].tok_off = off;
+          P.slow[i].cnt = written;
         } else {
-          sm.stage[s] = mid;
-          p += static_cast<int>(mlen);
-          if (mlen == first_len) {
-            word_first = 1;  // fast.cpp:89-91: the next position follows a spacing char => new word
+          seg_len = (meta >> 8) & 0xFFFFu;
+          tok_off = raw.z;
+          first_len = utf8_lead_len(P.text[seg_pos]);
+          active = true;
+          p = 0;
+          nid = 0;
+          word_first = 0;
+          kind = WP_KIND_PREFIX;
+          flags = ((meta >> 24) & 3u) == CLS_HAN ? SEG_HAN_FIRST : 0u;
+          const uint32_t k0 = seg_len < WP_KEY_BYTES ? seg_len : WP_KEY_BYTES;
+          lo = 0;
+          poff = 0;
+          reload = true;
+          if (meta & SLOW_META_MISSED) {  // the whole-window probe is known to miss (k0 >= 2 here)
+            hi = k0;
+            k = k0 >> 1;
           } else {
-            kind = WP_KIND_SUFFIX;
+            hi = k0 + 1;
+            k = k0;
           }
         }
-      } else if (mlen == 0) {  // fast.cpp:79-88: whole-word UNK, earlier pieces rolled back
-        sm.stage[s + word_first] = V.unk_id;
-        nid = word_first + 1;
-        done = true;
-      } else {
-        sm.stage[s + nid] = mid;
-        nid++;
-        p += static_cast<int>(mlen);
-        kind = WP_KIND_SUFFIX;
-      }
-      if (done || p >= e) {
-        sm.seg_e[cnt_at] = static_cast<uint16_t>(nid);
-        active = false;
-      } else {
-        const uint32_t wlen = static_cast<uint32_t>(e - p);
-        k = wlen < WP_KEY_BYTES ? wlen : WP_KEY_BYTES;
-        lo = 0;
-        hi = k + 1;
       }
     }
-  }
-  __syncthreads();
-
-  // ---- S3a: id counts -> per-warp totals.  Warp w scatters segments [w*R, (w+1)*R).
-  const uint32_t R = ((n_segs + WARPS - 1) / WARPS + 31u) & ~31u;
-  const uint32_t seg_lo = min(n_segs, static_cast<uint32_t>(warp) * R);
-  const uint32_t seg_hi = min(n_segs, seg_lo + R);
-  {
-    uint32_t sum = 0;
-    for (uint32_t i = seg_lo + lane; i < seg_hi; i += 32) sum += sm.seg_e[i + skip];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
-    if (lane == 0) sm.warp_tot[warp] = sum;
-  }
-  __syncthreads();
-  uint32_t warp_base = 0, tile_normal = 0;
-#pragma unroll
-  for (int wi = 0; wi < WARPS; wi++) {
-    const uint32_t ws = sm.warp_tot[wi];
-    if (wi < warp) warp_base += ws;
-    tile_normal += ws;
-  }
-
-  // ---- S3b: the long segment (count pass) and the look-back across tiles (warp 0)
-  if (warp == 0) {
-    size_t long_gs = 0;
-    if (lane == 0) {
-      if (sm.long_start != LONG_NONE) {
-        // window position -> text position (compacted windows: undo the compaction)
-        int wpos = sm.long_start;
-        if (dirty) {
-          int cc = 0;
-          while (cc + 1 <= NCHUNK && sm.kept_scan[cc + 1] <= static_cast<uint32_t>(wpos)) cc++;
-          const uint32_t kk = static_cast<uint32_t>(wpos) - sm.kept_scan[cc];
-          wpos = cc * CHUNK + static_cast<int>(__fns(sm.m_kept[cc], 0, static_cast<int>(kk) + 1));
-        }
-        long_gs = t0 + static_cast<size_t>(wpos);
-        int32_t unk_at;
-        sm.long_count = walk_segment(V, tv, long_gs, nullptr, 0, -1, &unk_at);
-        sm.long_unk_at = unk_at;
-        atomicAdd(P.stat_long_segments, 1ull);
-      }
-      if (dirty) atomicAdd(P.stat_dirty_tiles, 1ull);
+    if (!__any_sync(FULL, active)) {
+      if (cursor >= cursor_end) break;
+      continue;
     }
-    __syncwarp();
-    const unsigned long long total = static_cast<unsigned long long>(tile_normal) + sm.long_count;
+    if (!active) continue;
 
-    // decoupled look-back: state = flag << 62 | value; flag 1 = tile aggregate, 2 = inclusive prefix
-    volatile unsigned long long *state = P.tile_state;
-    constexpr unsigned long long VALUE_MASK = (1ull << 62) - 1;
-    unsigned long long base = 0;
-    if (tile == 0) {
-      if (lane == 0) state[0] = (2ull << 62) | total;
+    // -- one probe
+    if (reload) {
+      load_window_global(P.text, P.n_bytes, seg_pos + p, r);
+      reload = false;
+    }
+    uint32_t kw[6];
+    make_key_tab(key_mask, r, k, kind, kw);
+    const uint32_t idx = (key_hash(kw[0], kw[1], kw[2], kw[3], kw[4], kw[5]) + poff) & V.slot_mask;
+    const uint4 sa = __ldg(tab + 2 * idx);
+    const uint4 sb = __ldg(tab + 2 * idx + 1);
+    const bool occupied = slot_len(sb.y) != 0;
+    const bool match = sa.x == kw[0] && sa.y == kw[1] && sa.z == kw[2] && sa.w == kw[3] && sb.x == kw[4] &&
+                       ((sb.y ^ kw[5]) & WP_W5_KEYMASK) == 0;
+    if (occupied && !match) {  // collision: next slot, same key
+      poff++;
+      continue;
+    }
+    poff = 0;
+    if (match) {
+      lo = k;
+      node_w5 = sb.y;
+      node_term = static_cast<int32_t>(sb.z);
+      node_best = static_cast<int32_t>(sb.w);
+      node_slot = idx;
     } else {
-      if (lane == 0) state[tile] = (1ull << 62) | total;
-      long long pred = static_cast<long long>(tile) - 1 - lane;  // lane i looks at tile-1-i
-      for (;;) {
-        unsigned long long sv = 2ull << 62;  // tiles before 0 count as a zero prefix
-        if (pred >= 0) {
-          do {
-            sv = state[pred];
-          } while ((sv >> 62) == 0);
-        }
-        const uint32_t is_prefix = __ballot_sync(FULL, (sv >> 62) == 2);
-        // add the aggregates of the lanes before the first inclusive prefix, and that prefix
-        const int stop = is_prefix ? __ffs(is_prefix) - 1 : 31;
-        unsigned long long v = lane <= stop ? (sv & VALUE_MASK) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        base += v;
-        if (is_prefix) break;
-        pred -= 32;
-      }
-      if (lane == 0) state[tile] = (2ull << 62) | (base + total);
+      hi = k;
     }
-    if (lane == 0) {
-      sm.tile_base = base;
-      if (tile == P.n_tiles - 1) *P.n_ids_out = base + total;
-      if (sm.long_start != LONG_NONE) {
-        const unsigned long long at = base + tile_normal;
-        int32_t unk_at;
-        walk_segment(V, tv, long_gs, P.ids + at, at < P.capacity ? P.capacity - at : 0ull, sm.long_unk_at, &unk_at);
+    if (hi - lo > 1) {  // binary search for the deepest node goes on
+      k = (lo + hi) >> 1;
+      continue;
+    }
+
+    // -- the deepest node along the window is at depth lo: read the longest match off it
+    uint32_t mlen = 0;
+    int32_t mid = WP_NO_ID;
+    if (lo != 0) {
+      if (node_term != WP_NO_ID) {
+        mlen = lo;
+        mid = node_term;
+      } else if (slot_best_len(node_w5) != 0) {
+        mlen = slot_best_len(node_w5);
+        mid = node_best;
       }
+      if (lo == WP_KEY_BYTES && slot_has_long(node_w5) && seg_len - p > WP_KEY_BYTES) {
+        // tokens longer than the inline key hang off this node, longest first
+        const uint32_t ref = V.long_ref[node_slot];
+        const uint32_t cnt = V.long_entries[ref];
+        const uint8_t *txt = P.text + seg_pos + p;
+        for (uint32_t li = 0; li < cnt; li++) {
+          const uint32_t len = V.long_entries[ref + 1 + 3 * li];
+          if (len > seg_len - p) continue;
+          const uint8_t *tok = V.long_bytes + V.long_entries[ref + 3 + 3 * li];
+          uint32_t o = WP_KEY_BYTES;
+          while (o < len && txt[o] == tok[o]) o++;
+          if (o == len) {
+            mlen = len;
+            mid = static_cast<int32_t>(V.long_entries[ref + 2 + 3 * li]);
+            break;
+          }
+        }
+      }
+    }
+
+    // -- apply the piece (fast.cpp:66-91)
+    bool done = false;
+    int32_t *out = P.tok + tok_off;
+    if (flags & SEG_HAN_FIRST) {
+      flags = 0;
+      nid = 1;
+      if (mlen == 0) {
+        out[0] = V.unk_id;
+        if (V.han_swallow) {
+          done = true;  // fast.cpp:85-88: begin += word_len swallows the run
+        } else {
+          word_first = 1;
+          p += first_len;
+        }
+      } else {
+        out[0] = mid;
+        p += mlen;
+        if (mlen == first_len) {
+          word_first = 1;  // fast.cpp:89-91: the next position follows a spacing char => new word
+        } else {
+          kind = WP_KIND_SUFFIX;
+        }
+      }
+    } else if (mlen == 0) {  // fast.cpp:79-88: whole-word UNK, earlier pieces rolled back
+      out[word_first] = V.unk_id;
+      nid = word_first + 1;
+      done = true;
+    } else {
+      out[nid] = mid;
+      nid++;
+      p += mlen;
+      kind = WP_KIND_SUFFIX;
+    }
+    if (done || p >= seg_len) {
+      P.slow[ent_index].cnt = nid;
+      active = false;
+    } else {
+      const uint32_t wlen = seg_len - p;
+      k = wlen < WP_KEY_BYTES ? wlen : WP_KEY_BYTES;
+      lo = 0;
+      hi = k + 1;
+      reload = true;
     }
   }
-  __syncthreads();
+}
 
-  // ---- S3c: scatter.  One segment per lane, 32 consecutive segments per row, so
-  // the stores of a row fall into a few adjacent sectors.
-  {
-    unsigned long long run = sm.tile_base + warp_base;
-    for (uint32_t row = seg_lo; row < seg_hi; row += 32) {
-      const uint32_t i = row + lane;
-      const uint32_t cnt = i < seg_hi ? sm.seg_e[i + skip] : 0u;
-      const uint32_t s = i < seg_hi ? (sm.seg_s[i] & POS_MASK) : 0u;
-      uint32_t incl = cnt;
+// ============================================================== K3: scatter
+
+struct ScatterSmem {
+  int32_t stage[SCATTER_STAGE];
+  uint32_t warp_sums[SCATTER_THREADS / 32];
+  uint32_t block_index;
+  unsigned long long base;
+};
+
+__global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParams P) {
+  __shared__ ScatterSmem sm;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const unsigned long long n_segs = min(P.counters->n_segs, static_cast<unsigned long long>(P.seg_capacity));
+  const uint32_t n_blocks = static_cast<uint32_t>((n_segs + SCATTER_SEGS - 1) / SCATTER_SEGS);
+  const unsigned long long ids_in = P.call->ids_total[P.range_parity];
+  if (n_blocks == 0) {
+    if (blockIdx.x == 0 && tid == 0) P.call->ids_total[P.range_parity ^ 1u] = ids_in;
+    return;
+  }
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sm.block_index = atomicAdd(&P.counters->scatter_ticket, 1u);
+    __syncthreads();
+    const uint32_t b = sm.block_index;
+    if (b >= n_blocks) break;
+    const unsigned long long first = static_cast<unsigned long long>(b) * SCATTER_SEGS + tid * SCATTER_ITEMS;
+
+    // per-segment id counts (fast: 1; slow: from the entry K2 completed)
+    uint32_t res[SCATTER_ITEMS], cnt[SCATTER_ITEMS], off[SCATTER_ITEMS];
+    if (first + SCATTER_ITEMS <= n_segs) {
+      const uint4 a = *reinterpret_cast<const uint4 *>(P.seg_result + first);
+      const uint4 c = *reinterpret_cast<const uint4 *>(P.seg_result + first + 4);
+      res[0] = a.x; res[1] = a.y; res[2] = a.z; res[3] = a.w;
+      res[4] = c.x; res[5] = c.y; res[6] = c.z; res[7] = c.w;
+    } else {
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += y;
-      }
-      const unsigned long long at = run + incl - cnt;
-      uint32_t maxc = cnt;
+      for (int j = 0; j < SCATTER_ITEMS; j++) res[j] = first + j < n_segs ? P.seg_result[first + j] : 0xFFFFFFFFu;
+    }
+    uint32_t mine = 0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(FULL, maxc, o));
-      for (uint32_t j = 0; j < maxc; j++) {
-        if (j < cnt && at + j < P.capacity) P.ids[at + j] = sm.stage[s + j];
+    for (int j = 0; j < SCATTER_ITEMS; j++) {
+      cnt[j] = 1;
+      off[j] = 0;
+      if (first + j >= n_segs) {
+        cnt[j] = 0;
+      } else if (res[j] & SEG_RESULT_SLOW) {
+        const uint32_t si = res[j] & ~SEG_RESULT_SLOW;
+        if (si < P.slow_capacity) {
+          const uint4 e = *reinterpret_cast<const uint4 *>(&P.slow[si]);
+          off[j] = e.z;
+          cnt[j] = e.w;
+          if (static_cast<unsigned long long>(e.z) + e.w > P.tok_capacity) cnt[j] = 0;
+        } else {
+          cnt[j] = 0;
+        }
       }
-      run += __shfl_sync(FULL, incl, 31);
+      mine += cnt[j];
+    }
+    uint32_t total;
+    uint32_t at = block_exclusive_scan<SCATTER_THREADS / 32>(sm.warp_sums, mine, &total);
+
+    if (warp == 0) {
+      const unsigned long long base = lookback(P.block_state, b, total, lane);
+      if (lane == 0) {
+        sm.base = base;
+        if (b == n_blocks - 1) P.call->ids_total[P.range_parity ^ 1u] = ids_in + base + total;
+      }
+    }
+    __syncthreads();
+    const unsigned long long out0 = ids_in + sm.base;
+
+    if (total <= SCATTER_STAGE) {
+      // stage in shared memory, then write out coalesced
+#pragma unroll
+      for (int j = 0; j < SCATTER_ITEMS; j++) {
+        if (cnt[j] == 0) continue;
+        if (res[j] & SEG_RESULT_SLOW) {
+          for (uint32_t t = 0; t < cnt[j]; t++) sm.stage[at + t] = P.tok[off[j] + t];
+        } else {
+          sm.stage[at] = static_cast<int32_t>(res[j]) - 1;
+        }
+        at += cnt[j];
+      }
+      __syncthreads();
+      for (uint32_t i = tid; i < total; i += SCATTER_THREADS) {
+        if (out0 + i < P.capacity) P.ids[out0 + i] = sm.stage[i];
+      }
+    } else {
+      // a block with unusually many ids (long words cut into many pieces): write directly
+#pragma unroll
+      for (int j = 0; j < SCATTER_ITEMS; j++) {
+        if (cnt[j] == 0) continue;
+        if (res[j] & SEG_RESULT_SLOW) {
+          for (uint32_t t = 0; t < cnt[j]; t++) {
+            if (out0 + at + t < P.capacity) P.ids[out0 + at + t] = P.tok[off[j] + t];
+          }
+        } else if (out0 + at < P.capacity) {
+          P.ids[out0 + at] = static_cast<int32_t>(res[j]) - 1;
+        }
+        at += cnt[j];
+      }
     }
   }
 }
 
 // -------------------------------------------------------------------- launch
 
-size_t encode_smem_bytes() { return sizeof(TileSmem); }
 uint32_t encode_tile_bytes() { return TILE; }
+uint32_t scatter_block_segments() { return SCATTER_SEGS; }
 
-cudaError_t launch_encode(const EncodeParams &P, cudaStream_t stream) {
-  // the opt-in to > 48 KB of dynamic shared memory is per device
+cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_t stream, uint64_t *launches) {
+  // the opt-in to > 48 KB of dynamic shared memory is per device (K1 stays below it, but keep it explicit)
   static bool configured[64] = {false};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    e = cudaFuncSetAttribute(wp_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(wp_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(sizeof(TileSmem)));
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  wp_encode_kernel<<<P.n_tiles, THREADS, sizeof(TileSmem), stream>>>(P);
-  return cudaGetLastError();
+  if (sm_count <= 0) sm_count = 148;
+  wp_split_kernel<<<P.n_tiles, THREADS, sizeof(TileSmem), stream>>>(P);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  wp_match_kernel<<<sm_count * 8, MATCH_THREADS, 0, stream>>>(P);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  wp_scatter_kernel<<<sm_count * 4, SCATTER_THREADS, 0, stream>>>(P);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (launches) *launches += 3;
+  return cudaSuccess;
 }
 
 }  // namespace wp

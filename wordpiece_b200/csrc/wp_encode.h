@@ -1,4 +1,14 @@
-// Launch interface of the fused encode kernel (wp_encode.cu).
+// Launch interface of the three encode kernels (wp_encode.cu).
+//
+//   K1 wp_split_kernel   word split + whole-window probe, one text tile per CTA
+//   K2 wp_match_kernel   greedy longest-match chains of the segments K1 could
+//                        not settle with one probe, load-balanced over the GPU
+//   K3 wp_scatter_kernel scan of per-segment id counts + scatter of the ids
+//
+// The three run back to back on one stream over one RANGE of tiles of a text
+// (a whole text, or a block of it when the host bounds the scratch memory);
+// nothing is synchronised in between — K2 and K3 read their work sizes from
+// device memory.
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -8,23 +18,67 @@
 
 namespace wp {
 
-struct EncodeParams {
-  DeviceVocab vocab;
-  const uint8_t *text;              // device, n_bytes of UTF-8
-  size_t n_bytes;                   // > 0
-  int32_t *ids;                     // device, capacity entries
-  unsigned long long capacity;
-  uint32_t n_tiles;                 // ceil(n_bytes / tile bytes)
-  // scratch, zeroed before every launch:
-  unsigned int *ticket;             // tile dispenser
-  unsigned long long *tile_state;   // n_tiles look-back words
-  unsigned long long *n_ids_out;    // total id count
-  unsigned long long *stat_dirty_tiles;
-  unsigned long long *stat_long_segments;
+// One segment that needs more than the whole-window probe (16 bytes).
+struct SlowEntry {
+  uint32_t pos_lo;   // text position of the segment start, low 32 bits
+  uint32_t meta;     // bits 0..7 pos high bits, 8..23 byte length (0 for WALK), 24..25 char class,
+                     // bit 26 whole-window probe known to miss, bit 27 WALK (walk from global memory, see K2)
+  uint32_t tok_off;  // where this segment's ids go in the id scratch (K1 for plain entries, K2 for WALK)
+  uint32_t cnt;      // number of ids (written by K2)
+};
+static_assert(sizeof(SlowEntry) == 16, "slow entries are read as one 16-byte load");
+
+constexpr uint32_t SLOW_META_MISSED = 1u << 26;
+constexpr uint32_t SLOW_META_WALK = 1u << 27;
+constexpr uint32_t SEG_RESULT_SLOW = 0x80000000u;  // seg_result: fast = id + 1, slow = this | slow index
+
+// Counters in device memory, zeroed before every range.
+struct RangeCounters {
+  unsigned int split_ticket;         // tile dispenser of K1
+  unsigned int scatter_ticket;       // block dispenser of K3
+  unsigned int n_slow;               // slow entries appended by K1
+  unsigned int tok_reserved;         // id scratch reserved by K1 (plain entries)
+  unsigned int tok_spill;            // id scratch reserved by K2 past the K1 part (WALK entries)
+  unsigned int pad;
+  unsigned long long n_segs;         // segments of the range (K1, last tile)
 };
 
-size_t encode_smem_bytes();
+// Counters in device memory, zeroed once per encode call.
+struct CallCounters {
+  unsigned long long ids_total[2];   // running id count; range r reads [r & 1] and writes [(r + 1) & 1]
+  unsigned long long dirty_tiles;
+  unsigned long long long_segments;
+  unsigned int overflow;             // set if a scratch capacity was exceeded (the host retries with more)
+  unsigned int pad;
+};
+
+struct EncodeParams {
+  DeviceVocab vocab;
+  const uint8_t *text;              // device, the whole text (tiles read their halo from it)
+  size_t n_bytes;                   // size of the whole text
+  uint32_t first_tile;              // range = tiles [first_tile, first_tile + n_tiles)
+  uint32_t n_tiles;
+  // outputs
+  int32_t *ids;                     // device, capacity entries
+  unsigned long long capacity;
+  CallCounters *call;               // K3 appends at call->ids_total[range_parity]
+  uint32_t range_parity;
+  // scratch
+  RangeCounters *counters;
+  unsigned long long *tile_state;   // n_tiles look-back words (K1), zeroed
+  unsigned long long *block_state;  // look-back words of K3, zeroed
+  uint32_t *seg_result;             // seg_capacity entries
+  uint32_t seg_capacity;
+  SlowEntry *slow;                  // slow_capacity entries
+  uint32_t slow_capacity;
+  int32_t *tok;                     // tok_capacity ids
+  uint32_t tok_capacity;
+  uint32_t n_scatter_blocks;        // size of block_state
+};
+
 uint32_t encode_tile_bytes();
-cudaError_t launch_encode(const EncodeParams &P, cudaStream_t stream);
+uint32_t scatter_block_segments();
+// Enqueue K1, K2, K3 for one range.  *launches is incremented per kernel launched.
+cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_t stream, uint64_t *launches);
 
 }  // namespace wp
