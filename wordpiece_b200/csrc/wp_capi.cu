@@ -66,6 +66,8 @@ struct wp_vocab {
   size_t work_bytes = 0;
   wp::CallCounters *d_call = nullptr;
   int sm_count = 0;
+  size_t persist_bytes = 0;  // L2 access-policy window over the slot array
+  float persist_ratio = 0.f;
   uint8_t *d_text = nullptr;  // staging for the host-buffer entry points
   size_t text_cap = 0;
   int32_t *d_ids = nullptr;
@@ -107,6 +109,23 @@ wp_status upload(wp_vocab *v) {
   WP_CUDA(cudaMallocHost(&v->h_call, sizeof(wp::CallCounters)));
   WP_CUDA(cudaMalloc(&v->d_call, sizeof(wp::CallCounters)));
   WP_CUDA(cudaDeviceGetAttribute(&v->sm_count, cudaDevAttrMultiProcessorCount, v->device));
+  {
+    // keep the probed table resident in L2 (best effort: an unsupported attribute only costs the hint)
+    int max_persist = 0, max_window = 0;
+    if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, v->device) == cudaSuccess &&
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, v->device) == cudaSuccess &&
+        max_persist > 0 && max_window > 0) {
+      size_t set_aside = b_slots < static_cast<size_t>(max_persist) ? b_slots : static_cast<size_t>(max_persist);
+      size_t current = 0;
+      cudaDeviceGetLimit(&current, cudaLimitPersistingL2CacheSize);
+      if (current >= set_aside || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside) == cudaSuccess) {
+        v->persist_bytes = b_slots < static_cast<size_t>(max_window) ? b_slots : static_cast<size_t>(max_window);
+        v->persist_ratio = static_cast<float>(set_aside) / static_cast<float>(v->persist_bytes);
+        if (v->persist_ratio > 1.f) v->persist_ratio = 1.f;
+      }
+    }
+    cudaGetLastError();
+  }
   return WP_OK;
 }
 
@@ -200,6 +219,8 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   P.tok = reinterpret_cast<int32_t *>(v->d_work + w.off_tok);
   P.tok_capacity = w.tok_cap;
   P.n_scatter_blocks = w.n_scatter_blocks;
+  P.persist_bytes = v->persist_bytes;
+  P.persist_ratio = v->persist_ratio;
   uint64_t launches = 0;
   uint32_t range = 0;
   for (size_t first = 0; first < n_tiles; first += w.n_tiles, range++) {

@@ -852,64 +852,77 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   const uint4 *tab = reinterpret_cast<const uint4 *>(V.slots);
 
   // ---- S2a: one whole-window probe per segment, statically assigned (uniform
-  // work: every lane does the same thing).  It settles every segment that is a
-  // single token (fast.cpp:66-72 hit on the first, longest candidate) and every
-  // single-char segment; the rest go to the slow list.
-  for (uint32_t base = 0; base < n_segs; base += THREADS) {
-    const uint32_t k = base + tid;
-    uint32_t slow = 0;  // 0 = settled, else the flags of the tile slow-list entry | 1
-    if (k < n_segs) {
-      const uint32_t sv = sm.seg_s[k];
-      const int s = static_cast<int>(sv & POS_MASK);
-      const uint32_t j = k + skip;
-      int e = limit;
-      if (j < n_ends) {
-        e = sm.seg_e[j];
-      } else if (more_text) {  // leaves the window: walked from global memory in K2
-        slow = SLOW_WALK | 1u;
-      }
-      if (!slow) {
-        const uint32_t wlen = static_cast<uint32_t>(e - s);
-        const uint32_t first_len = utf8_lead_len(buf[s]);
-        const uint32_t k0 = wlen < WP_KEY_BYTES ? wlen : WP_KEY_BYTES;
-        uint32_t r[6], kw[6];
-        load_window(buf, s, r);
-        make_key_tab(sm.key_mask, r, k0, WP_KIND_PREFIX, kw);
-        uint32_t idx = key_hash(kw[0], kw[1], kw[2], kw[3], kw[4], kw[5]) & V.slot_mask;
-        int32_t term = WP_NO_ID;
-        bool found = false;
-        for (;;) {
-          const uint4 sa = __ldg(tab + 2 * idx);
-          const uint4 sb = __ldg(tab + 2 * idx + 1);
-          if (slot_len(sb.y) == 0) break;
-          if (sa.x == kw[0] && sa.y == kw[1] && sa.z == kw[2] && sa.w == kw[3] && sb.x == kw[4] &&
-              ((sb.y ^ kw[5]) & WP_W5_KEYMASK) == 0) {
-            found = true;
-            term = static_cast<int32_t>(sb.z);
-            break;
-          }
-          idx = (idx + 1) & V.slot_mask;
+  // work: every lane does the same thing; two segments per lane and turn so that
+  // two table loads are in flight).  It settles every segment that is a single
+  // token (fast.cpp:66-72 hit on the first, longest candidate) and every
+  // single-char segment; the rest — and the rare probe that lands on another
+  // key's slot — go to the slow list.
+  constexpr int PER_TURN = 2;
+  for (uint32_t base = 0; base < n_segs; base += PER_TURN * THREADS) {
+    uint32_t kk[PER_TURN], slow[PER_TURN], wlen[PER_TURN], first_len[PER_TURN], kw[PER_TURN][6];
+    uint4 sa[PER_TURN], sb[PER_TURN];
+#pragma unroll
+    for (int u = 0; u < PER_TURN; u++) {
+      const uint32_t k = base + u * THREADS + tid;
+      kk[u] = k;
+      slow[u] = 0;  // 0 = settled (or no segment), else the flags of the tile slow-list entry | 1
+      wlen[u] = 0;
+      first_len[u] = 0;
+      sa[u] = make_uint4(0, 0, 0, 0);
+      sb[u] = make_uint4(0, 0, 0, 0);
+      if (k < n_segs) {
+        const uint32_t sv = sm.seg_s[k];
+        const int s = static_cast<int>(sv & POS_MASK);
+        const uint32_t j = k + skip;
+        int e = limit;
+        if (j < n_ends) {
+          e = sm.seg_e[j];
+        } else if (more_text) {  // leaves the window: walked from global memory in K2
+          slow[u] = SLOW_WALK | 1u;
         }
-        const bool hit = found && term != WP_NO_ID && wlen <= WP_KEY_BYTES;
-        if (hit || wlen == first_len) {
-          const unsigned long long g = seg_base + k;
+        if (!slow[u]) {
+          wlen[u] = static_cast<uint32_t>(e - s);
+          first_len[u] = utf8_lead_len(buf[s]);
+          const uint32_t k0 = wlen[u] < WP_KEY_BYTES ? wlen[u] : WP_KEY_BYTES;
+          uint32_t r[6];
+          load_window(buf, s, r);
+          make_key_tab(sm.key_mask, r, k0, WP_KIND_PREFIX, kw[u]);
+          const uint32_t idx = key_hash(kw[u][0], kw[u][1], kw[u][2], kw[u][3], kw[u][4], kw[u][5]) & V.slot_mask;
+          sa[u] = __ldg(tab + 2 * idx);
+          sb[u] = __ldg(tab + 2 * idx + 1);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PER_TURN; u++) {
+      if (wlen[u] != 0) {
+        const bool occupied = slot_len(sb[u].y) != 0;
+        const bool match = sa[u].x == kw[u][0] && sa[u].y == kw[u][1] && sa[u].z == kw[u][2] && sa[u].w == kw[u][3] &&
+                           sb[u].x == kw[u][4] && ((sb[u].y ^ kw[u][5]) & WP_W5_KEYMASK) == 0;
+        const int32_t term = static_cast<int32_t>(sb[u].z);
+        const bool hit = match && term != WP_NO_ID && wlen[u] <= WP_KEY_BYTES;
+        const bool single_miss = wlen[u] == first_len[u] && !occupied;  // a one-char segment that is no token
+        const bool single_dead = wlen[u] == first_len[u] && match;      // ... or only a prefix of tokens
+        if (hit || single_miss || single_dead) {
+          const unsigned long long g = seg_base + kk[u];
           if (g < P.seg_capacity) {
             P.seg_result[g] = static_cast<uint32_t>((hit ? term : V.unk_id) + 1);
           } else {
             P.call->overflow = 1u;
           }
         } else {
-          slow = (found ? 0u : SLOW_FIRST_MISSED) | 1u;
+          // miss on an empty slot: K2 may skip the whole-window probe; match or collision: K2 redoes it
+          slow[u] = (occupied ? 0u : SLOW_FIRST_MISSED) | 1u;
         }
       }
-    }
-    const uint32_t slowm = __ballot_sync(FULL, slow != 0);
-    if (slowm) {
-      uint32_t at = 0;
-      const int leader = __ffs(slowm) - 1;
-      if (lane == leader) at = atomicAdd(&sm.n_slow, static_cast<uint32_t>(__popc(slowm)));
-      at = __shfl_sync(FULL, at, leader);
-      if (slow) sm.slow[at + __popc(slowm & ((1u << lane) - 1u))] = static_cast<uint16_t>(k | (slow & ~1u));
+      const uint32_t slowm = __ballot_sync(FULL, slow[u] != 0);
+      if (slowm) {
+        uint32_t at = 0;
+        const int leader = __ffs(slowm) - 1;
+        if (lane == leader) at = atomicAdd(&sm.n_slow, static_cast<uint32_t>(__popc(slowm)));
+        at = __shfl_sync(FULL, at, leader);
+        if (slow[u]) sm.slow[at + __popc(slowm & ((1u << lane) - 1u))] = static_cast<uint16_t>(kk[u] | (slow[u] & ~1u));
+      }
     }
   }
   __syncthreads();
@@ -989,9 +1002,38 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
 
 // ================================================================ K2: match
 
-constexpr uint32_t SEG_HAN_FIRST = 1u;  // about to match the first piece of a Han-led segment
+constexpr uint32_t SEG_HAN_FIRST = 1u;   // about to match the first piece of a Han-led segment
+constexpr uint32_t SEG_KNOWN_MISS = 2u;  // the whole-window probe of the first piece is known to miss (K1 did it)
 
-__global__ void __launch_bounds__(MATCH_THREADS) wp_match_kernel(EncodeParams P) {
+// The exact byte-wise lane for one entry: the segment left its tile's window or holds invalid UTF-8.
+__device__ __noinline__ void match_walk(const EncodeParams &P, uint32_t i, size_t seg_pos, uint32_t spill_base) {
+  const TextView tv{P.text, P.n_bytes};
+  int32_t unk_at, tmp;
+  const uint32_t cnt = walk_segment(P.vocab, tv, seg_pos, nullptr, 0, -1, &unk_at);
+  const uint32_t off = spill_base + atomicAdd(&P.counters->tok_spill, cnt);
+  uint32_t written = 0;
+  if (static_cast<unsigned long long>(off) + cnt <= P.tok_capacity) {
+    walk_segment(P.vocab, tv, seg_pos, P.tok + off, cnt, unk_at, &tmp);
+    written = cnt;
+  } else {
+    P.call->overflow = 1u;
+  }
+  P.slow[i].tok_off = off;
+  P.slow[i].cnt = written;
+}
+
+// Every lane owns a long run of slow-list entries (its warp's share / 32), so
+// chains of very different length average out.  The loop is aligned on PIECES:
+//   round:  lanes without a segment take the next entry
+//           every lane loads the 24-byte window of its next piece
+//           inner loop: one table probe per iteration until every lane's piece
+//                       is settled (whole-window probe, then binary search for
+//                       the deepest trie node; a collision is one more turn)
+//           every lane reads its longest match off the deepest node and applies
+//           the piece (fast.cpp:66-91)
+// so the refill / window / apply code runs once per piece and warp, fully
+// converged, and only the short probe body repeats.
+__global__ void __launch_bounds__(MATCH_THREADS, 4) wp_match_kernel(EncodeParams P) {
   __shared__ uint4 key_mask[2 * (WP_KEY_BYTES + 1)];
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -1007,177 +1049,160 @@ __global__ void __launch_bounds__(MATCH_THREADS) wp_match_kernel(EncodeParams P)
   uint32_t cursor = min(n_slow, gw * per);             // warp-uniform: next unassigned entry of this warp
   const uint32_t cursor_end = min(n_slow, cursor + per);
   const uint4 *tab = reinterpret_cast<const uint4 *>(V.slots);
-  const TextView tv{P.text, P.n_bytes};
 
-  bool active = false, reload = false;
+  bool have = false;       // this lane holds an unfinished segment
   size_t seg_pos = 0;
   uint32_t ent_index = 0, seg_len = 0, p = 0, tok_off = 0;
   uint32_t nid = 0, word_first = 0, kind = WP_KIND_PREFIX, flags = 0, first_len = 0;
-  uint32_t k = 0, lo = 0, hi = 0, poff = 0;
-  uint32_t r[6] = {0, 0, 0, 0, 0, 0};
-  uint32_t node_w5 = 0, node_slot = 0;
-  int32_t node_term = WP_NO_ID, node_best = WP_NO_ID;
 
   for (;;) {
-    // -- refill idle lanes with the next entries of this warp's share
-    const uint32_t needm = __ballot_sync(FULL, !active);
+    // -- refill: lanes without a segment take the next entries of this warp's share
+    const uint32_t needm = __ballot_sync(FULL, !have);
     if (needm && cursor < cursor_end) {
       const uint32_t i = cursor + __popc(needm & ((1u << lane) - 1u));
       cursor += __popc(needm);  // may pass cursor_end; entries beyond it are simply not taken
-      if (!active && i < cursor_end) {
+      if (!have && i < cursor_end) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(&P.slow[i]));
         const uint32_t meta = raw.y;
         seg_pos = static_cast<size_t>(raw.x) | (static_cast<size_t>(meta & 0xFFu) << 32);
-        ent_index = i;
         if (meta & SLOW_META_WALK) {
-          // exact byte-wise lane: the segment left its tile's window or holds invalid UTF-8
-          int32_t unk_at, tmp;
-          const uint32_t cnt = walk_segment(V, tv, seg_pos, nullptr, 0, -1, &unk_at);
-          const uint32_t off = spill_base + atomicAdd(&P.counters->tok_spill, cnt);
-          uint32_t written = 0;
-          if (static_cast<unsigned long long>(off) + cnt <= P.tok_capacity) {
-            walk_segment(V, tv, seg_pos, P.tok + off, cnt, unk_at, &tmp);
-            written = cnt;
-          } else {
-            P.call->overflow = 1u;
-          }
-          P.slow[i].tok_off = off;
-          P.slow[i].cnt = written;
+          match_walk(P, i, seg_pos, spill_base);
         } else {
+          ent_index = i;
           seg_len = (meta >> 8) & 0xFFFFu;
           tok_off = raw.z;
           first_len = utf8_lead_len(P.text[seg_pos]);
-          active = true;
+          have = true;
           p = 0;
           nid = 0;
           word_first = 0;
           kind = WP_KIND_PREFIX;
-          flags = ((meta >> 24) & 3u) == CLS_HAN ? SEG_HAN_FIRST : 0u;
-          const uint32_t k0 = seg_len < WP_KEY_BYTES ? seg_len : WP_KEY_BYTES;
-          lo = 0;
-          poff = 0;
-          reload = true;
-          if (meta & SLOW_META_MISSED) {  // the whole-window probe is known to miss (k0 >= 2 here)
-            hi = k0;
-            k = k0 >> 1;
-          } else {
-            hi = k0 + 1;
-            k = k0;
-          }
+          flags = (((meta >> 24) & 3u) == CLS_HAN ? SEG_HAN_FIRST : 0u) | ((meta & SLOW_META_MISSED) ? SEG_KNOWN_MISS : 0u);
         }
       }
     }
-    if (!__any_sync(FULL, active)) {
+    if (!__any_sync(FULL, have)) {
       if (cursor >= cursor_end) break;
       continue;
     }
-    if (!active) continue;
 
-    // -- one probe
-    if (reload) {
+    // -- piece start: window bytes and search bounds
+    uint32_t r[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t k = 0, lo = 0, hi = 0, poff = 0;
+    uint32_t node_w5 = 0, node_slot = 0;
+    int32_t node_term = WP_NO_ID, node_best = WP_NO_ID;
+    bool searching = have;
+    if (have) {
       load_window_global(P.text, P.n_bytes, seg_pos + p, r);
-      reload = false;
-    }
-    uint32_t kw[6];
-    make_key_tab(key_mask, r, k, kind, kw);
-    const uint32_t idx = (key_hash(kw[0], kw[1], kw[2], kw[3], kw[4], kw[5]) + poff) & V.slot_mask;
-    const uint4 sa = __ldg(tab + 2 * idx);
-    const uint4 sb = __ldg(tab + 2 * idx + 1);
-    const bool occupied = slot_len(sb.y) != 0;
-    const bool match = sa.x == kw[0] && sa.y == kw[1] && sa.z == kw[2] && sa.w == kw[3] && sb.x == kw[4] &&
-                       ((sb.y ^ kw[5]) & WP_W5_KEYMASK) == 0;
-    if (occupied && !match) {  // collision: next slot, same key
-      poff++;
-      continue;
-    }
-    poff = 0;
-    if (match) {
-      lo = k;
-      node_w5 = sb.y;
-      node_term = static_cast<int32_t>(sb.z);
-      node_best = static_cast<int32_t>(sb.w);
-      node_slot = idx;
-    } else {
-      hi = k;
-    }
-    if (hi - lo > 1) {  // binary search for the deepest node goes on
-      k = (lo + hi) >> 1;
-      continue;
+      const uint32_t wlen = seg_len - p;
+      const uint32_t k0 = wlen < WP_KEY_BYTES ? wlen : WP_KEY_BYTES;
+      if (flags & SEG_KNOWN_MISS) {  // k0 >= 2 here
+        hi = k0;
+        k = k0 >> 1;
+        flags &= ~SEG_KNOWN_MISS;
+      } else {
+        hi = k0 + 1;
+        k = k0;
+      }
     }
 
-    // -- the deepest node along the window is at depth lo: read the longest match off it
-    uint32_t mlen = 0;
-    int32_t mid = WP_NO_ID;
-    if (lo != 0) {
-      if (node_term != WP_NO_ID) {
-        mlen = lo;
-        mid = node_term;
-      } else if (slot_best_len(node_w5) != 0) {
-        mlen = slot_best_len(node_w5);
-        mid = node_best;
+    // -- probes: deepest trie node along the window (existence is monotone in the depth)
+    while (__any_sync(FULL, searching)) {
+      if (searching) {
+        uint32_t kw[6];
+        make_key_tab(key_mask, r, k, kind, kw);
+        const uint32_t idx = (key_hash(kw[0], kw[1], kw[2], kw[3], kw[4], kw[5]) + poff) & V.slot_mask;
+        const uint4 sa = __ldg(tab + 2 * idx);
+        const uint4 sb = __ldg(tab + 2 * idx + 1);
+        const bool occupied = slot_len(sb.y) != 0;
+        const bool match = sa.x == kw[0] && sa.y == kw[1] && sa.z == kw[2] && sa.w == kw[3] && sb.x == kw[4] &&
+                           ((sb.y ^ kw[5]) & WP_W5_KEYMASK) == 0;
+        if (occupied && !match) {
+          poff++;  // collision: next slot, same key
+        } else {
+          poff = 0;
+          if (match) {
+            lo = k;
+            node_w5 = sb.y;
+            node_term = static_cast<int32_t>(sb.z);
+            node_best = static_cast<int32_t>(sb.w);
+            node_slot = idx;
+          } else {
+            hi = k;
+          }
+          k = (lo + hi) >> 1;
+          searching = hi - lo > 1;
+        }
       }
-      if (lo == WP_KEY_BYTES && slot_has_long(node_w5) && seg_len - p > WP_KEY_BYTES) {
-        // tokens longer than the inline key hang off this node, longest first
-        const uint32_t ref = V.long_ref[node_slot];
-        const uint32_t cnt = V.long_entries[ref];
-        const uint8_t *txt = P.text + seg_pos + p;
-        for (uint32_t li = 0; li < cnt; li++) {
-          const uint32_t len = V.long_entries[ref + 1 + 3 * li];
-          if (len > seg_len - p) continue;
-          const uint8_t *tok = V.long_bytes + V.long_entries[ref + 3 + 3 * li];
-          uint32_t o = WP_KEY_BYTES;
-          while (o < len && txt[o] == tok[o]) o++;
-          if (o == len) {
-            mlen = len;
-            mid = static_cast<int32_t>(V.long_entries[ref + 2 + 3 * li]);
-            break;
+    }
+
+    // -- the deepest node is at depth lo: read the longest match off it and apply the piece
+    if (have) {
+      uint32_t mlen = 0;
+      int32_t mid = WP_NO_ID;
+      if (lo != 0) {
+        if (node_term != WP_NO_ID) {
+          mlen = lo;
+          mid = node_term;
+        } else if (slot_best_len(node_w5) != 0) {
+          mlen = slot_best_len(node_w5);
+          mid = node_best;
+        }
+        if (lo == WP_KEY_BYTES && slot_has_long(node_w5) && seg_len - p > WP_KEY_BYTES) {
+          // tokens longer than the inline key hang off this node, longest first
+          const uint32_t ref = V.long_ref[node_slot];
+          const uint32_t cnt = V.long_entries[ref];
+          const uint8_t *txt = P.text + seg_pos + p;
+          for (uint32_t li = 0; li < cnt; li++) {
+            const uint32_t len = V.long_entries[ref + 1 + 3 * li];
+            if (len > seg_len - p) continue;
+            const uint8_t *tok = V.long_bytes + V.long_entries[ref + 3 + 3 * li];
+            uint32_t o = WP_KEY_BYTES;
+            while (o < len && txt[o] == tok[o]) o++;
+            if (o == len) {
+              mlen = len;
+              mid = static_cast<int32_t>(V.long_entries[ref + 2 + 3 * li]);
+              break;
+            }
           }
         }
       }
-    }
-
-    // -- apply the piece (fast.cpp:66-91)
-    bool done = false;
-    int32_t *out = P.tok + tok_off;
-    if (flags & SEG_HAN_FIRST) {
-      flags = 0;
-      nid = 1;
-      if (mlen == 0) {
-        out[0] = V.unk_id;
-        if (V.han_swallow) {
-          done = true;  // fast.cpp:85-88: begin += word_len swallows the run
+      bool done = false;
+      int32_t *out = P.tok + tok_off;
+      if (flags & SEG_HAN_FIRST) {
+        flags = 0;
+        nid = 1;
+        if (mlen == 0) {
+          out[0] = V.unk_id;
+          if (V.han_swallow) {
+            done = true;  // fast.cpp:85-88: begin += word_len swallows the run
+          } else {
+            word_first = 1;
+            p += first_len;
+          }
         } else {
-          word_first = 1;
-          p += first_len;
+          out[0] = mid;
+          p += mlen;
+          if (mlen == first_len) {
+            word_first = 1;  // fast.cpp:89-91: the next position follows a spacing char => new word
+          } else {
+            kind = WP_KIND_SUFFIX;
+          }
         }
+      } else if (mlen == 0) {  // fast.cpp:79-88: whole-word UNK, earlier pieces rolled back
+        out[word_first] = V.unk_id;
+        nid = word_first + 1;
+        done = true;
       } else {
-        out[0] = mid;
+        out[nid] = mid;
+        nid++;
         p += mlen;
-        if (mlen == first_len) {
-          word_first = 1;  // fast.cpp:89-91: the next position follows a spacing char => new word
-        } else {
-          kind = WP_KIND_SUFFIX;
-        }
+        kind = WP_KIND_SUFFIX;
       }
-    } else if (mlen == 0) {  // fast.cpp:79-88: whole-word UNK, earlier pieces rolled back
-      out[word_first] = V.unk_id;
-      nid = word_first + 1;
-      done = true;
-    } else {
-      out[nid] = mid;
-      nid++;
-      p += mlen;
-      kind = WP_KIND_SUFFIX;
-    }
-    if (done || p >= seg_len) {
-      P.slow[ent_index].cnt = nid;
-      active = false;
-    } else {
-      const uint32_t wlen = seg_len - p;
-      k = wlen < WP_KEY_BYTES ? wlen : WP_KEY_BYTES;
-      lo = 0;
-      hi = k + 1;
-      reload = true;
+      if (done || p >= seg_len) {
+        P.slow[ent_index].cnt = nid;
+        have = false;
+      }
     }
   }
 }
@@ -1186,6 +1211,9 @@ __global__ void __launch_bounds__(MATCH_THREADS) wp_match_kernel(EncodeParams P)
 
 struct ScatterSmem {
   int32_t stage[SCATTER_STAGE];
+  uint32_t desc_pos[SCATTER_SEGS];     // multi-id segments of the block: stage position << 16 | id count
+  uint32_t desc_off[SCATTER_SEGS];     // ... and where their ids sit in the id scratch
+  uint32_t n_desc;
   uint32_t warp_sums[SCATTER_THREADS / 32];
   uint32_t block_index;
   unsigned long long base;
@@ -1205,7 +1233,10 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
   }
   for (;;) {
     __syncthreads();
-    if (tid == 0) sm.block_index = atomicAdd(&P.counters->scatter_ticket, 1u);
+    if (tid == 0) {
+      sm.block_index = atomicAdd(&P.counters->scatter_ticket, 1u);
+      sm.n_desc = 0;
+    }
     __syncthreads();
     const uint32_t b = sm.block_index;
     if (b >= n_blocks) break;
@@ -1256,16 +1287,29 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
     const unsigned long long out0 = ids_in + sm.base;
 
     if (total <= SCATTER_STAGE) {
-      // stage in shared memory, then write out coalesced
+      // stage in shared memory, then write out coalesced.  Single ids are placed at once; multi-id
+      // segments are first listed, then copied one segment per thread (few threads would otherwise
+      // loop while their warp waits).
 #pragma unroll
       for (int j = 0; j < SCATTER_ITEMS; j++) {
         if (cnt[j] == 0) continue;
         if (res[j] & SEG_RESULT_SLOW) {
-          for (uint32_t t = 0; t < cnt[j]; t++) sm.stage[at + t] = P.tok[off[j] + t];
+          const uint32_t d = atomicAdd(&sm.n_desc, 1u);
+          sm.desc_pos[d] = (at << 16) | cnt[j];
+          sm.desc_off[d] = off[j];
         } else {
           sm.stage[at] = static_cast<int32_t>(res[j]) - 1;
         }
         at += cnt[j];
+      }
+      __syncthreads();
+      const uint32_t n_desc = sm.n_desc;
+      for (uint32_t d = tid; d < n_desc; d += SCATTER_THREADS) {
+        const uint32_t dp = sm.desc_pos[d];
+        const int32_t *src = P.tok + sm.desc_off[d];
+        int32_t *dst = sm.stage + (dp >> 16);
+        const uint32_t c = dp & 0xFFFFu;
+        for (uint32_t t = 0; t < c; t++) dst[t] = src[t];
       }
       __syncthreads();
       for (uint32_t i = tid; i < total; i += SCATTER_THREADS) {
@@ -1307,14 +1351,40 @@ cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   if (sm_count <= 0) sm_count = 148;
-  wp_split_kernel<<<P.n_tiles, THREADS, sizeof(TileSmem), stream>>>(P);
-  e = cudaGetLastError();
+  // K1 and K2 probe the vocabulary table at random: ask L2 to keep it resident while text, ids and the
+  // intermediates stream through (access policy window = the slot array, everything else streaming).
+  cudaLaunchAttribute attr[1];
+  unsigned n_attr = 0;
+  if (P.persist_bytes > 0) {
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow.base_ptr = const_cast<Slot *>(P.vocab.slots);
+    attr[0].val.accessPolicyWindow.num_bytes = P.persist_bytes;
+    attr[0].val.accessPolicyWindow.hitRatio = P.persist_ratio;
+    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    n_attr = 1;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = n_attr;
+
+  cfg.gridDim = dim3(P.n_tiles);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = sizeof(TileSmem);
+  e = cudaLaunchKernelEx(&cfg, wp_split_kernel, P);
   if (e != cudaSuccess) return e;
-  wp_match_kernel<<<sm_count * 8, MATCH_THREADS, 0, stream>>>(P);
-  e = cudaGetLastError();
+
+  cfg.gridDim = dim3(sm_count * 8);
+  cfg.blockDim = dim3(MATCH_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  e = cudaLaunchKernelEx(&cfg, wp_match_kernel, P);
   if (e != cudaSuccess) return e;
-  wp_scatter_kernel<<<sm_count * 4, SCATTER_THREADS, 0, stream>>>(P);
-  e = cudaGetLastError();
+
+  cfg.gridDim = dim3(sm_count * 4);
+  cfg.blockDim = dim3(SCATTER_THREADS);
+  cfg.numAttrs = 0;
+  e = cudaLaunchKernelEx(&cfg, wp_scatter_kernel, P);
   if (e != cudaSuccess) return e;
   if (launches) *launches += 3;
   return cudaSuccess;

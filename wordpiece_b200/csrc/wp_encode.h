@@ -74,6 +74,9 @@ struct EncodeParams {
   int32_t *tok;                     // tok_capacity ids
   uint32_t tok_capacity;
   uint32_t n_scatter_blocks;        // size of block_state
+  // L2 residency hint for the vocabulary table (0 bytes = none)
+  size_t persist_bytes;
+  float persist_ratio;
 };
 
 uint32_t encode_tile_bytes();
