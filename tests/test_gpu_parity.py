@@ -259,3 +259,34 @@ def test_several_ranges_per_call(gpu_device, monkeypatch):
     monkeypatch.delenv("WORDPIECE_B200_RANGE_BYTES")
     assert np.array_equal(exp, v.encode(text))
     v.close()
+
+
+def test_host_buffer_pipeline(gpu_device, monkeypatch):
+    """wp_encode_into on large texts runs a three-stage pipeline (copy in / encode / copy out) over chunks
+    cut after a space; force small chunks so that many of them — and a text with a stretch that has no
+    space to cut at, which must fall back to the single-shot path — are covered."""
+    text, vocab = textgen.case(71, 400_000, invalid_rate=0.003)
+    o = Oracle(vocab)
+    exp = o.encode(text)
+    v = _vocab(vocab, gpu_device)
+    out = np.full(len(exp) + 5, -9, np.int32)
+    for chunk in (4096, 30_000, 150_000):
+        monkeypatch.setenv("WORDPIECE_B200_PIPE_CHUNK", str(chunk))
+        out[:] = -9
+        n = v.encode_into(text, out)
+        assert n == len(exp) and np.array_equal(out[:n], exp) and (out[n:] == -9).all(), chunk
+        assert v.stats().kernel_launches >= 3 * (len(text) // chunk)
+    # too small a buffer: exact count reported
+    from wordpiece_b200 import WordPieceError
+
+    with pytest.raises(WordPieceError) as ei:
+        v.encode_into(text, np.zeros(len(exp) // 3, np.int32))
+    assert ei.value.status == 5
+    # no space within a chunk: falls back, same ids
+    monkeypatch.setenv("WORDPIECE_B200_PIPE_CHUNK", "4096")
+    glued = text[:50_000] + b"x" * 9000 + text[50_000:]
+    e2 = o.encode(glued)
+    out2 = np.zeros(len(e2) + 8, np.int32)
+    n2 = v.encode_into(glued, out2)
+    assert n2 == len(e2) and np.array_equal(out2[:n2], e2)
+    v.close()

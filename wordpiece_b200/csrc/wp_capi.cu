@@ -73,6 +73,15 @@ struct wp_vocab {
   int32_t *d_ids = nullptr;
   size_t ids_cap = 0;
   wp::CallCounters *h_call = nullptr;  // pinned
+  // host-buffer pipeline (wp_encode_into on large texts): three chunks in flight
+  struct PipeSlot {
+    uint8_t *d_text = nullptr;
+    int32_t *d_ids = nullptr;
+    wp::CallCounters *h_call = nullptr;  // pinned
+    cudaEvent_t h2d_done = nullptr, cmp_done = nullptr, d2h_done = nullptr;
+  } slot[3];
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  bool pipe_ready = false;
   wp_stats stats{};
 };
 
@@ -269,6 +278,127 @@ wp_status run_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_t *d
   return fail(WP_ERR_CUDA, "internal scratch overflow");
 }
 
+constexpr size_t kPipeChunk = size_t(32) << 20;  // host-buffer pipeline: text bytes per chunk
+constexpr int kPipeSlots = 3;
+
+wp_status ensure_pipeline(wp_vocab *v) {
+  if (v->pipe_ready) return WP_OK;
+  WP_CUDA(cudaStreamCreateWithFlags(&v->s_h2d, cudaStreamNonBlocking));
+  WP_CUDA(cudaStreamCreateWithFlags(&v->s_d2h, cudaStreamNonBlocking));
+  for (auto &sl : v->slot) {
+    WP_CUDA(cudaMalloc(&sl.d_text, kPipeChunk + 256));
+    WP_CUDA(cudaMalloc(&sl.d_ids, kPipeChunk * sizeof(int32_t)));  // ids <= bytes
+    WP_CUDA(cudaMallocHost(&sl.h_call, sizeof(wp::CallCounters)));
+    WP_CUDA(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+    WP_CUDA(cudaEventCreateWithFlags(&sl.cmp_done, cudaEventDisableTiming));
+    WP_CUDA(cudaEventCreateWithFlags(&sl.d2h_done, cudaEventDisableTiming));
+  }
+  v->pipe_ready = true;
+  return WP_OK;
+}
+
+inline bool is_ascii_space(unsigned char c) { return (c >= 0x09 && c <= 0x0D) || c == 0x20; }
+
+// Cut [0, n) into chunks of at most kPipeChunk bytes, each ending right after an ASCII space: the
+// reference's serial state is reset at every is_space code point (fast.cpp:89-91,113-115), so the chunks
+// encode independently and their ids concatenate.  Returns false if some stretch has no space to cut at.
+size_t pipe_chunk_bytes() {
+  if (const char *e = std::getenv("WORDPIECE_B200_PIPE_CHUNK")) {  // test hook: pipeline small texts
+    const long long x = std::atoll(e);
+    if (x >= 64 && static_cast<size_t>(x) <= kPipeChunk) return static_cast<size_t>(x);
+  }
+  return kPipeChunk;
+}
+
+bool plan_chunks(const char *text, size_t n, size_t chunk, std::vector<size_t> *cuts) {
+  cuts->clear();
+  cuts->push_back(0);
+  size_t start = 0;
+  while (n - start > chunk) {
+    size_t end = start + chunk;
+    size_t cut = end;
+    const size_t floor = start + chunk / 2;
+    while (cut > floor && !is_ascii_space(static_cast<unsigned char>(text[cut - 1]))) cut--;
+    if (cut <= floor) return false;
+    cuts->push_back(cut);
+    start = cut;
+  }
+  cuts->push_back(n);
+  return true;
+}
+
+// Host text -> host ids through a three-stage pipeline: while chunk i is encoded, chunk i+1 is copied in
+// and the ids of chunk i-1 are copied out (the PCIe copies, not the kernels, bound this entry point).
+// *fell_back is set if the text could not be chunked or a chunk outgrew the scratch; nothing is lost then,
+// the caller runs the single-shot path.
+wp_status encode_pipelined(wp_vocab *v, const char *text, size_t n_bytes, int32_t *ids, size_t capacity,
+                           size_t *n_ids, bool *fell_back) {
+  *fell_back = false;
+  std::vector<size_t> cuts;
+  if (!plan_chunks(text, n_bytes, pipe_chunk_bytes(), &cuts)) {
+    *fell_back = true;
+    return WP_OK;
+  }
+  wp_status st = ensure_pipeline(v);
+  if (st != WP_OK) return st;
+  const size_t n_chunks = cuts.size() - 1;
+  std::vector<EnqueueInfo> infos(n_chunks);
+  size_t total = 0;
+  bool overflow = false;
+  wp_stats acc{};
+
+  auto finalize = [&](size_t j) -> wp_status {
+    wp_vocab::PipeSlot &sl = v->slot[j % kPipeSlots];
+    WP_CUDA(cudaEventSynchronize(sl.cmp_done));
+    const size_t cnt = static_cast<size_t>(sl.h_call->ids_total[infos[j].n_ranges & 1u]);
+    overflow = overflow || sl.h_call->overflow != 0;
+    acc.n_tiles += infos[j].n_tiles;
+    acc.dirty_tiles += sl.h_call->dirty_tiles;
+    acc.long_segments += sl.h_call->long_segments;
+    acc.kernel_launches += infos[j].launches;
+    if (!overflow && cnt > 0 && total + cnt <= capacity) {
+      WP_CUDA(cudaStreamWaitEvent(v->s_d2h, sl.cmp_done, 0));
+      WP_CUDA(cudaMemcpyAsync(ids + total, sl.d_ids, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, v->s_d2h));
+    }
+    WP_CUDA(cudaEventRecord(sl.d2h_done, v->s_d2h));
+    total += cnt;
+    return WP_OK;
+  };
+
+  for (size_t i = 0; i < n_chunks; i++) {
+    wp_vocab::PipeSlot &sl = v->slot[i % kPipeSlots];
+    const size_t begin = cuts[i], len = cuts[i + 1] - cuts[i];
+    if (i >= kPipeSlots) {  // the slot's previous ids must have left before its buffers are reused
+      WP_CUDA(cudaStreamWaitEvent(v->s_h2d, sl.d2h_done, 0));
+      WP_CUDA(cudaStreamWaitEvent(v->stream, sl.d2h_done, 0));
+    }
+    WP_CUDA(cudaMemcpyAsync(sl.d_text, text + begin, len, cudaMemcpyHostToDevice, v->s_h2d));
+    WP_CUDA(cudaEventRecord(sl.h2d_done, v->s_h2d));
+    WP_CUDA(cudaStreamWaitEvent(v->stream, sl.h2d_done, 0));
+    st = enqueue_encode(v, sl.d_text, len, sl.d_ids, kPipeChunk, v->stream, 0, &infos[i]);
+    if (st != WP_OK) return st;
+    WP_CUDA(cudaMemcpyAsync(sl.h_call, v->d_call, sizeof(wp::CallCounters), cudaMemcpyDeviceToHost, v->stream));
+    WP_CUDA(cudaEventRecord(sl.cmp_done, v->stream));
+    if (i >= 1) {
+      st = finalize(i - 1);
+      if (st != WP_OK) return st;
+    }
+  }
+  st = finalize(n_chunks - 1);
+  if (st != WP_OK) return st;
+  WP_CUDA(cudaStreamSynchronize(v->s_d2h));
+  if (overflow) {
+    *fell_back = true;
+    return WP_OK;
+  }
+  v->stats = acc;
+  v->stats.n_bytes = n_bytes;
+  v->stats.n_ids = total;
+  *n_ids = total;
+  if (total > capacity) return fail(WP_ERR_CAPACITY, "id buffer too small");
+  return WP_OK;
+}
+
 wp_status create_common(wp_vocab *v, const char *const *tokens, const size_t *lens, size_t n, int device,
                         wp_vocab **out) {
   std::string err;
@@ -363,6 +493,16 @@ void wp_vocab_destroy(wp_vocab *v) {
     cudaFree(v->d_text);
     cudaFree(v->d_ids);
     if (v->h_call) cudaFreeHost(v->h_call);
+    for (auto &sl : v->slot) {
+      cudaFree(sl.d_text);
+      cudaFree(sl.d_ids);
+      if (sl.h_call) cudaFreeHost(sl.h_call);
+      if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
+      if (sl.cmp_done) cudaEventDestroy(sl.cmp_done);
+      if (sl.d2h_done) cudaEventDestroy(sl.d2h_done);
+    }
+    if (v->s_h2d) cudaStreamDestroy(v->s_h2d);
+    if (v->s_d2h) cudaStreamDestroy(v->s_d2h);
     cudaFree(v->d_call);
     if (v->stream) cudaStreamDestroy(v->stream);
   }
@@ -431,6 +571,11 @@ wp_status wp_encode_into(wp_vocab *v, const char *text, size_t n_bytes, int32_t 
     return WP_OK;
   }
   DeviceGuard g(v->device);
+  if (n_bytes > 2 * pipe_chunk_bytes()) {
+    bool fell_back = false;
+    const wp_status pst = encode_pipelined(v, text, n_bytes, ids, capacity, n_ids, &fell_back);
+    if (pst != WP_OK || !fell_back) return pst;
+  }
   if (n_bytes > v->text_cap) {
     cudaFree(v->d_text);
     v->d_text = nullptr;
