@@ -119,6 +119,13 @@ wp_status wp_encode_device_async(wp_vocab *v, const void *d_text, size_t n_bytes
 /* Counters of the last completed wp_encode / wp_encode_into / wp_encode_device call. */
 wp_status wp_last_stats(wp_vocab *v, wp_stats *out);
 
+/* Per-kernel device time (diagnostics for bench.py's roofline): when enabled, every following encode call
+ * on the handle records CUDA events around its three kernels — K1 split + whole-window probe, K2 match,
+ * K3 scan + scatter — on the stream the kernels are launched on.  wp_last_kernel_ms waits for the last
+ * call and returns the summed milliseconds of each kernel over the call's ranges. */
+wp_status wp_set_kernel_timing(wp_vocab *v, int enabled);
+wp_status wp_last_kernel_ms(wp_vocab *v, float ms[3], uint32_t *n_ranges);
+
 /* ---- decode -------------------------------------------------------------
  * Replaces word_piece::fast::decode (fast.cpp:165-187): id -> token text with
  * "##" re-added for continuation tokens.  The texts are concatenated into one

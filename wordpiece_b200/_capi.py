@@ -72,6 +72,8 @@ EXPORTED_SYMBOLS = [
     "wp_encode_device",
     "wp_encode_device_async",
     "wp_last_stats",
+    "wp_set_kernel_timing",
+    "wp_last_kernel_ms",
     "wp_decode",
     "wp_free",
     "wp_debug_longest_match",
@@ -127,6 +129,10 @@ def load_library() -> C.CDLL:
     L.wp_encode_device_async.restype = C.c_int
     L.wp_last_stats.argtypes = [vp, C.POINTER(_StatsStruct)]
     L.wp_last_stats.restype = C.c_int
+    L.wp_set_kernel_timing.argtypes = [vp, C.c_int]
+    L.wp_set_kernel_timing.restype = C.c_int
+    L.wp_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
+    L.wp_last_kernel_ms.restype = C.c_int
     L.wp_decode.argtypes = [vp, vp, sz, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
     L.wp_decode.restype = C.c_int
     L.wp_free.argtypes = [vp]
@@ -308,6 +314,16 @@ class Vocab:
             stream = torch.cuda.current_stream(d_text.device).cuda_stream
         _check(self._L.wp_encode_device_async(self._h, d_text.data_ptr(), d_text.numel(), d_ids.data_ptr(),
                                               d_ids.numel(), d_count.data_ptr(), stream))
+
+    def set_kernel_timing(self, enabled: bool) -> None:
+        _check(self._L.wp_set_kernel_timing(self._h, 1 if enabled else 0))
+
+    def last_kernel_ms(self):
+        """(ms of K1 split, K2 match, K3 scatter summed over the last call's ranges, number of ranges)."""
+        ms = (C.c_float * 3)()
+        n = C.c_uint32()
+        _check(self._L.wp_last_kernel_ms(self._h, ms, C.byref(n)))
+        return [float(ms[0]), float(ms[1]), float(ms[2])], int(n.value)
 
     def stats(self) -> Stats:
         s = _StatsStruct()

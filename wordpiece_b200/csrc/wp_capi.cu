@@ -82,6 +82,10 @@ struct wp_vocab {
   } slot[3];
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   bool pipe_ready = false;
+  // optional per-kernel timing (wp_set_kernel_timing): events around K1/K2/K3 of every range
+  bool timing = false;
+  std::vector<cudaEvent_t> timing_events;  // 4 per range of the last call
+  size_t timing_used = 0;
   wp_stats stats{};
 };
 
@@ -211,6 +215,7 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   wp_status st = ensure_work(v, w.total);
   if (st != WP_OK) return st;
   WP_CUDA(cudaMemsetAsync(v->d_call, 0, sizeof(wp::CallCounters), stream));
+  v->timing_used = 0;
   wp::EncodeParams P{};
   P.vocab = device_view(v);
   P.text = static_cast<const uint8_t *>(d_text);
@@ -238,7 +243,17 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
     P.first_tile = static_cast<uint32_t>(first);
     P.n_tiles = static_cast<uint32_t>(count);
     P.range_parity = range & 1u;
-    WP_CUDA(wp::launch_encode_range(P, v->sm_count, stream, &launches));
+    cudaEvent_t *tev = nullptr;
+    if (v->timing) {
+      while (v->timing_events.size() < v->timing_used + 4) {
+        cudaEvent_t e;
+        WP_CUDA(cudaEventCreate(&e));
+        v->timing_events.push_back(e);
+      }
+      tev = v->timing_events.data() + v->timing_used;
+      v->timing_used += 4;
+    }
+    WP_CUDA(wp::launch_encode_range(P, v->sm_count, stream, &launches, tev));
   }
   g_launches.fetch_add(launches, std::memory_order_relaxed);
   info->n_tiles = static_cast<uint32_t>(n_tiles);
@@ -501,6 +516,7 @@ void wp_vocab_destroy(wp_vocab *v) {
       if (sl.cmp_done) cudaEventDestroy(sl.cmp_done);
       if (sl.d2h_done) cudaEventDestroy(sl.d2h_done);
     }
+    for (cudaEvent_t e : v->timing_events) cudaEventDestroy(e);
     if (v->s_h2d) cudaStreamDestroy(v->s_h2d);
     if (v->s_d2h) cudaStreamDestroy(v->s_d2h);
     cudaFree(v->d_call);
@@ -658,6 +674,29 @@ wp_status wp_encode(wp_vocab *v, const char *text, size_t n_bytes, int32_t **ids
   }
   *ids_out = host;
   *n_ids = cnt;
+  return WP_OK;
+}
+
+wp_status wp_set_kernel_timing(wp_vocab *v, int enabled) {
+  if (!v) return fail(WP_ERR_INVALID_ARG, "null argument");
+  v->timing = enabled != 0;
+  return WP_OK;
+}
+
+wp_status wp_last_kernel_ms(wp_vocab *v, float ms[3], uint32_t *n_ranges) {
+  if (!v || !ms) return fail(WP_ERR_INVALID_ARG, "null argument");
+  if (v->device < 0) return fail(WP_ERR_NO_DEVICE, kHostOnly);
+  DeviceGuard g(v->device);
+  ms[0] = ms[1] = ms[2] = 0.f;
+  for (size_t i = 0; i + 4 <= v->timing_used; i += 4) {
+    WP_CUDA(cudaEventSynchronize(v->timing_events[i + 3]));
+    for (int k = 0; k < 3; k++) {
+      float t = 0.f;
+      WP_CUDA(cudaEventElapsedTime(&t, v->timing_events[i + k], v->timing_events[i + k + 1]));
+      ms[k] += t;
+    }
+  }
+  if (n_ranges) *n_ranges = static_cast<uint32_t>(v->timing_used / 4);
   return WP_OK;
 }
 

@@ -36,6 +36,7 @@
 //   S3 scatter: per-segment id counts -> block scan -> decoupled look-back ->
 //              ids staged in shared memory and written out coalesced.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "wp_encode.h"
@@ -707,9 +708,30 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       }
       *reinterpret_cast<uint4 *>(sm.raw + 16 * u) = v;
     }
-    if (tid == THREADS - 1) sm.prev_class = gprev_class(tv, t0);
   }
   __syncthreads();
+  if (tid == THREADS - 1) {
+    // class of the last valid char before the tile: from the left halo in shared memory when it holds one
+    // (always, for valid UTF-8), else by walking back through the text in global memory
+    uint32_t pc = CLS_SPACE;
+    bool found = t0 == 0;
+    if (!found) {
+      const uint8_t *h = sm.raw + LEFT;  // h[-1] is the byte before the tile
+      for (int j = -1; j >= -4 && !found; j--) {
+        const uint32_t b0 = h[j];
+        if (is_cont_byte(b0)) continue;
+        uint32_t cp = 0;
+        const uint32_t len = b0 < 0x80u ? (cp = b0, 1u) : utf8_decode(b0, h[j + 1], h[j + 2], h[j + 3], 4u, &cp);
+        if (len != 0) {
+          pc = cp_class(cp);
+          found = true;
+        }
+        break;  // an invalid lead: the exact answer needs the walk below
+      }
+      if (!found) pc = gprev_class(tv, t0);
+    }
+    sm.prev_class = pc;
+  }
 
   // ---- S1b: classify the window; find bytes that the strict decoder drops
   uint8_t *const buf = sm.raw + LEFT;
@@ -951,8 +973,14 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     uint32_t total_len;
     uint32_t run = block_exclusive_scan<WARPS>(sm.warp_sums, my_len, &total_len);
     if (tid == 0) {
-      sm.slow_base = atomicAdd(&P.counters->n_slow, n_slow);
-      sm.tok_base = atomicAdd(&P.counters->tok_reserved, total_len);
+      // n_slow and tok_reserved sit side by side: one 64-bit atomic reserves both (one round trip to L2)
+      static_assert(offsetof(RangeCounters, tok_reserved) == offsetof(RangeCounters, n_slow) + 4 &&
+                        offsetof(RangeCounters, n_slow) % 8 == 0,
+                    "n_slow / tok_reserved must form one aligned 64-bit word");
+      const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(&P.counters->n_slow),
+                                               (static_cast<unsigned long long>(total_len) << 32) | n_slow);
+      sm.slow_base = static_cast<uint32_t>(old);
+      sm.tok_base = static_cast<uint32_t>(old >> 32);
     }
     if (n_walk) atomicAdd(&P.call->long_segments, static_cast<unsigned long long>(n_walk));
     __syncthreads();
@@ -1338,7 +1366,8 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
 uint32_t encode_tile_bytes() { return TILE; }
 uint32_t scatter_block_segments() { return SCATTER_SEGS; }
 
-cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_t stream, uint64_t *launches) {
+cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_t stream, uint64_t *launches,
+                                cudaEvent_t *timing) {
   // the opt-in to > 48 KB of dynamic shared memory is per device (K1 stays below it, but keep it explicit)
   static bool configured[64] = {false};
   int dev = 0;
@@ -1369,23 +1398,27 @@ cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
 
+  if (timing) cudaEventRecord(timing[0], stream);
   cfg.gridDim = dim3(P.n_tiles);
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = sizeof(TileSmem);
   e = cudaLaunchKernelEx(&cfg, wp_split_kernel, P);
   if (e != cudaSuccess) return e;
 
-  cfg.gridDim = dim3(sm_count * 8);
+  if (timing) cudaEventRecord(timing[1], stream);
+  cfg.gridDim = dim3(sm_count * 4);  // = resident capacity (__launch_bounds__(256, 4)): one wave, large shares
   cfg.blockDim = dim3(MATCH_THREADS);
   cfg.dynamicSmemBytes = 0;
   e = cudaLaunchKernelEx(&cfg, wp_match_kernel, P);
   if (e != cudaSuccess) return e;
 
+  if (timing) cudaEventRecord(timing[2], stream);
   cfg.gridDim = dim3(sm_count * 4);
   cfg.blockDim = dim3(SCATTER_THREADS);
   cfg.numAttrs = 0;
   e = cudaLaunchKernelEx(&cfg, wp_scatter_kernel, P);
   if (e != cudaSuccess) return e;
+  if (timing) cudaEventRecord(timing[3], stream);
   if (launches) *launches += 3;
   return cudaSuccess;
 }

@@ -82,6 +82,8 @@ struct EncodeParams {
 uint32_t encode_tile_bytes();
 uint32_t scatter_block_segments();
 // Enqueue K1, K2, K3 for one range.  *launches is incremented per kernel launched.
-cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_t stream, uint64_t *launches);
+// `timing` (optional): 4 events recorded around the three launches (before K1, K1|K2, K2|K3, after K3).
+cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_t stream, uint64_t *launches,
+                                cudaEvent_t *timing = nullptr);
 
 }  // namespace wp
