@@ -1,0 +1,141 @@
+#!/usr/bin/env python
+"""Throughput of the five BASELINE.json configurations and the 4 KB micro-batch latency (config 5),
+one JSON line each.  Run on the GPU box:  python tools/run_configs.py [--mib 256] > gpurun_out/configs.jsonl
+
+Every configuration is also checked against the CPU oracle on its first 4 MiB (bit-exact ids)."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import wordpiece_b200  # noqa: E402
+from _oracle import Oracle, Ref  # noqa: E402
+from wordpiece_b200 import synth  # noqa: E402
+
+MIB = 1 << 20
+
+
+def throughput(name: str, mib: int, reps: int = 7):
+    g = synth.generator(name)
+    text = g.generate(mib * MIB, seed={"en": 2, "ru": 31, "ja": 32, "zh": 33, "adv": 5}[name])
+    vocab_tokens = g.spec.vocab
+    v = wordpiece_b200.Vocab(vocab_tokens, device=0)
+    d_text = torch.from_numpy(text).cuda()
+    d_ids = torch.empty(text.size // 2 + 4096, dtype=torch.int32, device="cuda")
+    d_cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _, n_ids = v.encode_device(d_text, d_ids)
+    st = v.stats()
+    # parity on a prefix (cut at a space)
+    cut = 4 * MIB
+    while text[cut - 1] not in (0x20, 0x0A):
+        cut -= 1
+    o = Oracle(vocab_tokens)
+    exp = o.encode(text[:cut])
+    got = v.encode(text[:cut])
+    parity = bool(np.array_equal(exp, got))
+    times = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        v.encode_device_async(d_text, d_ids, d_cnt)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    v.set_kernel_timing(True)
+    v.encode_device_async(d_text, d_ids, d_cnt)
+    k_ms, n_ranges = v.last_kernel_ms()
+    v.set_kernel_timing(False)
+    med = float(np.median(times))
+    cps = None
+    line = {
+        "config": name, "text_mib": mib, "vocab_entries": len(vocab_tokens), "table_bytes": v.device_bytes,
+        "max_len": v.max_len, "n_ids": n_ids, "ids_per_byte": n_ids / text.size, "unk_fraction": float((exp == o.unk_id).mean()),
+        "parity_first_4mib": parity, "ms_median": med, "ms_best": float(min(times)),
+        "gb_per_s": text.size / (med * 1e-3) / 1e9, "tokens_per_s": n_ids / (med * 1e-3),
+        "algo_gb_per_s": (text.size + 4 * n_ids) / (med * 1e-3) / 1e9,
+        "kernel_ms": dict(zip(["split", "match", "scatter"], k_ms)), "ranges": n_ranges,
+        "dirty_tiles": st.dirty_tiles, "long_segments": st.long_segments,
+    }
+    v.close()
+    return line, text, vocab_tokens
+
+
+def latency(text: np.ndarray, vocab_tokens, n_slices: int = 3000):
+    """4 096-byte slices cut at a space, one call each (BASELINE configs[4])."""
+    v = wordpiece_b200.Vocab(vocab_tokens, device=0)
+    rng = np.random.default_rng(0)
+    slices = []
+    for start in rng.integers(0, text.size - 8192, size=n_slices):
+        s = int(start)
+        while text[s - 1] != 0x20:
+            s += 1
+        e = s + 4096
+        while text[e - 1] != 0x20:
+            e -= 1
+        slices.append(np.ascontiguousarray(text[s:e]))
+    out = np.zeros(4096, np.int32)
+    for sl in slices[:50]:
+        v.encode_into(sl, out)
+    t_host = []
+    for sl in slices:
+        t0 = time.perf_counter()
+        v.encode_into(sl, out)
+        t_host.append((time.perf_counter() - t0) * 1e6)
+    d_slices = [torch.from_numpy(sl).cuda() for sl in slices[:1000]]
+    d_ids = torch.empty(4096, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    t_dev = []
+    for ds in d_slices:
+        t0 = time.perf_counter()
+        v.encode_device(ds, d_ids)
+        t_dev.append((time.perf_counter() - t0) * 1e6)
+    # the reference's stateless call on the same slices (it re-parses the vocabulary every time)
+    ref_us = None
+    if Ref.available():
+        Ref.lib(os.cpu_count() or 1)
+        r = []
+        for sl in slices[:20]:
+            _, sec = Ref.encode(sl.tobytes(), vocab_tokens, "fast", return_seconds=True)
+            r.append(sec * 1e6)
+        ref_us = float(np.median(r))
+    v.close()
+
+    def pct(a, q):
+        return float(np.percentile(a, q))
+
+    return {"config": "latency-4KiB", "slices": n_slices,
+            "host_buffers_us": {"p50": pct(t_host, 50), "p99": pct(t_host, 99), "call": "wp_encode_into, handle reused"},
+            "device_resident_us": {"p50": pct(t_dev, 50), "p99": pct(t_dev, 99), "call": "wp_encode_device"},
+            "reference_cpu_us_median": ref_us,
+            "note": "reference = fast::encode(text, vocab_vector): re-parses the vocabulary and rebuilds both hash maps per call"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mib", type=int, default=256)
+    ap.add_argument("--configs", default="en,ru,ja,zh,adv")
+    args = ap.parse_args()
+    en_text = en_vocab = None
+    for name in args.configs.split(","):
+        line, text, vocab = throughput(name, args.mib)
+        print(json.dumps(line), flush=True)
+        if name == "en":
+            en_text, en_vocab = text, vocab
+    if en_text is not None:
+        print(json.dumps(latency(en_text, en_vocab)), flush=True)
+
+
+if __name__ == "__main__":
+    main()
