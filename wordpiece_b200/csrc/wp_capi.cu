@@ -147,7 +147,7 @@ wp_status upload(wp_vocab *v) {
 // tile's window may be arbitrarily long); `spill_ids` bounds that part and the caller retries with more.
 struct Workspace {
   size_t zero_bytes;     // counters + look-back words, zeroed before every range
-  size_t off_tile_state, off_block_state, off_seg, off_slow, off_tok, total;
+  size_t off_tile_state, off_block_state, off_seg, off_slow, off_slow_text, off_tok, total;
   uint32_t n_tiles, n_scatter_blocks, seg_cap, slow_cap, tok_cap;
 };
 
@@ -175,6 +175,8 @@ Workspace plan_workspace(size_t range_bytes, size_t spill_ids) {
   off = align_up(off + static_cast<size_t>(w.seg_cap) * 4, 256);
   w.off_slow = off;
   off = align_up(off + static_cast<size_t>(w.slow_cap) * sizeof(wp::SlowEntry), 256);
+  w.off_slow_text = off;
+  off = align_up(off + static_cast<size_t>(w.slow_cap) * 32, 256);
   w.off_tok = off;
   off = align_up(off + static_cast<size_t>(w.tok_cap) * 4, 256);
   w.total = off;
@@ -229,6 +231,7 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   P.seg_result = reinterpret_cast<uint32_t *>(v->d_work + w.off_seg);
   P.seg_capacity = w.seg_cap;
   P.slow = reinterpret_cast<wp::SlowEntry *>(v->d_work + w.off_slow);
+  P.slow_text = reinterpret_cast<uint4 *>(v->d_work + w.off_slow_text);
   P.slow_capacity = w.slow_cap;
   P.tok = reinterpret_cast<int32_t *>(v->d_work + w.off_tok);
   P.tok_capacity = w.tok_cap;

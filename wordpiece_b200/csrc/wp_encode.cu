@@ -1021,6 +1021,21 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       out.tok_off = tok_base + run;
       out.cnt = 0;
       run += len;
+      if (!walk && len <= SLOW_TEXT_BYTES) {
+        // K2 would otherwise fetch these bytes from DRAM again, one random sector per piece
+        out.meta |= SLOW_META_TEXT;
+        const int a = wpos & ~3;
+        const uint32_t sh = (wpos & 3) * 8;
+        uint32_t x[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) x[q] = ld_u32(buf + a + 4 * q);
+        uint32_t y[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) y[q] = __funnelshift_r(x[q], x[q + 1], sh);
+        uint4 *dst = P.slow_text + 2 * static_cast<size_t>(slow_base + i);
+        dst[0] = make_uint4(y[0], y[1], y[2], y[3]);
+        dst[1] = make_uint4(y[4], y[5], y[6], y[7]);
+      }
       *reinterpret_cast<uint4 *>(&P.slow[slow_base + i]) = *reinterpret_cast<const uint4 *>(&out);
       const unsigned long long g = seg_base + k;
       if (g < P.seg_capacity) P.seg_result[g] = SEG_RESULT_SLOW | (slow_base + i);
@@ -1046,8 +1061,7 @@ __device__ __noinline__ void match_walk(const EncodeParams &P, uint32_t i, size_
   } else {
     P.call->overflow = 1u;
   }
-  P.slow[i].tok_off = off;
-  P.slow[i].cnt = written;
+  *reinterpret_cast<uint4 *>(&P.slow[i]) = make_uint4(written, off, 0u, 0u);  // result form, not inline
 }
 
 // Every lane owns a long run of slow-list entries (its warp's share / 32), so
@@ -1061,8 +1075,11 @@ __device__ __noinline__ void match_walk(const EncodeParams &P, uint32_t i, size_
 //           the piece (fast.cpp:66-91)
 // so the refill / window / apply code runs once per piece and warp, fully
 // converged, and only the short probe body repeats.
-__global__ void __launch_bounds__(MATCH_THREADS, 4) wp_match_kernel(EncodeParams P) {
+constexpr int LANE_TEXT_WORDS = 17;  // 68 bytes per lane: 32 + 28 readable past any piece start, odd stride (banks)
+
+__global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams P) {
   __shared__ uint4 key_mask[2 * (WP_KEY_BYTES + 1)];
+  __shared__ uint32_t lane_text[MATCH_THREADS * LANE_TEXT_WORDS];
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const DeviceVocab &V = P.vocab;
@@ -1079,9 +1096,12 @@ __global__ void __launch_bounds__(MATCH_THREADS, 4) wp_match_kernel(EncodeParams
   const uint4 *tab = reinterpret_cast<const uint4 *>(V.slots);
 
   bool have = false;       // this lane holds an unfinished segment
+  bool in_smem = false;    // ... whose bytes sit in this lane's shared-memory buffer
+  uint32_t *const my_text = lane_text + tid * LANE_TEXT_WORDS;
   size_t seg_pos = 0;
   uint32_t ent_index = 0, seg_len = 0, p = 0, tok_off = 0;
   uint32_t nid = 0, word_first = 0, kind = WP_KIND_PREFIX, flags = 0, first_len = 0;
+  int32_t t0 = 0, t1 = 0, t2 = 0;  // the first three ids of the segment stay in registers (see the result form)
 
   for (;;) {
     // -- refill: lanes without a segment take the next entries of this warp's share
@@ -1099,7 +1119,16 @@ __global__ void __launch_bounds__(MATCH_THREADS, 4) wp_match_kernel(EncodeParams
           ent_index = i;
           seg_len = (meta >> 8) & 0xFFFFu;
           tok_off = raw.z;
-          first_len = utf8_lead_len(P.text[seg_pos]);
+          in_smem = (meta & SLOW_META_TEXT) != 0;
+          if (in_smem) {
+            const uint4 ta = __ldg(P.slow_text + 2 * static_cast<size_t>(i));
+            const uint4 tb = __ldg(P.slow_text + 2 * static_cast<size_t>(i) + 1);
+            my_text[0] = ta.x; my_text[1] = ta.y; my_text[2] = ta.z; my_text[3] = ta.w;
+            my_text[4] = tb.x; my_text[5] = tb.y; my_text[6] = tb.z; my_text[7] = tb.w;
+            first_len = utf8_lead_len(ta.x & 0xFFu);
+          } else {
+            first_len = utf8_lead_len(P.text[seg_pos]);
+          }
           have = true;
           p = 0;
           nid = 0;
@@ -1121,7 +1150,18 @@ __global__ void __launch_bounds__(MATCH_THREADS, 4) wp_match_kernel(EncodeParams
     int32_t node_term = WP_NO_ID, node_best = WP_NO_ID;
     bool searching = have;
     if (have) {
-      load_window_global(P.text, P.n_bytes, seg_pos + p, r);
+      if (in_smem) {
+        // p < 32, so the 28 bytes read stay inside the 68-byte lane buffer; bytes past the segment are
+        // stale but never enter a key (k <= remaining length)
+        const uint32_t a = p >> 2, sh = (p & 3u) * 8u;
+        uint32_t x[7];
+#pragma unroll
+        for (int q = 0; q < 7; q++) x[q] = my_text[a + q];
+#pragma unroll
+        for (int q = 0; q < 6; q++) r[q] = __funnelshift_r(x[q], x[q + 1], sh);
+      } else {
+        load_window_global(P.text, P.n_bytes, seg_pos + p, r);
+      }
       const uint32_t wlen = seg_len - p;
       const uint32_t k0 = wlen < WP_KEY_BYTES ? wlen : WP_KEY_BYTES;
       if (flags & SEG_KNOWN_MISS) {  // k0 >= 2 here
@@ -1197,11 +1237,18 @@ __global__ void __launch_bounds__(MATCH_THREADS, 4) wp_match_kernel(EncodeParams
       }
       bool done = false;
       int32_t *out = P.tok + tok_off;
+      // ids 0..2 go to registers, later ones straight to the id scratch
+      auto put = [&](uint32_t index, int32_t v) {
+        if (index == 0) t0 = v;
+        else if (index == 1) t1 = v;
+        else if (index == 2) t2 = v;
+        else out[index] = v;
+      };
       if (flags & SEG_HAN_FIRST) {
         flags = 0;
         nid = 1;
         if (mlen == 0) {
-          out[0] = V.unk_id;
+          t0 = V.unk_id;
           if (V.han_swallow) {
             done = true;  // fast.cpp:85-88: begin += word_len swallows the run
           } else {
@@ -1209,7 +1256,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, 4) wp_match_kernel(EncodeParams
             p += first_len;
           }
         } else {
-          out[0] = mid;
+          t0 = mid;
           p += mlen;
           if (mlen == first_len) {
             word_first = 1;  // fast.cpp:89-91: the next position follows a spacing char => new word
@@ -1218,17 +1265,29 @@ __global__ void __launch_bounds__(MATCH_THREADS, 4) wp_match_kernel(EncodeParams
           }
         }
       } else if (mlen == 0) {  // fast.cpp:79-88: whole-word UNK, earlier pieces rolled back
-        out[word_first] = V.unk_id;
+        put(word_first, V.unk_id);
         nid = word_first + 1;
         done = true;
       } else {
-        out[nid] = mid;
+        put(nid, mid);
         nid++;
         p += mlen;
         kind = WP_KIND_SUFFIX;
       }
       if (done || p >= seg_len) {
-        P.slow[ent_index].cnt = nid;
+        // result form of the entry (read by K3): up to three ids inline — one 16-byte store and nothing
+        // else for most segments — else the count and where the ids sit in the id scratch
+        uint4 res;
+        if (nid <= 3) {
+          res = make_uint4(nid | SLOW_RESULT_INLINE, static_cast<uint32_t>(t0), static_cast<uint32_t>(t1),
+                           static_cast<uint32_t>(t2));
+        } else {
+          out[0] = t0;
+          out[1] = t1;
+          out[2] = t2;
+          res = make_uint4(nid, tok_off, 0u, 0u);
+        }
+        *reinterpret_cast<uint4 *>(&P.slow[ent_index]) = res;
         have = false;
       }
     }
@@ -1292,9 +1351,9 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
         const uint32_t si = res[j] & ~SEG_RESULT_SLOW;
         if (si < P.slow_capacity) {
           const uint4 e = *reinterpret_cast<const uint4 *>(&P.slow[si]);
-          off[j] = e.z;
-          cnt[j] = e.w;
-          if (static_cast<unsigned long long>(e.z) + e.w > P.tok_capacity) cnt[j] = 0;
+          cnt[j] = e.x & ~SLOW_RESULT_INLINE;
+          off[j] = (e.x & SLOW_RESULT_INLINE) ? 0xFFFFFFFFu : e.y;  // all ones: ids are inline in the entry
+          if (off[j] != 0xFFFFFFFFu && static_cast<unsigned long long>(e.y) + cnt[j] > P.tok_capacity) cnt[j] = 0;
         } else {
           cnt[j] = 0;
         }
@@ -1321,7 +1380,12 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
 #pragma unroll
       for (int j = 0; j < SCATTER_ITEMS; j++) {
         if (cnt[j] == 0) continue;
-        if (res[j] & SEG_RESULT_SLOW) {
+        if ((res[j] & SEG_RESULT_SLOW) && off[j] == 0xFFFFFFFFu) {
+          const uint4 e = *reinterpret_cast<const uint4 *>(&P.slow[res[j] & ~SEG_RESULT_SLOW]);  // cached
+          sm.stage[at] = static_cast<int32_t>(e.y);
+          if (cnt[j] > 1) sm.stage[at + 1] = static_cast<int32_t>(e.z);
+          if (cnt[j] > 2) sm.stage[at + 2] = static_cast<int32_t>(e.w);
+        } else if (res[j] & SEG_RESULT_SLOW) {
           const uint32_t d = atomicAdd(&sm.n_desc, 1u);
           sm.desc_pos[d] = (at << 16) | cnt[j];
           sm.desc_off[d] = off[j];
@@ -1348,7 +1412,13 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
 #pragma unroll
       for (int j = 0; j < SCATTER_ITEMS; j++) {
         if (cnt[j] == 0) continue;
-        if (res[j] & SEG_RESULT_SLOW) {
+        if ((res[j] & SEG_RESULT_SLOW) && off[j] == 0xFFFFFFFFu) {
+          const uint4 e = *reinterpret_cast<const uint4 *>(&P.slow[res[j] & ~SEG_RESULT_SLOW]);
+          const int32_t v[3] = {static_cast<int32_t>(e.y), static_cast<int32_t>(e.z), static_cast<int32_t>(e.w)};
+          for (uint32_t t = 0; t < cnt[j]; t++) {
+            if (out0 + at + t < P.capacity) P.ids[out0 + at + t] = v[t];
+          }
+        } else if (res[j] & SEG_RESULT_SLOW) {
           for (uint32_t t = 0; t < cnt[j]; t++) {
             if (out0 + at + t < P.capacity) P.ids[out0 + at + t] = P.tok[off[j] + t];
           }
@@ -1406,7 +1476,7 @@ cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_
   if (e != cudaSuccess) return e;
 
   if (timing) cudaEventRecord(timing[1], stream);
-  cfg.gridDim = dim3(sm_count * 4);  // = resident capacity (__launch_bounds__(256, 4)): one wave, large shares
+  cfg.gridDim = dim3(sm_count * 3);  // = resident capacity (__launch_bounds__(256, 3)): one wave, large shares
   cfg.blockDim = dim3(MATCH_THREADS);
   cfg.dynamicSmemBytes = 0;
   e = cudaLaunchKernelEx(&cfg, wp_match_kernel, P);

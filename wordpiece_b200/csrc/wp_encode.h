@@ -19,6 +19,8 @@
 namespace wp {
 
 // One segment that needs more than the whole-window probe (16 bytes).
+// K1 writes the WORK form below; K2 overwrites the entry with the RESULT form: word 0 = id count
+// (| SLOW_RESULT_INLINE if at most three ids, which then sit in words 1..3), else word 1 = id-scratch offset.
 struct SlowEntry {
   uint32_t pos_lo;   // text position of the segment start, low 32 bits
   uint32_t meta;     // bits 0..7 pos high bits, 8..23 byte length (0 for WALK), 24..25 char class,
@@ -30,6 +32,9 @@ static_assert(sizeof(SlowEntry) == 16, "slow entries are read as one 16-byte loa
 
 constexpr uint32_t SLOW_META_MISSED = 1u << 26;
 constexpr uint32_t SLOW_META_WALK = 1u << 27;
+constexpr uint32_t SLOW_META_TEXT = 1u << 28;    // the segment's bytes (<= 32) were copied to slow_text[] by K1
+constexpr uint32_t SLOW_TEXT_BYTES = 32;
+constexpr uint32_t SLOW_RESULT_INLINE = 0x80000000u;  // result form of an entry (after K2): word 0 = id count | this
 constexpr uint32_t SEG_RESULT_SLOW = 0x80000000u;  // seg_result: fast = id + 1, slow = this | slow index
 
 // Counters in device memory, zeroed before every range.
@@ -70,6 +75,7 @@ struct EncodeParams {
   uint32_t *seg_result;             // seg_capacity entries
   uint32_t seg_capacity;
   SlowEntry *slow;                  // slow_capacity entries
+  uint4 *slow_text;                 // 2 x uint4 per entry: the first 32 bytes of the segment (SLOW_META_TEXT)
   uint32_t slow_capacity;
   int32_t *tok;                     // tok_capacity ids
   uint32_t tok_capacity;

@@ -55,19 +55,16 @@ WP_HD uint32_t make_w5(uint32_t bytes2021, uint32_t len, uint32_t kind) {
   return (bytes2021 & 0xFFFFu) | (len << 16) | (kind << 24);
 }
 
-// Hash of the six key words (w[5] already reduced to WP_W5_KEYMASK bits).
+// Hash of the six key words (w[5] already reduced to WP_W5_KEYMASK bits).  Multiply-xor: the six products
+// are independent (they issue back to back on the GPU), then one xor-shift-multiply finaliser; the table
+// index is taken from the low bits, so the finaliser folds the high halves down.
 WP_HD uint32_t key_hash(uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3, uint32_t k4, uint32_t k5) {
-  uint32_t h = (k5 ^ 0x9E3779B9u) * 0x85EBCA6Bu;
+  uint32_t h = (k0 * 0x9E3779B1u) ^ (k1 * 0x85EBCA77u) ^ (k2 * 0xC2B2AE3Du) ^ (k3 * 0x27D4EB2Fu) ^ (k4 * 0x165667B1u) ^
+               ((k5 + 0x7F4A7C15u) * 0xD6E8FEB9u);
   h ^= h >> 15;
-  h = (h ^ k0) * 0xC2B2AE35u;
+  h *= 0x2C1B3C6Du;
   h ^= h >> 13;
-  h = (h ^ k1) * 0x27D4EB2Fu;
-  h ^= h >> 15;
-  h = (h ^ k2) * 0x165667B1u;
-  h ^= h >> 13;
-  h = (h ^ k3) * 0x85EBCA6Bu;
-  h ^= h >> 15;
-  h = (h ^ k4) * 0xC2B2AE35u;
+  h *= 0x297A2D39u;
   h ^= h >> 16;
   return h;
 }
