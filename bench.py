@@ -233,6 +233,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("WP_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -291,7 +292,7 @@ def main():
     e1.record()
     barrier()
     sampler.stop()
-    launches = wordpiece_b200.kernel_launch_count() - launches0
+    launches = int(sum_over_ranks(float(wordpiece_b200.kernel_launch_count() - launches0)))
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps
     assert int(d_cnt.item()) == n_ids

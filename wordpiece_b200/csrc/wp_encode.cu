@@ -79,6 +79,7 @@ struct __align__(16) TileSmem {
   uint16_t seg_s[TILE];                // owned segment k (text order): start position | class << 14
   uint16_t seg_e[WINDOW + 64];         // j-th segment end in the window
   uint16_t slow[MAX_TILE_SLOW];        // segments the whole-window probe did not settle: ordinal | flags
+  uint32_t settled[TILE / 32];         // bit k: segment k was settled by S2a (its result is parked in seg_s/seg_e)
   uint32_t m_lead[NCHUNK + 1];         // valid lead bytes
   uint32_t m_space[NCHUNK + 1];
   uint32_t m_punct[NCHUNK + 1];
@@ -111,6 +112,14 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
 }
 
 __device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
+
+// One 32-byte table slot with ONE 256-bit load (sm_100: LDG.E.256) through the read-only path: half the
+// L1 wavefronts of two 16-byte gathers — the probes are the dominant L1 traffic of K2.
+__device__ __forceinline__ void ld_slot(const uint4 *tab, uint32_t idx, uint4 *a, uint4 *b) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a->x), "=r"(a->y), "=r"(a->z), "=r"(a->w), "=r"(b->x), "=r"(b->y), "=r"(b->z), "=r"(b->w)
+               : "l"(tab + 2 * static_cast<size_t>(idx)));
+}
 
 // 0x80 in every byte lane whose (7-bit) value lies in [lo, hi]; lanes must be < 0x80.
 __device__ __forceinline__ uint32_t swar_range(uint32_t w, uint32_t lo, uint32_t hi) {
@@ -575,20 +584,24 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t *warp_sums, ui
   return wbase + incl - v;
 }
 
-// Decoupled look-back over a chain of units (tiles of K1, blocks of K3), run by
-// one full warp.  state[i] = flag << 62 | value; flag 1 = the unit's own total,
-// 2 = inclusive prefix.  Publishes `total` for unit `index` and returns the sum
-// over all earlier units.  Units are handed out in launch order by a ticket, so
-// every predecessor is already running: the spin always ends.
-__device__ __forceinline__ unsigned long long lookback(volatile unsigned long long *state, uint32_t index,
-                                                       unsigned long long total, int lane) {
+// Decoupled look-back over a chain of units (tiles of K1, blocks of K3).  state[i] = flag << 62 | value;
+// flag 1 = the unit's own total, 2 = inclusive prefix.  Units are handed out in launch order by a
+// ticket, so every predecessor is already running: the spin always ends.
+//
+// lookback_publish (one thread) makes the unit's total visible as early as possible; lookback_walk (one
+// full warp) later returns the sum over all earlier units and publishes the inclusive prefix.  Work that
+// does not need the prefix goes in between: by then the predecessors have published theirs and the
+// walk is short (when every unit walked right away, it crossed hundreds of concurrent units).
+__device__ __forceinline__ void lookback_publish(volatile unsigned long long *state, uint32_t index,
+                                                 unsigned long long total) {
+  state[index] = ((index == 0 ? 2ull : 1ull) << 62) | total;
+}
+
+__device__ __forceinline__ unsigned long long lookback_walk(volatile unsigned long long *state, uint32_t index,
+                                                            unsigned long long total, int lane) {
   constexpr unsigned long long VALUE_MASK = (1ull << 62) - 1;
   unsigned long long base = 0;
-  if (index == 0) {
-    if (lane == 0) state[0] = (2ull << 62) | total;
-    return 0;
-  }
-  if (lane == 0) state[index] = (1ull << 62) | total;
+  if (index == 0) return 0;
   long long pred = static_cast<long long>(index) - 1 - lane;  // lane i looks at unit index-1-i
   for (;;) {
     unsigned long long sv = 2ull << 62;  // units before 0 count as a zero prefix
@@ -860,17 +873,11 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   const uint32_t n_ends = sm.n_ends;
   const uint32_t skip = sm.prev_class != CLS_SPACE ? 1u : 0u;
 
-  // ---- segment numbering across tiles: look-back on the segment counts (warp 0)
-  if (warp == 0) {
-    const unsigned long long base = lookback(P.tile_state, rel_tile, n_segs, lane);
-    if (lane == 0) {
-      sm.seg_base = base;
-      if (rel_tile == P.n_tiles - 1) P.counters->n_segs = base + n_segs;
-      if (dirty) atomicAdd(&P.call->dirty_tiles, 1ull);
-    }
+  // ---- segment numbering across tiles: publish this tile's segment count now, walk back after S2a
+  if (tid == 0) {
+    lookback_publish(P.tile_state, rel_tile, n_segs);
+    if (dirty) atomicAdd(&P.call->dirty_tiles, 1ull);
   }
-  __syncthreads();
-  const unsigned long long seg_base = sm.seg_base;
   const uint4 *tab = reinterpret_cast<const uint4 *>(V.slots);
 
   // ---- S2a: one whole-window probe per segment, statically assigned (uniform
@@ -910,13 +917,13 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
           load_window(buf, s, r);
           make_key_tab(sm.key_mask, r, k0, WP_KIND_PREFIX, kw[u]);
           const uint32_t idx = key_hash(kw[u][0], kw[u][1], kw[u][2], kw[u][3], kw[u][4], kw[u][5]) & V.slot_mask;
-          sa[u] = __ldg(tab + 2 * idx);
-          sb[u] = __ldg(tab + 2 * idx + 1);
+          ld_slot(tab, idx, &sa[u], &sb[u]);
         }
       }
     }
 #pragma unroll
     for (int u = 0; u < PER_TURN; u++) {
+      bool settled = false;
       if (wlen[u] != 0) {
         const bool occupied = slot_len(sb[u].y) != 0;
         const bool match = sa[u].x == kw[u][0] && sa[u].y == kw[u][1] && sa[u].z == kw[u][2] && sa[u].w == kw[u][3] &&
@@ -926,17 +933,19 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
         const bool single_miss = wlen[u] == first_len[u] && !occupied;  // a one-char segment that is no token
         const bool single_dead = wlen[u] == first_len[u] && match;      // ... or only a prefix of tokens
         if (hit || single_miss || single_dead) {
-          const unsigned long long g = seg_base + kk[u];
-          if (g < P.seg_capacity) {
-            P.seg_result[g] = static_cast<uint32_t>((hit ? term : V.unk_id) + 1);
-          } else {
-            P.call->overflow = 1u;
-          }
+          // settled: park the result (id + 1) in the two list entries of the segment, which are no longer
+          // needed, until the tile knows its first global segment number
+          const uint32_t res = static_cast<uint32_t>((hit ? term : V.unk_id) + 1);
+          sm.seg_s[kk[u]] = static_cast<uint16_t>(res);
+          sm.seg_e[kk[u] + skip] = static_cast<uint16_t>(res >> 16);
+          settled = true;
         } else {
           // miss on an empty slot: K2 may skip the whole-window probe; match or collision: K2 redoes it
           slow[u] = (occupied ? 0u : SLOW_FIRST_MISSED) | 1u;
         }
       }
+      const uint32_t settledm = __ballot_sync(FULL, settled);
+      if (lane == 0 && base + u * THREADS + (tid & ~31) < n_segs) sm.settled[(base + u * THREADS + tid) >> 5] = settledm;
       const uint32_t slowm = __ballot_sync(FULL, slow[u] != 0);
       if (slowm) {
         uint32_t at = 0;
@@ -948,6 +957,25 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     }
   }
   __syncthreads();
+
+  // ---- the walk back over earlier tiles (short by now), then the settled results go out coalesced
+  if (warp == 0) {
+    const unsigned long long base = lookback_walk(P.tile_state, rel_tile, n_segs, lane);
+    if (lane == 0) {
+      sm.seg_base = base;
+      if (rel_tile == P.n_tiles - 1) P.counters->n_segs = base + n_segs;
+    }
+  }
+  __syncthreads();
+  const unsigned long long seg_base = sm.seg_base;
+  if (seg_base + n_segs > P.seg_capacity) {
+    if (tid == 0) P.call->overflow = 1u;
+    return;  // uniform
+  }
+  for (uint32_t k = tid; k < n_segs; k += THREADS) {
+    if ((sm.settled[k >> 5] >> (k & 31)) & 1u)
+      P.seg_result[seg_base + k] = static_cast<uint32_t>(sm.seg_s[k]) | (static_cast<uint32_t>(sm.seg_e[k + skip]) << 16);
+  }
 
   // ---- hand the unsettled segments to K2: 16-byte entries in the global slow
   // list (one reservation per tile), id-scratch space reserved by byte length
@@ -1037,8 +1065,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
         dst[1] = make_uint4(y[4], y[5], y[6], y[7]);
       }
       *reinterpret_cast<uint4 *>(&P.slow[slow_base + i]) = *reinterpret_cast<const uint4 *>(&out);
-      const unsigned long long g = seg_base + k;
-      if (g < P.seg_capacity) P.seg_result[g] = SEG_RESULT_SLOW | (slow_base + i);
+      P.seg_result[seg_base + k] = SEG_RESULT_SLOW | (slow_base + i);
     }
   }
 }
@@ -1180,8 +1207,8 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams
         uint32_t kw[6];
         make_key_tab(key_mask, r, k, kind, kw);
         const uint32_t idx = (key_hash(kw[0], kw[1], kw[2], kw[3], kw[4], kw[5]) + poff) & V.slot_mask;
-        const uint4 sa = __ldg(tab + 2 * idx);
-        const uint4 sb = __ldg(tab + 2 * idx + 1);
+        uint4 sa, sb;
+        ld_slot(tab, idx, &sa, &sb);
         const bool occupied = slot_len(sb.y) != 0;
         const bool match = sa.x == kw[0] && sa.y == kw[1] && sa.z == kw[2] && sa.w == kw[3] && sb.x == kw[4] &&
                            ((sb.y ^ kw[5]) & WP_W5_KEYMASK) == 0;
@@ -1363,15 +1390,7 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
     uint32_t total;
     uint32_t at = block_exclusive_scan<SCATTER_THREADS / 32>(sm.warp_sums, mine, &total);
 
-    if (warp == 0) {
-      const unsigned long long base = lookback(P.block_state, b, total, lane);
-      if (lane == 0) {
-        sm.base = base;
-        if (b == n_blocks - 1) P.call->ids_total[P.range_parity ^ 1u] = ids_in + base + total;
-      }
-    }
-    __syncthreads();
-    const unsigned long long out0 = ids_in + sm.base;
+    if (tid == 0) lookback_publish(P.block_state, b, total);
 
     if (total <= SCATTER_STAGE) {
       // stage in shared memory, then write out coalesced.  Single ids are placed at once; multi-id
@@ -1403,12 +1422,30 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
         const uint32_t c = dp & 0xFFFFu;
         for (uint32_t t = 0; t < c; t++) dst[t] = src[t];
       }
+      // the ids are staged; only now the block needs its place in the output
+      if (warp == 0) {
+        const unsigned long long base = lookback_walk(P.block_state, b, total, lane);
+        if (lane == 0) {
+          sm.base = base;
+          if (b == n_blocks - 1) P.call->ids_total[P.range_parity ^ 1u] = ids_in + base + total;
+        }
+      }
       __syncthreads();
+      const unsigned long long out0 = ids_in + sm.base;
       for (uint32_t i = tid; i < total; i += SCATTER_THREADS) {
         if (out0 + i < P.capacity) P.ids[out0 + i] = sm.stage[i];
       }
     } else {
       // a block with unusually many ids (long words cut into many pieces): write directly
+      if (warp == 0) {
+        const unsigned long long base = lookback_walk(P.block_state, b, total, lane);
+        if (lane == 0) {
+          sm.base = base;
+          if (b == n_blocks - 1) P.call->ids_total[P.range_parity ^ 1u] = ids_in + base + total;
+        }
+      }
+      __syncthreads();
+      const unsigned long long out0 = ids_in + sm.base;
 #pragma unroll
       for (int j = 0; j < SCATTER_ITEMS; j++) {
         if (cnt[j] == 0) continue;
