@@ -62,6 +62,11 @@ constexpr uint32_t POS_MASK = 0x3FFFu;           // window positions fit 14 bits
 constexpr uint32_t SLOW_FIRST_MISSED = 0x8000u;  // tile slow-list flag: the whole-window probe already missed
 constexpr uint32_t SLOW_WALK = 0x4000u;          // tile slow-list flag: segment leaves the window
 
+// Rows of the key-mask table are 48 bytes apart (32 used): lanes read rows by their own k, and with this
+// stride the rows of k = 1..8 — nearly all probes — start in eight different groups of four banks, so the
+// two 16-byte loads of a probe do not serialise on bank conflicts.
+constexpr int KEY_MASK_ROW = 3;                  // in uint4 units
+
 constexpr int MATCH_THREADS = 256;               // K2
 constexpr int SCATTER_THREADS = 256;             // K3
 constexpr int SCATTER_ITEMS = 8;                 // segments per thread and block iteration
@@ -88,7 +93,7 @@ struct __align__(16) TileSmem {
   uint32_t m_kept[NCHUNK + 1];         // bytes of the RAW window that survive the strict decoder (dirty tiles)
   uint32_t kept_scan[NCHUNK + 2];      // exclusive scan of kept bytes per chunk (dirty tiles)
   uint8_t spill[NCHUNK + 1];           // bytes by which the chunk's last sequence runs into the next chunk
-  uint4 key_mask[2 * (WP_KEY_BYTES + 1)];  // row k: masks of the six key words for a k-byte key, then k << 16
+  uint4 key_mask[KEY_MASK_ROW * (WP_KEY_BYTES + 1)];  // row k: masks of the six key words for a k-byte key, then k << 16
   uint32_t warp_sums[WARPS];
   uint32_t tile_index;
   uint32_t prev_class;                 // class of the last valid char before the tile
@@ -174,12 +179,12 @@ __device__ __forceinline__ void make_key(const uint32_t r[6], uint32_t k, uint32
   kw[5] = make_w5(tail, k, kind);
 }
 
-// Same, with the byte masks read from a 32-byte row of a shared-memory table
+// Same, with the byte masks read from a row of a shared-memory table
 // (two 16-byte loads and six ANDs instead of a compare/select chain per word).
 __device__ __forceinline__ void make_key_tab(const uint4 *key_mask, const uint32_t r[6], uint32_t k, uint32_t kind,
                                              uint32_t kw[6]) {
-  const uint4 ma = key_mask[2 * k];
-  const uint4 mb = key_mask[2 * k + 1];
+  const uint4 ma = key_mask[KEY_MASK_ROW * k];
+  const uint4 mb = key_mask[KEY_MASK_ROW * k + 1];
   kw[0] = r[0] & ma.x;
   kw[1] = r[1] & ma.y;
   kw[2] = r[2] & ma.z;
@@ -670,8 +675,8 @@ __device__ __forceinline__ void init_key_mask(uint4 *key_mask, int tid) {
       const int nb = static_cast<int>(k) - 4 * i;
       m[i] = nb >= 4 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
     }
-    key_mask[2 * k] = make_uint4(m[0], m[1], m[2], m[3]);
-    key_mask[2 * k + 1] = make_uint4(m[4], m[5] & 0xFFFFu, k << 16, 0u);
+    key_mask[KEY_MASK_ROW * k] = make_uint4(m[0], m[1], m[2], m[3]);
+    key_mask[KEY_MASK_ROW * k + 1] = make_uint4(m[4], m[5] & 0xFFFFu, k << 16, 0u);
   }
 }
 
@@ -1105,7 +1110,7 @@ __device__ __noinline__ void match_walk(const EncodeParams &P, uint32_t i, size_
 constexpr int LANE_TEXT_WORDS = 17;  // 68 bytes per lane: 32 + 28 readable past any piece start, odd stride (banks)
 
 __global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams P) {
-  __shared__ uint4 key_mask[2 * (WP_KEY_BYTES + 1)];
+  __shared__ uint4 key_mask[KEY_MASK_ROW * (WP_KEY_BYTES + 1)];
   __shared__ uint32_t lane_text[MATCH_THREADS * LANE_TEXT_WORDS];
   const int tid = threadIdx.x;
   const int lane = tid & 31;
