@@ -141,6 +141,25 @@ __device__ __forceinline__ uint32_t class_of(uint32_t cp) { return cp_class(cp);
 
 // ---------------------------------------------------------------- table probe
 
+// Outcome of looking at two consecutive slots (idx, idx+1) for one key: with linear probing at load <= 0.25
+// the key, or the empty slot that proves its absence, is in this pair for all but ~1 % of the probes, so a
+// probe is one turn (two 256-bit loads issued together) instead of a chain of dependent single-slot turns.
+enum PairOutcome : uint32_t { PAIR_MISS = 0, PAIR_HIT0 = 1, PAIR_HIT1 = 2, PAIR_BOTH_OTHER = 3 };
+
+__device__ __forceinline__ bool slot_matches(const uint4 &a, const uint4 &b, const uint32_t kw[6]) {
+  return a.x == kw[0] && a.y == kw[1] && a.z == kw[2] && a.w == kw[3] && b.x == kw[4] &&
+         ((b.y ^ kw[5]) & WP_W5_KEYMASK) == 0;
+}
+
+__device__ __forceinline__ uint32_t pair_outcome(const uint4 &a0, const uint4 &b0, const uint4 &a1, const uint4 &b1,
+                                                 const uint32_t kw[6]) {
+  if (slot_len(b0.y) == 0) return PAIR_MISS;
+  if (slot_matches(a0, b0, kw)) return PAIR_HIT0;
+  if (slot_len(b1.y) == 0) return PAIR_MISS;
+  if (slot_matches(a1, b1, kw)) return PAIR_HIT1;
+  return PAIR_BOTH_OTHER;
+}
+
 struct NodeHit {
   uint32_t w5;
   int32_t term_id;
@@ -930,12 +949,12 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     for (int u = 0; u < PER_TURN; u++) {
       bool settled = false;
       if (wlen[u] != 0) {
-        const bool occupied = slot_len(sb[u].y) != 0;
-        const bool match = sa[u].x == kw[u][0] && sa[u].y == kw[u][1] && sa[u].z == kw[u][2] && sa[u].w == kw[u][3] &&
-                           sb[u].x == kw[u][4] && ((sb[u].y ^ kw[u][5]) & WP_W5_KEYMASK) == 0;
+        // one slot only here (K2 looks at pairs): a probe that lands on another key's slot is left to K2
+        const bool empty = slot_len(sb[u].y) == 0;
+        const bool match = !empty && slot_matches(sa[u], sb[u], kw[u]);
         const int32_t term = static_cast<int32_t>(sb[u].z);
         const bool hit = match && term != WP_NO_ID && wlen[u] <= WP_KEY_BYTES;
-        const bool single_miss = wlen[u] == first_len[u] && !occupied;  // a one-char segment that is no token
+        const bool single_miss = wlen[u] == first_len[u] && empty;  // a one-char segment that is no token
         const bool single_dead = wlen[u] == first_len[u] && match;      // ... or only a prefix of tokens
         if (hit || single_miss || single_dead) {
           // settled: park the result (id + 1) in the two list entries of the segment, which are no longer
@@ -946,7 +965,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
           settled = true;
         } else {
           // miss on an empty slot: K2 may skip the whole-window probe; match or collision: K2 redoes it
-          slow[u] = (occupied ? 0u : SLOW_FIRST_MISSED) | 1u;
+          slow[u] = (empty ? SLOW_FIRST_MISSED : 0u) | 1u;
         }
       }
       const uint32_t settledm = __ballot_sync(FULL, settled);
@@ -1212,21 +1231,21 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams
         uint32_t kw[6];
         make_key_tab(key_mask, r, k, kind, kw);
         const uint32_t idx = (key_hash(kw[0], kw[1], kw[2], kw[3], kw[4], kw[5]) + poff) & V.slot_mask;
-        uint4 sa, sb;
+        uint4 sa, sb, sc, sd;
         ld_slot(tab, idx, &sa, &sb);
-        const bool occupied = slot_len(sb.y) != 0;
-        const bool match = sa.x == kw[0] && sa.y == kw[1] && sa.z == kw[2] && sa.w == kw[3] && sb.x == kw[4] &&
-                           ((sb.y ^ kw[5]) & WP_W5_KEYMASK) == 0;
-        if (occupied && !match) {
-          poff++;  // collision: next slot, same key
+        ld_slot(tab, (idx + 1) & V.slot_mask, &sc, &sd);
+        const uint32_t oc = pair_outcome(sa, sb, sc, sd, kw);
+        if (oc == PAIR_BOTH_OTHER) {
+          poff += 2;  // both slots hold other keys: walk on, same key
         } else {
           poff = 0;
-          if (match) {
+          if (oc != PAIR_MISS) {
+            const bool second = oc == PAIR_HIT1;
             lo = k;
-            node_w5 = sb.y;
-            node_term = static_cast<int32_t>(sb.z);
-            node_best = static_cast<int32_t>(sb.w);
-            node_slot = idx;
+            node_w5 = second ? sd.y : sb.y;
+            node_term = static_cast<int32_t>(second ? sd.z : sb.z);
+            node_best = static_cast<int32_t>(second ? sd.w : sb.w);
+            node_slot = (idx + (second ? 1u : 0u)) & V.slot_mask;
           } else {
             hi = k;
           }
