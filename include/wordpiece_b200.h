@@ -52,6 +52,7 @@ typedef struct wp_stats {
   uint64_t dirty_tiles;    /* tiles that held invalid UTF-8 (bytes dropped, utf8.cpp:130-147) */
   uint64_t long_segments;  /* segments longer than a tile's window (walked from global memory) */
   uint64_t kernel_launches;/* kernels launched by this call */
+  uint64_t memo_hits;      /* segments settled by the per-call word memo (repeats of a word matched earlier) */
 } wp_stats;
 
 /* Message for the last non-OK status returned on the calling thread. */

@@ -333,3 +333,45 @@ def test_cpp_drop_in_runner(gpu_device, tmp_path):
     # unknown modes are rejected like the reference does for bad argv
     bad = subprocess.run([runner, "linear", str(tf), str(vf)], capture_output=True, text=True)
     assert bad.returncode != 0
+
+
+def test_word_memo(gpu_device, monkeypatch):
+    """The per-call word memo (K2 records bytes -> ids of short unsettled segments, K1 of later ranges
+    settles repeats with one lookup) must not change a single id.  Small ranges maximise the traffic
+    through it; dirty tiles, walked segments and Han-led segments ride along."""
+    import wordpiece_b200
+
+    tile = wordpiece_b200.tile_bytes()
+    monkeypatch.setenv("WORDPIECE_B200_MEMO", "1")
+    for seed, n, kw in [(81, 40 * tile, {}), (82, 25 * tile + 77, dict(invalid_rate=0.01)),
+                        (83, 30 * tile, dict(long_run_rate=0.03, long_tokens=12))]:
+        text, vocab = textgen.case(seed, n, **kw)
+        exp = Oracle(vocab).encode(text)
+        v = _vocab(vocab, gpu_device)
+        hits = []
+        for range_bytes in (tile, 4 * tile, 1 << 30):
+            monkeypatch.setenv("WORDPIECE_B200_RANGE_BYTES", str(range_bytes))
+            got = v.encode(text)
+            assert np.array_equal(exp, got), (seed, range_bytes)
+            hits.append(v.stats().memo_hits)
+        # one range: nothing to look up yet; many ranges: repeats hit (tiles with invalid bytes bypass the memo,
+        # and at this rate every tile of case 82 has some)
+        assert hits[2] == 0 and (hits[0] > 0 or seed == 82), hits
+        # the memo is reset per call: same ids and same hit count when the call is repeated
+        monkeypatch.setenv("WORDPIECE_B200_RANGE_BYTES", str(tile))
+        assert np.array_equal(exp, v.encode(text)) and v.stats().memo_hits == hits[0]
+        monkeypatch.setenv("WORDPIECE_B200_MEMO", "0")
+        assert np.array_equal(exp, v.encode(text)) and v.stats().memo_hits == 0
+        monkeypatch.setenv("WORDPIECE_B200_MEMO", "1")
+        v.close()
+    # English-like corpus with its Zipf repeats, memo on by size (>= 4 MiB), against the oracle
+    monkeypatch.delenv("WORDPIECE_B200_MEMO")
+    monkeypatch.setenv("WORDPIECE_B200_RANGE_BYTES", str(1 << 20))
+    from wordpiece_b200 import synth
+
+    g = synth.generator("en")
+    text = g.generate(6 << 20, seed=12).tobytes()
+    v = _vocab(g.spec.vocab, gpu_device)
+    assert np.array_equal(Oracle(g.spec.vocab).encode(text), v.encode(text))
+    assert v.stats().memo_hits > 10000
+    v.close()

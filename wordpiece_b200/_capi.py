@@ -40,6 +40,7 @@ class _StatsStruct(C.Structure):
         ("dirty_tiles", C.c_uint64),
         ("long_segments", C.c_uint64),
         ("kernel_launches", C.c_uint64),
+        ("memo_hits", C.c_uint64),
     ]
 
 
@@ -51,6 +52,7 @@ class Stats:
     dirty_tiles: int
     long_segments: int
     kernel_launches: int
+    memo_hits: int = 0
 
 
 # every symbol include/wordpiece_b200.h declares (tests check that all are exported)
@@ -328,7 +330,7 @@ class Vocab:
     def stats(self) -> Stats:
         s = _StatsStruct()
         _check(self._L.wp_last_stats(self._h, C.byref(s)))
-        return Stats(s.n_bytes, s.n_ids, s.n_tiles, s.dirty_tiles, s.long_segments, s.kernel_launches)
+        return Stats(s.n_bytes, s.n_ids, s.n_tiles, s.dirty_tiles, s.long_segments, s.kernel_launches, s.memo_hits)
 
     # ---- decode ---------------------------------------------------------
     def decode(self, ids: Iterable[int]) -> List[bytes]:

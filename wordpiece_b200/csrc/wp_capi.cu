@@ -47,7 +47,9 @@ struct DeviceGuard {
   }
 };
 
-constexpr size_t kRangeBytesMax = size_t(64) << 20;  // text bytes encoded per K1/K2/K3 round (bounds the scratch)
+constexpr size_t kRangeBytesMax = size_t(64) << 20;
+constexpr uint32_t kMemoSlots = 1u << 20;            // word memo: 32 MiB of 32-byte slots
+constexpr size_t kMemoMinBytes = size_t(4) << 20;    // texts below this skip the memo (it would only cost the reset)  // text bytes encoded per K1/K2/K3 round (bounds the scratch)
 
 }  // namespace
 
@@ -65,6 +67,7 @@ struct wp_vocab {
   uint8_t *d_work = nullptr;
   size_t work_bytes = 0;
   wp::CallCounters *d_call = nullptr;
+  uint4 *d_memo = nullptr;  // word memo (wp_encode.h), allocated on the first large call
   int sm_count = 0;
   size_t persist_bytes = 0;  // L2 access-policy window over the slot array
   float persist_ratio = 0.f;
@@ -203,7 +206,7 @@ struct EnqueueInfo {
 // Enqueue the kernels for a whole text on `stream`: K1/K2/K3 per range of at most kRangeBytesMax bytes.
 // No synchronisation.  The running id count ends up in d_call->ids_total[n_ranges & 1].
 wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_t *d_ids, size_t capacity,
-                         cudaStream_t stream, size_t spill_ids, EnqueueInfo *info) {
+                         cudaStream_t stream, size_t spill_ids, EnqueueInfo *info, bool memo_reset = true) {
   const size_t tile = wp::encode_tile_bytes();
   const size_t n_tiles = (n_bytes + tile - 1) / tile;
   if (n_tiles > 0x7FFFFFFFull) return fail(WP_ERR_INVALID_ARG, "text too large for one call (> 2^31 tiles)");
@@ -218,6 +221,14 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   if (st != WP_OK) return st;
   WP_CUDA(cudaMemsetAsync(v->d_call, 0, sizeof(wp::CallCounters), stream));
   v->timing_used = 0;
+  bool use_memo = n_bytes >= kMemoMinBytes;
+  if (const char *e = std::getenv("WORDPIECE_B200_MEMO")) use_memo = std::atoi(e) != 0;  // 0 = off, 1 = on (tests)
+  if (use_memo) {
+    if (!v->d_memo) WP_CUDA(cudaMalloc(&v->d_memo, static_cast<size_t>(kMemoSlots) * 32));
+    // every user call starts with an empty memo: results never depend on earlier calls (the chunks of one
+    // pipelined host-buffer call share it)
+    if (memo_reset) WP_CUDA(cudaMemsetAsync(v->d_memo, 0, static_cast<size_t>(kMemoSlots) * 32, stream));
+  }
   wp::EncodeParams P{};
   P.vocab = device_view(v);
   P.text = static_cast<const uint8_t *>(d_text);
@@ -236,6 +247,8 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   P.tok = reinterpret_cast<int32_t *>(v->d_work + w.off_tok);
   P.tok_capacity = w.tok_cap;
   P.n_scatter_blocks = w.n_scatter_blocks;
+  P.memo = use_memo ? v->d_memo : nullptr;
+  P.memo_mask = kMemoSlots - 1;
   P.persist_bytes = v->persist_bytes;
   P.persist_ratio = v->persist_ratio;
   uint64_t launches = 0;
@@ -274,6 +287,7 @@ wp_status finish_stats(wp_vocab *v, size_t n_bytes, const EnqueueInfo &info, cud
   v->stats.n_tiles = info.n_tiles;
   v->stats.dirty_tiles = v->h_call->dirty_tiles;
   v->stats.long_segments = v->h_call->long_segments;
+  v->stats.memo_hits = v->h_call->memo_hits;
   v->stats.kernel_launches = info.launches;
   *overflow = v->h_call->overflow != 0;
   return WP_OK;
@@ -373,6 +387,7 @@ wp_status encode_pipelined(wp_vocab *v, const char *text, size_t n_bytes, int32_
     acc.n_tiles += infos[j].n_tiles;
     acc.dirty_tiles += sl.h_call->dirty_tiles;
     acc.long_segments += sl.h_call->long_segments;
+    acc.memo_hits += sl.h_call->memo_hits;
     acc.kernel_launches += infos[j].launches;
     if (!overflow && cnt > 0 && total + cnt <= capacity) {
       WP_CUDA(cudaStreamWaitEvent(v->s_d2h, sl.cmp_done, 0));
@@ -393,7 +408,7 @@ wp_status encode_pipelined(wp_vocab *v, const char *text, size_t n_bytes, int32_
     WP_CUDA(cudaMemcpyAsync(sl.d_text, text + begin, len, cudaMemcpyHostToDevice, v->s_h2d));
     WP_CUDA(cudaEventRecord(sl.h2d_done, v->s_h2d));
     WP_CUDA(cudaStreamWaitEvent(v->stream, sl.h2d_done, 0));
-    st = enqueue_encode(v, sl.d_text, len, sl.d_ids, kPipeChunk, v->stream, 0, &infos[i]);
+    st = enqueue_encode(v, sl.d_text, len, sl.d_ids, kPipeChunk, v->stream, 0, &infos[i], /*memo_reset=*/i == 0);
     if (st != WP_OK) return st;
     WP_CUDA(cudaMemcpyAsync(sl.h_call, v->d_call, sizeof(wp::CallCounters), cudaMemcpyDeviceToHost, v->stream));
     WP_CUDA(cudaEventRecord(sl.cmp_done, v->stream));
@@ -471,6 +486,7 @@ wp_status wp_vocab_create(const char *const *tokens, const size_t *token_lens, s
                           wp_vocab **out) {
   if (out == nullptr || (n_tokens > 0 && (tokens == nullptr || token_lens == nullptr)))
     return fail(WP_ERR_INVALID_ARG, "null argument");
+  if (n_tokens >= (size_t(1) << 30) - 1) return fail(WP_ERR_INVALID_ARG, "vocabulary too large (ids must fit 30 bits)");
   *out = nullptr;
   wp_vocab *v = new (std::nothrow) wp_vocab();
   if (!v) return fail(WP_ERR_NOMEM, "out of memory");
@@ -523,6 +539,7 @@ void wp_vocab_destroy(wp_vocab *v) {
     if (v->s_h2d) cudaStreamDestroy(v->s_h2d);
     if (v->s_d2h) cudaStreamDestroy(v->s_d2h);
     cudaFree(v->d_call);
+    cudaFree(v->d_memo);
     if (v->stream) cudaStreamDestroy(v->stream);
   }
   delete v;

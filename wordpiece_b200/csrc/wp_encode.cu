@@ -85,6 +85,9 @@ struct __align__(16) TileSmem {
   uint16_t seg_e[WINDOW + 64];         // j-th segment end in the window
   uint16_t slow[MAX_TILE_SLOW];        // segments the whole-window probe did not settle: ordinal | flags
   uint32_t settled[TILE / 32];         // bit k: segment k was settled by S2a (its result is parked in seg_s/seg_e)
+  uint16_t slow2[MAX_TILE_SLOW];       // slow[] minus the segments the word memo settled
+  uint32_t n_slow2;
+  uint32_t memo_hits;
   uint32_t m_lead[NCHUNK + 1];         // valid lead bytes
   uint32_t m_space[NCHUNK + 1];
   uint32_t m_punct[NCHUNK + 1];
@@ -715,6 +718,8 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     sm.tile_index = atomicAdd(&P.counters->split_ticket, 1u);
     sm.left_spill = 0;
     sm.n_slow = 0;
+    sm.n_slow2 = 0;
+    sm.memo_hits = 0;
   }
   init_key_mask(sm.key_mask, tid);
   __syncthreads();
@@ -1001,18 +1006,77 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       P.seg_result[seg_base + k] = static_cast<uint32_t>(sm.seg_s[k]) | (static_cast<uint32_t>(sm.seg_e[k + skip]) << 16);
   }
 
+  // ---- word memo: an unsettled segment of at most 16 bytes whose exact bytes were matched before (by K2,
+  // in an earlier range of this call) is settled here with one lookup; the rest form the final slow list
+  const uint16_t *slow_list = sm.slow;
+  uint32_t n_slow = sm.n_slow;
+  if (n_slow == 0) return;  // uniform
+  if (P.memo != nullptr && !dirty) {
+    for (uint32_t base = 0; base < n_slow; base += THREADS) {
+      const uint32_t i = base + tid;
+      bool keep = false;
+      uint32_t ent = 0;
+      if (i < n_slow) {
+        ent = sm.slow[i];
+        keep = true;
+        if (!(ent & SLOW_WALK)) {
+          const uint32_t k = ent & 0xFFFu;
+          const int s = static_cast<int>(sm.seg_s[k] & POS_MASK);
+          const uint32_t j = k + skip;
+          const int e = j < n_ends ? static_cast<int>(sm.seg_e[j]) : limit;
+          const uint32_t len = static_cast<uint32_t>(e - s);
+          if (len <= MEMO_KEY_BYTES) {
+            uint32_t r[6];
+            load_window(buf, s, r);
+            const uint4 ma = sm.key_mask[KEY_MASK_ROW * len];
+            const uint32_t k0 = r[0] & ma.x, k1 = r[1] & ma.y, k2 = r[2] & ma.z, k3 = r[3] & ma.w;
+            uint32_t idx = key_hash(k0, k1, k2, k3, len, MEMO_SALT) & P.memo_mask;
+            for (int t = 0; t < 2; t++) {
+              const uint4 a = __ldg(P.memo + 2 * static_cast<size_t>(idx));
+              const uint4 b = __ldg(P.memo + 2 * static_cast<size_t>(idx) + 1);
+              if (b.x == 0) break;
+              if ((b.x & MEMO_READY) && (b.x & 0xFFu) == len && a.x == k0 && a.y == k1 && a.z == k2 && a.w == k3) {
+                P.seg_result[seg_base + k] = SEG_RESULT_MEMO | idx;
+                keep = false;
+                break;
+              }
+              idx = (idx + 1) & P.memo_mask;
+            }
+          }
+        }
+      }
+      const uint32_t keepm = __ballot_sync(FULL, keep);
+      const uint32_t hitm = __ballot_sync(FULL, i < n_slow && !keep);
+      if (keepm) {
+        uint32_t at = 0;
+        const int leader = __ffs(keepm) - 1;
+        if (lane == leader) {
+          at = atomicAdd(&sm.n_slow2, static_cast<uint32_t>(__popc(keepm)));
+          if (hitm) atomicAdd(&sm.memo_hits, static_cast<uint32_t>(__popc(hitm)));
+        }
+        at = __shfl_sync(FULL, at, leader);
+        if (keep) sm.slow2[at + __popc(keepm & ((1u << lane) - 1u))] = static_cast<uint16_t>(ent);
+      } else if (hitm && lane == 0) {
+        atomicAdd(&sm.memo_hits, static_cast<uint32_t>(__popc(hitm)));
+      }
+    }
+    __syncthreads();
+    slow_list = sm.slow2;
+    n_slow = sm.n_slow2;
+    if (tid == 0 && sm.memo_hits) atomicAdd(&P.call->memo_hits, static_cast<unsigned long long>(sm.memo_hits));
+    if (n_slow == 0) return;  // uniform
+  }
+
   // ---- hand the unsettled segments to K2: 16-byte entries in the global slow
   // list (one reservation per tile), id-scratch space reserved by byte length
   // (a segment never has more ids than bytes).
-  const uint32_t n_slow = sm.n_slow;
-  if (n_slow == 0) return;  // uniform
   {
     const uint32_t per = (n_slow + THREADS - 1) / THREADS;
     const uint32_t lo = min(n_slow, static_cast<uint32_t>(tid) * per);
     const uint32_t hi = min(n_slow, lo + per);
     uint32_t my_len = 0, n_walk = 0;
     for (uint32_t i = lo; i < hi; i++) {
-      const uint32_t ent = sm.slow[i];
+      const uint32_t ent = slow_list[i];
       const uint32_t k = ent & 0xFFFu;
       if (dirty || (ent & SLOW_WALK)) {
         n_walk += (ent & SLOW_WALK) ? 1u : 0u;
@@ -1044,7 +1108,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       return;  // uniform
     }
     for (uint32_t i = lo; i < hi; i++) {
-      const uint32_t ent = sm.slow[i];
+      const uint32_t ent = slow_list[i];
       const uint32_t k = ent & 0xFFFu;
       const uint32_t sv = sm.seg_s[k];
       int wpos = static_cast<int>(sv & POS_MASK);
@@ -1147,6 +1211,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams
   const uint4 *tab = reinterpret_cast<const uint4 *>(V.slots);
 
   bool have = false;       // this lane holds an unfinished segment
+  bool memo_on = P.memo != nullptr;
   bool in_smem = false;    // ... whose bytes sit in this lane's shared-memory buffer
   uint32_t *const my_text = lane_text + tid * LANE_TEXT_WORDS;
   size_t seg_pos = 0;
@@ -1340,6 +1405,34 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams
         }
         *reinterpret_cast<uint4 *>(&P.slow[ent_index]) = res;
         have = false;
+        if (memo_on && in_smem && seg_len <= MEMO_KEY_BYTES && nid <= 3) {
+          // record bytes -> ids in the word memo so that K1 settles every later occurrence itself
+          const uint4 ma = key_mask[KEY_MASK_ROW * seg_len];
+          const uint32_t k0 = my_text[0] & ma.x, k1 = my_text[1] & ma.y, k2 = my_text[2] & ma.z, k3 = my_text[3] & ma.w;
+          uint32_t idx = key_hash(k0, k1, k2, k3, seg_len, MEMO_SALT) & P.memo_mask;
+          bool placed = false;
+          for (int t = 0; t < 4 && !placed; t++) {
+            uint4 *slot = P.memo + 2 * static_cast<size_t>(idx);
+            unsigned int *state = reinterpret_cast<unsigned int *>(slot + 1);
+            const unsigned int old = atomicCAS(state, 0u, 1u);
+            if (old == 0u) {  // claimed: key and ids first, the READY state last
+              slot[0] = make_uint4(k0, k1, k2, k3);
+              state[1] = static_cast<unsigned int>(t0);
+              state[2] = static_cast<unsigned int>(t1);
+              state[3] = static_cast<unsigned int>(t2);
+              __threadfence();
+              atomicExch(state, MEMO_READY | (nid << 8) | seg_len);
+              placed = true;
+            } else if (old == 1u) {
+              placed = true;  // another lane is writing this slot right now (most likely the same word)
+            } else if ((old & 0xFFu) == seg_len) {
+              const uint4 a = __ldcg(slot);
+              if (a.x == k0 && a.y == k1 && a.z == k2 && a.w == k3) placed = true;  // already there
+            }
+            idx = (idx + 1) & P.memo_mask;
+          }
+          if (!placed) memo_on = false;  // crowded neighbourhood: this lane stops feeding the memo
+        }
       }
     }
   }
@@ -1398,6 +1491,10 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
       off[j] = 0;
       if (first + j >= n_segs) {
         cnt[j] = 0;
+      } else if (!(res[j] & SEG_RESULT_SLOW) && (res[j] & SEG_RESULT_MEMO)) {
+        const uint4 mb = *reinterpret_cast<const uint4 *>(P.memo + 2 * static_cast<size_t>(res[j] & ~SEG_RESULT_MEMO) + 1);
+        cnt[j] = (mb.x >> 8) & 0xFFu;
+        off[j] = 0xFFFFFFFEu;  // ids are in the memo slot
       } else if (res[j] & SEG_RESULT_SLOW) {
         const uint32_t si = res[j] & ~SEG_RESULT_SLOW;
         if (si < P.slow_capacity) {
@@ -1423,8 +1520,10 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
 #pragma unroll
       for (int j = 0; j < SCATTER_ITEMS; j++) {
         if (cnt[j] == 0) continue;
-        if ((res[j] & SEG_RESULT_SLOW) && off[j] == 0xFFFFFFFFu) {
-          const uint4 e = *reinterpret_cast<const uint4 *>(&P.slow[res[j] & ~SEG_RESULT_SLOW]);  // cached
+        if (off[j] >= 0xFFFFFFFEu) {  // up to three ids inline in the slow entry / in the memo slot (cached loads)
+          const uint4 e = off[j] == 0xFFFFFFFFu
+                              ? *reinterpret_cast<const uint4 *>(&P.slow[res[j] & ~SEG_RESULT_SLOW])
+                              : *reinterpret_cast<const uint4 *>(P.memo + 2 * static_cast<size_t>(res[j] & ~SEG_RESULT_MEMO) + 1);
           sm.stage[at] = static_cast<int32_t>(e.y);
           if (cnt[j] > 1) sm.stage[at + 1] = static_cast<int32_t>(e.z);
           if (cnt[j] > 2) sm.stage[at + 2] = static_cast<int32_t>(e.w);
@@ -1473,8 +1572,10 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
 #pragma unroll
       for (int j = 0; j < SCATTER_ITEMS; j++) {
         if (cnt[j] == 0) continue;
-        if ((res[j] & SEG_RESULT_SLOW) && off[j] == 0xFFFFFFFFu) {
-          const uint4 e = *reinterpret_cast<const uint4 *>(&P.slow[res[j] & ~SEG_RESULT_SLOW]);
+        if (off[j] >= 0xFFFFFFFEu) {
+          const uint4 e = off[j] == 0xFFFFFFFFu
+                              ? *reinterpret_cast<const uint4 *>(&P.slow[res[j] & ~SEG_RESULT_SLOW])
+                              : *reinterpret_cast<const uint4 *>(P.memo + 2 * static_cast<size_t>(res[j] & ~SEG_RESULT_MEMO) + 1);
           const int32_t v[3] = {static_cast<int32_t>(e.y), static_cast<int32_t>(e.z), static_cast<int32_t>(e.w)};
           for (uint32_t t = 0; t < cnt[j]; t++) {
             if (out0 + at + t < P.capacity) P.ids[out0 + at + t] = v[t];

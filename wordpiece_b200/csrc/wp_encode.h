@@ -35,7 +35,17 @@ constexpr uint32_t SLOW_META_WALK = 1u << 27;
 constexpr uint32_t SLOW_META_TEXT = 1u << 28;    // the segment's bytes (<= 32) were copied to slow_text[] by K1
 constexpr uint32_t SLOW_TEXT_BYTES = 32;
 constexpr uint32_t SLOW_RESULT_INLINE = 0x80000000u;  // result form of an entry (after K2): word 0 = id count | this
-constexpr uint32_t SEG_RESULT_SLOW = 0x80000000u;  // seg_result: fast = id + 1, slow = this | slow index
+constexpr uint32_t SEG_RESULT_SLOW = 0x80000000u;
+constexpr uint32_t SEG_RESULT_MEMO = 0x40000000u;  // seg_result: this | memo slot (ids read from the memo table)
+
+// Word memo (per encode call): exact bytes of a short segment -> its ids.  Text repeats its rare words; the
+// first occurrence of a word that needs more than one probe is matched by K2, which records the result, and
+// later tiles settle every further occurrence in K1 with one lookup.  Slot = 2 x uint4: the 16 key bytes
+// (zero padded), then {state, id0, id1, id2}; state 0 = empty, 1 = being written, else MEMO_READY | count << 8
+// | byte length.  Cleared at the start of every call, so results never depend on earlier calls.
+constexpr uint32_t MEMO_READY = 0x80000000u;
+constexpr uint32_t MEMO_KEY_BYTES = 16;
+constexpr uint32_t MEMO_SALT = 0x5BD1E995u;  // seg_result: fast = id + 1, slow = this | slow index
 
 // Counters in device memory, zeroed before every range.
 struct RangeCounters {
@@ -55,6 +65,7 @@ struct CallCounters {
   unsigned long long long_segments;
   unsigned int overflow;             // set if a scratch capacity was exceeded (the host retries with more)
   unsigned int pad;
+  unsigned long long memo_hits;      // segments settled by the word memo in K1
 };
 
 struct EncodeParams {
@@ -80,6 +91,8 @@ struct EncodeParams {
   int32_t *tok;                     // tok_capacity ids
   uint32_t tok_capacity;
   uint32_t n_scatter_blocks;        // size of block_state
+  uint4 *memo;                      // word memo, memo_mask + 1 slots of 2 x uint4 (nullptr = off)
+  uint32_t memo_mask;
   // L2 residency hint for the vocabulary table (0 bytes = none)
   size_t persist_bytes;
   float persist_ratio;
