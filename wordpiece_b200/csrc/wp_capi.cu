@@ -253,8 +253,15 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   P.persist_ratio = v->persist_ratio;
   uint64_t launches = 0;
   uint32_t range = 0;
-  for (size_t first = 0; first < n_tiles; first += w.n_tiles, range++) {
-    const size_t count = n_tiles - first < w.n_tiles ? n_tiles - first : w.n_tiles;
+  // Ranges grow 4 MiB, 16 MiB, 64 MiB, 64 MiB, ...: the first, small ranges fill the word memo (their own
+  // unsettled words all go through K2), so that the bulk of the text already finds its repeats there.
+  size_t next_tiles = w.n_tiles;
+  if (use_memo) {
+    const size_t first_tiles = (size_t(4) << 20) / tile;
+    if (first_tiles < next_tiles) next_tiles = first_tiles;
+  }
+  for (size_t first = 0; first < n_tiles; range++) {
+    size_t count = n_tiles - first < next_tiles ? n_tiles - first : next_tiles;
     WP_CUDA(cudaMemsetAsync(v->d_work, 0, w.zero_bytes, stream));
     P.first_tile = static_cast<uint32_t>(first);
     P.n_tiles = static_cast<uint32_t>(count);
@@ -270,6 +277,8 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
       v->timing_used += 4;
     }
     WP_CUDA(wp::launch_encode_range(P, v->sm_count, stream, &launches, tev));
+    first += count;
+    next_tiles = next_tiles * 4 < w.n_tiles ? next_tiles * 4 : w.n_tiles;
   }
   g_launches.fetch_add(launches, std::memory_order_relaxed);
   info->n_tiles = static_cast<uint32_t>(n_tiles);
