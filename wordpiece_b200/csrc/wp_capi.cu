@@ -103,6 +103,7 @@ wp::DeviceVocab device_view(const wp_vocab *v) {
   d.long_bytes = v->d_long_bytes;
   d.unk_id = v->host.unk_id;
   d.han_swallow = v->host.max_len >= 2 ? 1u : 0u;
+  d.probe_pairs = v->host.slots.size() * sizeof(wp::Slot) <= (size_t(16) << 20) ? 1u : 0u;
   return d;
 }
 
@@ -253,11 +254,12 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   P.persist_ratio = v->persist_ratio;
   uint64_t launches = 0;
   uint32_t range = 0;
-  // Ranges grow 4 MiB, 16 MiB, 64 MiB, 64 MiB, ...: the first, small ranges fill the word memo (their own
-  // unsettled words all go through K2), so that the bulk of the text already finds its repeats there.
+  // Two small ranges first (2 MiB, 8 MiB): the first fills the word memo — its own unsettled words all go
+  // through K2 — the second shows whether the text repeats its words (memo_worthwhile), so that the bulk of
+  // the text, in full ranges, either finds the frequent repeats in the memo or does not pay for it.
   size_t next_tiles = w.n_tiles;
   if (use_memo) {
-    const size_t first_tiles = (size_t(4) << 20) / tile;
+    const size_t first_tiles = (size_t(2) << 20) / tile;
     if (first_tiles < next_tiles) next_tiles = first_tiles;
   }
   for (size_t first = 0; first < n_tiles; range++) {
@@ -266,6 +268,7 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
     P.first_tile = static_cast<uint32_t>(first);
     P.n_tiles = static_cast<uint32_t>(count);
     P.range_parity = range & 1u;
+    P.range_index = range;
     cudaEvent_t *tev = nullptr;
     if (v->timing) {
       while (v->timing_events.size() < v->timing_used + 4) {
@@ -278,7 +281,8 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
     }
     WP_CUDA(wp::launch_encode_range(P, v->sm_count, stream, &launches, tev));
     first += count;
-    next_tiles = next_tiles * 4 < w.n_tiles ? next_tiles * 4 : w.n_tiles;
+    // 2 MiB, then 8 MiB (enough lookups to judge whether the memo pays on this text), then full ranges
+    next_tiles = (use_memo && range == 0 && ((size_t(8) << 20) / tile) < w.n_tiles) ? (size_t(8) << 20) / tile : w.n_tiles;
   }
   g_launches.fetch_add(launches, std::memory_order_relaxed);
   info->n_tiles = static_cast<uint32_t>(n_tiles);

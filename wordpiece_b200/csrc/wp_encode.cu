@@ -1011,7 +1011,9 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   const uint16_t *slow_list = sm.slow;
   uint32_t n_slow = sm.n_slow;
   if (n_slow == 0) return;  // uniform
-  if (P.memo != nullptr && !dirty) {
+  if (P.memo != nullptr && !dirty &&
+      (P.range_index < 2 || memo_worthwhile(P.call->memo_lookups, P.call->memo_hits))) {
+    uint32_t my_lookups = 0;
     for (uint32_t base = 0; base < n_slow; base += THREADS) {
       const uint32_t i = base + tid;
       bool keep = false;
@@ -1019,6 +1021,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       if (i < n_slow) {
         ent = sm.slow[i];
         keep = true;
+        my_lookups++;  // counted per unsettled segment, eligible or not: the memo must pay for the whole slow lane
         if (!(ent & SLOW_WALK)) {
           const uint32_t k = ent & 0xFFFu;
           const int s = static_cast<int>(sm.seg_s[k] & POS_MASK);
@@ -1064,6 +1067,11 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     slow_list = sm.slow2;
     n_slow = sm.n_slow2;
     if (tid == 0 && sm.memo_hits) atomicAdd(&P.call->memo_hits, static_cast<unsigned long long>(sm.memo_hits));
+    if (P.range_index >= 1) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) my_lookups += __shfl_xor_sync(FULL, my_lookups, o);
+      if (lane == 0 && my_lookups) atomicAdd(&P.call->memo_lookups, static_cast<unsigned long long>(my_lookups));
+    }
     if (n_slow == 0) return;  // uniform
   }
 
@@ -1211,7 +1219,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams
   const uint4 *tab = reinterpret_cast<const uint4 *>(V.slots);
 
   bool have = false;       // this lane holds an unfinished segment
-  bool memo_on = P.memo != nullptr;
+  bool memo_on = P.memo != nullptr && (P.range_index < 2 || memo_worthwhile(P.call->memo_lookups, P.call->memo_hits));
   bool in_smem = false;    // ... whose bytes sit in this lane's shared-memory buffer
   uint32_t *const my_text = lane_text + tid * LANE_TEXT_WORDS;
   size_t seg_pos = 0;
@@ -1298,10 +1306,17 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams
         const uint32_t idx = (key_hash(kw[0], kw[1], kw[2], kw[3], kw[4], kw[5]) + poff) & V.slot_mask;
         uint4 sa, sb, sc, sd;
         ld_slot(tab, idx, &sa, &sb);
-        ld_slot(tab, (idx + 1) & V.slot_mask, &sc, &sd);
-        const uint32_t oc = pair_outcome(sa, sb, sc, sd, kw);
+        uint32_t oc;
+        if (V.probe_pairs) {  // uniform
+          ld_slot(tab, (idx + 1) & V.slot_mask, &sc, &sd);
+          oc = pair_outcome(sa, sb, sc, sd, kw);
+        } else {
+          sc = sa;
+          sd = sb;
+          oc = slot_len(sb.y) == 0 ? PAIR_MISS : (slot_matches(sa, sb, kw) ? PAIR_HIT0 : PAIR_BOTH_OTHER);
+        }
         if (oc == PAIR_BOTH_OTHER) {
-          poff += 2;  // both slots hold other keys: walk on, same key
+          poff += V.probe_pairs ? 2u : 1u;  // the slot(s) hold other keys: walk on, same key
         } else {
           poff = 0;
           if (oc != PAIR_MISS) {
@@ -1415,13 +1430,15 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams
             uint4 *slot = P.memo + 2 * static_cast<size_t>(idx);
             unsigned int *state = reinterpret_cast<unsigned int *>(slot + 1);
             const unsigned int old = atomicCAS(state, 0u, 1u);
-            if (old == 0u) {  // claimed: key and ids first, the READY state last
+            if (old == 0u) {
+              // claimed.  No fence between the payload and READY: the readers that need a complete slot (K1
+              // and K3) run in later kernels; a concurrent K2 lane that sees READY early can at worst fail to
+              // recognise its own word here and store a harmless duplicate one slot further.
               slot[0] = make_uint4(k0, k1, k2, k3);
               state[1] = static_cast<unsigned int>(t0);
               state[2] = static_cast<unsigned int>(t1);
               state[3] = static_cast<unsigned int>(t2);
-              __threadfence();
-              atomicExch(state, MEMO_READY | (nid << 8) | seg_len);
+              *reinterpret_cast<volatile unsigned int *>(state) = MEMO_READY | (nid << 8) | seg_len;
               placed = true;
             } else if (old == 1u) {
               placed = true;  // another lane is writing this slot right now (most likely the same word)

@@ -45,7 +45,15 @@ constexpr uint32_t SEG_RESULT_MEMO = 0x40000000u;  // seg_result: this | memo sl
 // | byte length.  Cleared at the start of every call, so results never depend on earlier calls.
 constexpr uint32_t MEMO_READY = 0x80000000u;
 constexpr uint32_t MEMO_KEY_BYTES = 16;
-constexpr uint32_t MEMO_SALT = 0x5BD1E995u;  // seg_result: fast = id + 1, slow = this | slow index
+constexpr uint32_t MEMO_SALT = 0x5BD1E995u;
+
+// The memo pays only if words repeat (natural-language text); on text whose unsettled words never repeat
+// (random strings, long CJK runs) it is switched off for the rest of the call once enough lookups of the
+// ranges >= 1 have shown that it settles less than 1/3 of ALL unsettled segments (a lookup per short
+// unsettled word, an atomic insert per miss and a dependent read in K3 per hit cost about that much).  A heuristic on speed only: ids never depend on it.
+__host__ __device__ inline bool memo_worthwhile(unsigned long long lookups, unsigned long long hits) {
+  return !(lookups > 20000ull && hits * 3ull < lookups);
+}  // seg_result: fast = id + 1, slow = this | slow index
 
 // Counters in device memory, zeroed before every range.
 struct RangeCounters {
@@ -66,6 +74,7 @@ struct CallCounters {
   unsigned int overflow;             // set if a scratch capacity was exceeded (the host retries with more)
   unsigned int pad;
   unsigned long long memo_hits;      // segments settled by the word memo in K1
+  unsigned long long memo_lookups;   // unsettled segments seen by K1's memo phase in ranges >= 1 (range 0 cannot hit)
 };
 
 struct EncodeParams {
@@ -93,6 +102,7 @@ struct EncodeParams {
   uint32_t n_scatter_blocks;        // size of block_state
   uint4 *memo;                      // word memo, memo_mask + 1 slots of 2 x uint4 (nullptr = off)
   uint32_t memo_mask;
+  uint32_t range_index;             // 0, 1, 2, ... within the call
   // L2 residency hint for the vocabulary table (0 bytes = none)
   size_t persist_bytes;
   float persist_ratio;

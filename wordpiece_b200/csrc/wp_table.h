@@ -85,6 +85,7 @@ struct DeviceVocab {
   const uint8_t *long_bytes;    // byte pool of long tokens
   int32_t unk_id;               // utils.hpp:30 / utils.cpp:112-114
   uint32_t han_swallow;         // 1 iff max_len >= 2 (an OOV Han char swallows the following run)
+  uint32_t probe_pairs;         // K2 looks at two slots per probe (pays while the table is L2-resident: <= 16 MiB)
 };
 
 }  // namespace wp
