@@ -147,6 +147,8 @@ wp_status wp_debug_longest_match(const wp_vocab *v, const char *text, size_t win
 size_t wp_debug_table_slots(const wp_vocab *v);
 size_t wp_debug_table_nodes(const wp_vocab *v);
 size_t wp_debug_long_tokens(const wp_vocab *v);
+/* code points of single-char word-initial nodes displaced from their home slot; returns their number */
+size_t wp_debug_displaced_singles(const wp_vocab *v, uint32_t *out, size_t cap);
 
 #ifdef __cplusplus
 }

@@ -335,6 +335,54 @@ def test_cpp_drop_in_runner(gpu_device, tmp_path):
     assert bad.returncode != 0
 
 
+def test_displaced_single_char_nodes(gpu_device, monkeypatch):
+    """A single-char segment whose table node is not in its home slot (another key got there first) is
+    settled by K1's rare pass, never handed to K2: the slow-list capacities assume >= 2 bytes per entry.
+    Worst case: a text of nothing but such a char (one segment per byte)."""
+    import string
+    import wordpiece_b200
+
+    rng = random.Random(0)
+    words = list(dict.fromkeys("".join(rng.choice(string.ascii_lowercase) for _ in range(rng.randint(2, 6)))
+                               for _ in range(3000)))
+    vocab = ["[UNK]"] + words + ["##" + w for w in words[:500]] + list(string.punctuation)
+    v = _vocab(vocab, gpu_device)
+    displaced = [chr(c) for c in v.debug_displaced_singles() if c < 128]
+    assert len(displaced) >= 3, displaced
+    ora = Oracle(vocab)
+    tile = wordpiece_b200.tile_bytes()
+    # every byte its own segment, all displaced; then mixed with at-home punctuation, words and spaces
+    texts = [(displaced[0] * (5 * tile + 17)).encode(), ("".join(displaced) * (tile // 2)).encode()]
+    parts = []
+    for _ in range(60000):
+        x = rng.random()
+        parts.append(rng.choice(displaced) if x < 0.3 else rng.choice(string.punctuation) if x < 0.4
+                     else rng.choice(words) if x < 0.8 else " ")
+    texts.append("".join(parts).encode())
+    for memo in ("0", "1"):
+        monkeypatch.setenv("WORDPIECE_B200_MEMO", memo)
+        monkeypatch.setenv("WORDPIECE_B200_RANGE_BYTES", str(8 * tile))
+        for t in texts:
+            assert np.array_equal(ora.encode(t), v.encode(t)), (memo, len(t))
+    v.close()
+    # multi-byte chars: the displaced nodes of the 120k vocabulary (CJK, their own segments) in running text
+    from wordpiece_b200 import synth
+
+    g = synth.generator("zh")
+    v = _vocab(g.spec.vocab, gpu_device)
+    d = [chr(c) for c in v.debug_displaced_singles()]
+    assert d
+    base = g.generate(1 << 20, seed=5).tobytes().decode("utf-8", "ignore")
+    mixed = []
+    for i in range(0, len(base), 50):
+        mixed.append(base[i:i + 50])
+        mixed.append(rng.choice(d) + rng.choice(["", " ", ",", rng.choice(d)]))
+    t = "".join(mixed).encode()
+    monkeypatch.delenv("WORDPIECE_B200_MEMO")
+    assert np.array_equal(Oracle(g.spec.vocab).encode(t), v.encode(t))
+    v.close()
+
+
 def test_word_memo(gpu_device, monkeypatch):
     """The per-call word memo (K2 records bytes -> ids of short unsettled segments, K1 of later ranges
     settles repeats with one lookup) must not change a single id.  Small ranges maximise the traffic
@@ -374,4 +422,14 @@ def test_word_memo(gpu_device, monkeypatch):
     v = _vocab(g.spec.vocab, gpu_device)
     assert np.array_equal(Oracle(g.spec.vocab).encode(text), v.encode(text))
     assert v.stats().memo_hits > 10000
+    v.close()
+    # random strings never repeat: the memo is switched off in the middle of the call (the decision is taken
+    # per tile while other tiles move the counters), and not one id may change
+    g = synth.generator("adv")
+    text = g.generate(8 << 20, seed=13).tobytes()
+    monkeypatch.setenv("WORDPIECE_B200_RANGE_BYTES", str(256 << 10))
+    v = _vocab(g.spec.vocab, gpu_device)
+    exp = Oracle(g.spec.vocab).encode(text)
+    for _ in range(3):
+        assert np.array_equal(exp, v.encode(text))
     v.close()

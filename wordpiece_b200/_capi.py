@@ -82,6 +82,7 @@ EXPORTED_SYMBOLS = [
     "wp_debug_table_slots",
     "wp_debug_table_nodes",
     "wp_debug_long_tokens",
+    "wp_debug_displaced_singles",
 ]
 
 _lib = None
@@ -144,6 +145,8 @@ def load_library() -> C.CDLL:
     for f in ("wp_debug_table_slots", "wp_debug_table_nodes", "wp_debug_long_tokens"):
         getattr(L, f).argtypes = [vp]
         getattr(L, f).restype = sz
+    L.wp_debug_displaced_singles.argtypes = [vp, C.POINTER(C.c_uint32), sz]
+    L.wp_debug_displaced_singles.restype = sz
     _lib = L
     return L
 
@@ -251,6 +254,13 @@ class Vocab:
             "nodes": int(self._L.wp_debug_table_nodes(self._h)),
             "long_tokens": int(self._L.wp_debug_long_tokens(self._h)),
         }
+
+    def debug_displaced_singles(self) -> list:
+        """Code points of single-char word-initial table nodes that are not in their home slot (test hook)."""
+        n = int(self._L.wp_debug_displaced_singles(self._h, None, 0))
+        buf = (C.c_uint32 * max(n, 1))()
+        self._L.wp_debug_displaced_singles(self._h, buf, n)
+        return [int(buf[i]) for i in range(n)]
 
     def debug_longest_match(self, text: bytes, kind: int):
         ln, tid = C.c_uint32(), C.c_int32()

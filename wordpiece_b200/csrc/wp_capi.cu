@@ -796,4 +796,25 @@ size_t wp_debug_table_slots(const wp_vocab *v) { return v ? v->host.slots.size()
 size_t wp_debug_table_nodes(const wp_vocab *v) { return v ? v->host.n_nodes : 0; }
 size_t wp_debug_long_tokens(const wp_vocab *v) { return v ? v->host.n_long : 0; }
 
+/* Fills out[0..cap) with the code points of single-char word-initial nodes that do NOT sit in their home
+ * slot (another key got there first); returns how many there are.  Lets a test aim at K1's rare pass. */
+size_t wp_debug_displaced_singles(const wp_vocab *v, uint32_t *out, size_t cap) {
+  if (!v) return 0;
+  size_t n = 0;
+  const uint32_t mask = static_cast<uint32_t>(v->host.slots.size() - 1);
+  for (size_t i = 0; i < v->host.slots.size(); i++) {
+    const wp::Slot &s = v->host.slots[i];
+    const uint32_t len = wp::slot_len(s.w[5]);
+    if (len == 0 || len > 4 || ((s.w[5] >> 24) & 1u) != wp::WP_KIND_PREFIX) continue;
+    if (wp::utf8_lead_len(s.w[0] & 0xFFu) != len) continue;  // more than one char
+    if ((wp::key_hash(s.w[0], s.w[1], s.w[2], s.w[3], s.w[4], s.w[5] & wp::WP_W5_KEYMASK) & mask) == i) continue;
+    uint32_t cp = 0;
+    if (len == 1) cp = s.w[0] & 0xFFu;
+    else wp::utf8_decode(s.w[0] & 0xFFu, (s.w[0] >> 8) & 0xFFu, (s.w[0] >> 16) & 0xFFu, s.w[0] >> 24, 4u, &cp);
+    if (n < cap && out) out[n] = cp;
+    n++;
+  }
+  return n;
+}
+
 }  // extern "C"

@@ -88,6 +88,8 @@ struct __align__(16) TileSmem {
   uint16_t slow2[MAX_TILE_SLOW];       // slow[] minus the segments the word memo settled
   uint32_t n_slow2;
   uint32_t memo_hits;
+  uint32_t memo_use;                   // this tile runs the memo phase (decided by one thread)
+  uint32_t any_single;                 // some single-char segment is still to be settled (see S2a)
   uint32_t m_lead[NCHUNK + 1];         // valid lead bytes
   uint32_t m_space[NCHUNK + 1];
   uint32_t m_punct[NCHUNK + 1];
@@ -704,6 +706,24 @@ __device__ __forceinline__ void init_key_mask(uint4 *key_mask, int tid) {
 
 // ================================================================ K1: split
 
+// A single-char segment whose home slot holds another key: walk the probe sequence to the key or to an
+// empty slot.  Rare (a few lanes per tile at most), so kept out of line; returns the node's term id
+// (possibly WP_NO_ID) or SINGLE_WALK_MISS.
+constexpr int32_t SINGLE_WALK_MISS = WP_NO_ID - 1;
+constexpr uint16_t PARK_PENDING = 0xFFFFu;  // parked high half of a result is < 0x4000 (results are < 2^30)
+__device__ __noinline__ int32_t single_char_walk(const uint4 *tab, uint32_t slot_mask, uint32_t k0, uint32_t k1,
+                                                 uint32_t k2, uint32_t k3, uint32_t k4, uint32_t k5) {
+  const uint32_t kw[6] = {k0, k1, k2, k3, k4, k5};
+  uint32_t idx = (key_hash(k0, k1, k2, k3, k4, k5) + 1) & slot_mask;
+  for (;;) {
+    uint4 a, b;
+    ld_slot(tab, idx, &a, &b);
+    if (slot_len(b.y) == 0) return SINGLE_WALK_MISS;
+    if (slot_matches(a, b, kw)) return static_cast<int32_t>(b.z);
+    idx = (idx + 1) & slot_mask;
+  }
+}
+
 __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
@@ -720,6 +740,12 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     sm.n_slow = 0;
     sm.n_slow2 = 0;
     sm.memo_hits = 0;
+    sm.any_single = 0;
+  }
+  if (tid == 32) {
+    // whether the memo is still worth its lookups was decided by K2 of the previous range (uniform over this
+    // range: the phase has barriers); read here, next to the ticket, so that the round trip is hidden
+    sm.memo_use = P.memo != nullptr && (P.range_index < 2 || P.call->memo_off == 0u);
   }
   init_key_mask(sm.key_mask, tid);
   __syncthreads();
@@ -954,19 +980,25 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     for (int u = 0; u < PER_TURN; u++) {
       bool settled = false;
       if (wlen[u] != 0) {
-        // one slot only here (K2 looks at pairs): a probe that lands on another key's slot is left to K2
+        // one slot only here (K2 looks at pairs): a probe that lands on another key's slot is left to K2 —
+        // except for single-char segments: every segment handed to K2 must have at least two bytes (the
+        // slow-list capacities rely on it), so those are marked and settled by the pass below (rare)
         const bool empty = slot_len(sb[u].y) == 0;
         const bool match = !empty && slot_matches(sa[u], sb[u], kw[u]);
         const int32_t term = static_cast<int32_t>(sb[u].z);
         const bool hit = match && term != WP_NO_ID && wlen[u] <= WP_KEY_BYTES;
-        const bool single_miss = wlen[u] == first_len[u] && empty;  // a one-char segment that is no token
-        const bool single_dead = wlen[u] == first_len[u] && match;      // ... or only a prefix of tokens
-        if (hit || single_miss || single_dead) {
+        const bool single = wlen[u] == first_len[u];  // no token (empty), only a prefix of tokens, or a collision
+        if (hit || single) {
           // settled: park the result (id + 1) in the two list entries of the segment, which are no longer
           // needed, until the tile knows its first global segment number
           const uint32_t res = static_cast<uint32_t>((hit ? term : V.unk_id) + 1);
-          sm.seg_s[kk[u]] = static_cast<uint16_t>(res);
-          sm.seg_e[kk[u] + skip] = static_cast<uint16_t>(res >> 16);
+          if (single && !empty && !match) {
+            sm.seg_e[kk[u] + skip] = PARK_PENDING;  // seg_s keeps the position for the pass below
+            sm.any_single = 1u;
+          } else {
+            sm.seg_s[kk[u]] = static_cast<uint16_t>(res);
+            sm.seg_e[kk[u] + skip] = static_cast<uint16_t>(res >> 16);
+          }
           settled = true;
         } else {
           // miss on an empty slot: K2 may skip the whole-window probe; match or collision: K2 redoes it
@@ -986,6 +1018,20 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     }
   }
   __syncthreads();
+
+  // ---- (rare) single-char segments whose home slot holds another key: follow the probe sequence
+  if (sm.any_single) {  // uniform
+    for (uint32_t k = tid; k < n_segs; k += THREADS) {
+      if (!((sm.settled[k >> 5] >> (k & 31)) & 1u) || sm.seg_e[k + skip] != PARK_PENDING) continue;
+      uint32_t r[6], key[6];
+      load_window(buf, static_cast<int>(sm.seg_s[k] & POS_MASK), r);
+      make_key_tab(sm.key_mask, r, utf8_lead_len(r[0] & 0xFFu), WP_KIND_PREFIX, key);
+      const int32_t term = single_char_walk(tab, V.slot_mask, key[0], key[1], key[2], key[3], key[4], key[5]);
+      const uint32_t res = static_cast<uint32_t>((term >= 0 ? term : V.unk_id) + 1);
+      sm.seg_s[k] = static_cast<uint16_t>(res);
+      sm.seg_e[k + skip] = static_cast<uint16_t>(res >> 16);
+    }
+  }
 
   // ---- the walk back over earlier tiles (short by now), then the settled results go out coalesced
   if (warp == 0) {
@@ -1011,8 +1057,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   const uint16_t *slow_list = sm.slow;
   uint32_t n_slow = sm.n_slow;
   if (n_slow == 0) return;  // uniform
-  if (P.memo != nullptr && !dirty &&
-      (P.range_index < 2 || memo_worthwhile(P.call->memo_lookups, P.call->memo_hits))) {
+  if (sm.memo_use && !dirty) {  // uniform
     uint32_t my_lookups = 0;
     for (uint32_t base = 0; base < n_slow; base += THREADS) {
       const uint32_t i = base + tid;
@@ -1209,6 +1254,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams
   init_key_mask(key_mask, tid);
   __syncthreads();
 
+  if (P.call->overflow) return;  // a K1 tile gave up (scratch too small): its entries are unwritten, the host retries
   const uint32_t n_slow = min(P.counters->n_slow, P.slow_capacity);
   const uint32_t spill_base = min(P.counters->tok_reserved, P.tok_capacity);
   const uint32_t n_warps = gridDim.x * (MATCH_THREADS / 32);
@@ -1219,7 +1265,11 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams
   const uint4 *tab = reinterpret_cast<const uint4 *>(V.slots);
 
   bool have = false;       // this lane holds an unfinished segment
-  bool memo_on = P.memo != nullptr && (P.range_index < 2 || memo_worthwhile(P.call->memo_lookups, P.call->memo_hits));
+  // K1 of this range is done, so the counters are final: every lane reads the same verdict, and one thread
+  // records it for the K1 tiles of the next range (in a cache line of its own: the counters' line is hot)
+  const bool worth = memo_worthwhile(P.call->memo_lookups, P.call->memo_hits);
+  if (blockIdx.x == 0 && tid == 0 && !worth) P.call->memo_off = 1u;
+  bool memo_on = P.memo != nullptr && (P.range_index < 2 || worth);
   bool in_smem = false;    // ... whose bytes sit in this lane's shared-memory buffer
   uint32_t *const my_text = lane_text + tid * LANE_TEXT_WORDS;
   size_t seg_pos = 0;
@@ -1475,6 +1525,7 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
   const unsigned long long n_segs = min(P.counters->n_segs, static_cast<unsigned long long>(P.seg_capacity));
   const uint32_t n_blocks = static_cast<uint32_t>((n_segs + SCATTER_SEGS - 1) / SCATTER_SEGS);
   const unsigned long long ids_in = P.call->ids_total[P.range_parity];
+  if (P.call->overflow) return;  // uniform over the grid (K1 and K2 are done): the host retries the call
   if (n_blocks == 0) {
     if (blockIdx.x == 0 && tid == 0) P.call->ids_total[P.range_parity ^ 1u] = ids_in;
     return;

@@ -49,7 +49,8 @@ constexpr uint32_t MEMO_SALT = 0x5BD1E995u;
 
 // The memo pays only if words repeat (natural-language text); on text whose unsettled words never repeat
 // (random strings, long CJK runs) it is switched off for the rest of the call once enough lookups of the
-// ranges >= 1 have shown that it settles less than 1/3 of ALL unsettled segments (a lookup per short
+// ranges >= 1 have shown that it settles less than 1/3 of ALL unsettled segments (judged once per range, by K2,
+// for the ranges after it) (a lookup per short
 // unsettled word, an atomic insert per miss and a dependent read in K3 per hit cost about that much).  A heuristic on speed only: ids never depend on it.
 __host__ __device__ inline bool memo_worthwhile(unsigned long long lookups, unsigned long long hits) {
   return !(lookups > 20000ull && hits * 3ull < lookups);
@@ -75,7 +76,11 @@ struct CallCounters {
   unsigned int pad;
   unsigned long long memo_hits;      // segments settled by the word memo in K1
   unsigned long long memo_lookups;   // unsettled segments seen by K1's memo phase in ranges >= 1 (range 0 cannot hit)
+  unsigned int pad2[18];             // (the counters above are hit by atomics from every tile)
+  unsigned int memo_off;             // set by K2 once the memo has shown not to pay (memo_worthwhile); read by K1
+  unsigned int pad3[31];
 };
+static_assert(offsetof(CallCounters, memo_off) % 128 == 0, "memo_off sits in a cache line of its own");
 
 struct EncodeParams {
   DeviceVocab vocab;
