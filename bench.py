@@ -325,8 +325,8 @@ def main():
     achieved = algo_bytes / (k_ms[dom] * 1e-3) / 1e9
     prof = traffic_from_profile()
     traffic = None
-    if prof and prof.get("kernel") == names[dom]:
-        traffic = prof.get("dram_bytes_per_launch")
+    if prof and names[dom] in prof.get("per_kernel", {}):
+        traffic = prof["per_kernel"][names[dom]].get("dram_bytes")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": names[dom],
                 "algo_bytes_per_launch": algo_bytes / max(n_ranges, 1), "launches_per_step": n_ranges,
@@ -339,6 +339,8 @@ def main():
                         "range (CUDA events on the launching stream); a step = launches_per_step x (scratch memset + "
                         "K1 + K2 + K3)"}
     if prof:
+        # the capture is one launch over a FULL 64 MiB range (a step also has a 2 MiB, an 8 MiB and a tail range)
+        roofline["traffic_launch_algo_bytes"] = algo_bytes * min(1.0, 64.0 * MIB / n_bytes)
         roofline["traffic_source"] = prof.get("source")
 
     # ---- e2e: the host-buffer C-ABI call (pinned host text in, host ids out), copies inside the timed region
