@@ -85,8 +85,7 @@ struct __align__(16) TileSmem {
   uint16_t seg_e[WINDOW + 64];         // j-th segment end in the window
   uint16_t slow[MAX_TILE_SLOW];        // segments the whole-window probe did not settle: ordinal | flags
   uint32_t settled[TILE / 32];         // bit k: segment k was settled by S2a (its result is parked in seg_s/seg_e)
-  uint16_t slow2[MAX_TILE_SLOW];       // slow[] minus the segments the word memo settled
-  uint32_t n_slow2;
+  uint32_t n_slow2;                    // entries of slow[] left after the word memo settled its share
   uint32_t memo_hits;
   uint32_t memo_use;                   // this tile runs the memo phase (decided by one thread)
   uint32_t any_single;                 // some single-char segment is still to be settled (see S2a)
@@ -100,7 +99,6 @@ struct __align__(16) TileSmem {
   uint8_t spill[NCHUNK + 1];           // bytes by which the chunk's last sequence runs into the next chunk
   uint4 key_mask[KEY_MASK_ROW * (WP_KEY_BYTES + 1)];  // row k: masks of the six key words for a k-byte key, then k << 16
   uint32_t warp_sums[WARPS];
-  uint32_t tile_index;
   uint32_t prev_class;                 // class of the last valid char before the tile
   uint32_t left_spill;                 // bytes of the tile start covered by a sequence that began before it
   uint32_t n_segs;                     // owned segments in this tile
@@ -732,10 +730,9 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   const int warp = tid >> 5;
   const DeviceVocab &V = P.vocab;
 
-  // tiles are handed out in launch order so that a tile's predecessors are
-  // always already running (decoupled look-back needs forward progress)
+  // tile = block index: blocks of a 1-D grid are dispatched in index order, so a tile's predecessors are
+  // always already running (decoupled look-back needs forward progress); no ticket round trip
   if (tid == 0) {
-    sm.tile_index = atomicAdd(&P.counters->split_ticket, 1u);
     sm.left_spill = 0;
     sm.n_slow = 0;
     sm.n_slow2 = 0;
@@ -749,7 +746,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   }
   init_key_mask(sm.key_mask, tid);
   __syncthreads();
-  const uint32_t rel_tile = sm.tile_index;                 // within the range
+  const uint32_t rel_tile = blockIdx.x;                    // within the range
   const size_t t0 = (static_cast<size_t>(P.first_tile) + rel_tile) * TILE;
   const size_t n = P.n_bytes;
   const size_t avail = n - t0;  // > 0
@@ -1054,62 +1051,86 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
 
   // ---- word memo: an unsettled segment of at most 16 bytes whose exact bytes were matched before (by K2,
   // in an earlier range of this call) is settled here with one lookup; the rest form the final slow list
-  const uint16_t *slow_list = sm.slow;
   uint32_t n_slow = sm.n_slow;
   if (n_slow == 0) return;  // uniform
   if (sm.memo_use && !dirty) {  // uniform
+    // two entries per lane and round, all lookups of a round in flight together; the list is compacted in
+    // place (a round's survivors land below the entries the next round reads)
+    constexpr int MP = 2;
     uint32_t my_lookups = 0;
-    for (uint32_t base = 0; base < n_slow; base += THREADS) {
-      const uint32_t i = base + tid;
-      bool keep = false;
-      uint32_t ent = 0;
-      if (i < n_slow) {
-        ent = sm.slow[i];
-        keep = true;
-        my_lookups++;  // counted per unsettled segment, eligible or not: the memo must pay for the whole slow lane
-        if (!(ent & SLOW_WALK)) {
-          const uint32_t k = ent & 0xFFFu;
-          const int s = static_cast<int>(sm.seg_s[k] & POS_MASK);
-          const uint32_t j = k + skip;
-          const int e = j < n_ends ? static_cast<int>(sm.seg_e[j]) : limit;
-          const uint32_t len = static_cast<uint32_t>(e - s);
-          if (len <= MEMO_KEY_BYTES) {
-            uint32_t r[6];
-            load_window(buf, s, r);
-            const uint4 ma = sm.key_mask[KEY_MASK_ROW * len];
-            const uint32_t k0 = r[0] & ma.x, k1 = r[1] & ma.y, k2 = r[2] & ma.z, k3 = r[3] & ma.w;
-            uint32_t idx = key_hash(k0, k1, k2, k3, len, MEMO_SALT) & P.memo_mask;
-            for (int t = 0; t < 2; t++) {
-              const uint4 a = __ldg(P.memo + 2 * static_cast<size_t>(idx));
-              const uint4 b = __ldg(P.memo + 2 * static_cast<size_t>(idx) + 1);
-              if (b.x == 0) break;
-              if ((b.x & MEMO_READY) && (b.x & 0xFFu) == len && a.x == k0 && a.y == k1 && a.z == k2 && a.w == k3) {
-                P.seg_result[seg_base + k] = SEG_RESULT_MEMO | idx;
-                keep = false;
-                break;
-              }
-              idx = (idx + 1) & P.memo_mask;
+    for (uint32_t base = 0; base < n_slow; base += MP * THREADS) {
+      uint32_t ent[MP], mlen[MP], midx[MP], mk[MP][4];
+      uint4 ma[MP], mb[MP];
+      bool keep[MP], have[MP];
+#pragma unroll
+      for (int u = 0; u < MP; u++) {
+        const uint32_t i = base + u * THREADS + tid;
+        have[u] = i < n_slow;
+        keep[u] = have[u];
+        ent[u] = 0;
+        mlen[u] = 0;
+        midx[u] = 0;
+        ma[u] = make_uint4(0, 0, 0, 0);
+        mb[u] = make_uint4(0, 0, 0, 0);
+        if (have[u]) {
+          ent[u] = sm.slow[i];
+          my_lookups++;  // counted per unsettled segment, eligible or not: the memo must pay for the whole slow lane
+          if (!(ent[u] & SLOW_WALK)) {
+            const uint32_t k = ent[u] & 0xFFFu;
+            const int s = static_cast<int>(sm.seg_s[k] & POS_MASK);
+            const uint32_t j = k + skip;
+            const int e = j < n_ends ? static_cast<int>(sm.seg_e[j]) : limit;
+            const uint32_t len = static_cast<uint32_t>(e - s);
+            if (len <= MEMO_KEY_BYTES) {
+              uint32_t r[6];
+              load_window(buf, s, r);
+              const uint4 km = sm.key_mask[KEY_MASK_ROW * len];
+              mk[u][0] = r[0] & km.x; mk[u][1] = r[1] & km.y; mk[u][2] = r[2] & km.z; mk[u][3] = r[3] & km.w;
+              midx[u] = key_hash(mk[u][0], mk[u][1], mk[u][2], mk[u][3], len, MEMO_SALT) & P.memo_mask;
+              ma[u] = __ldg(P.memo + 2 * static_cast<size_t>(midx[u]));
+              mb[u] = __ldg(P.memo + 2 * static_cast<size_t>(midx[u]) + 1);
+              mlen[u] = len;
             }
           }
         }
       }
-      const uint32_t keepm = __ballot_sync(FULL, keep);
-      const uint32_t hitm = __ballot_sync(FULL, i < n_slow && !keep);
-      if (keepm) {
-        uint32_t at = 0;
-        const int leader = __ffs(keepm) - 1;
-        if (lane == leader) {
-          at = atomicAdd(&sm.n_slow2, static_cast<uint32_t>(__popc(keepm)));
-          if (hitm) atomicAdd(&sm.memo_hits, static_cast<uint32_t>(__popc(hitm)));
+#pragma unroll
+      for (int u = 0; u < MP; u++) {
+        if (mlen[u] == 0) continue;
+        for (int t = 0;; t++) {
+          if (mb[u].x == 0) break;
+          if ((mb[u].x & MEMO_READY) && (mb[u].x & 0xFFu) == mlen[u] && ma[u].x == mk[u][0] && ma[u].y == mk[u][1] &&
+              ma[u].z == mk[u][2] && ma[u].w == mk[u][3]) {
+            P.seg_result[seg_base + (ent[u] & 0xFFFu)] = SEG_RESULT_MEMO | midx[u];
+            keep[u] = false;
+            break;
+          }
+          if (t == 1) break;  // K2 inserts within a few slots of home; two are looked at here
+          midx[u] = (midx[u] + 1) & P.memo_mask;
+          ma[u] = __ldg(P.memo + 2 * static_cast<size_t>(midx[u]));
+          mb[u] = __ldg(P.memo + 2 * static_cast<size_t>(midx[u]) + 1);
         }
-        at = __shfl_sync(FULL, at, leader);
-        if (keep) sm.slow2[at + __popc(keepm & ((1u << lane) - 1u))] = static_cast<uint16_t>(ent);
-      } else if (hitm && lane == 0) {
-        atomicAdd(&sm.memo_hits, static_cast<uint32_t>(__popc(hitm)));
+      }
+      __syncthreads();  // every entry of this round has been read
+#pragma unroll
+      for (int u = 0; u < MP; u++) {
+        const uint32_t keepm = __ballot_sync(FULL, keep[u]);
+        const uint32_t hitm = __ballot_sync(FULL, have[u] && !keep[u]);
+        if (keepm) {
+          uint32_t at = 0;
+          const int leader = __ffs(keepm) - 1;
+          if (lane == leader) {
+            at = atomicAdd(&sm.n_slow2, static_cast<uint32_t>(__popc(keepm)));
+            if (hitm) atomicAdd(&sm.memo_hits, static_cast<uint32_t>(__popc(hitm)));
+          }
+          at = __shfl_sync(FULL, at, leader);
+          if (keep[u]) sm.slow[at + __popc(keepm & ((1u << lane) - 1u))] = static_cast<uint16_t>(ent[u]);
+        } else if (hitm && lane == 0) {
+          atomicAdd(&sm.memo_hits, static_cast<uint32_t>(__popc(hitm)));
+        }
       }
     }
     __syncthreads();
-    slow_list = sm.slow2;
     n_slow = sm.n_slow2;
     if (tid == 0 && sm.memo_hits) atomicAdd(&P.call->memo_hits, static_cast<unsigned long long>(sm.memo_hits));
     if (P.range_index >= 1) {
@@ -1129,7 +1150,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     const uint32_t hi = min(n_slow, lo + per);
     uint32_t my_len = 0, n_walk = 0;
     for (uint32_t i = lo; i < hi; i++) {
-      const uint32_t ent = slow_list[i];
+      const uint32_t ent = sm.slow[i];
       const uint32_t k = ent & 0xFFFu;
       if (dirty || (ent & SLOW_WALK)) {
         n_walk += (ent & SLOW_WALK) ? 1u : 0u;
@@ -1161,7 +1182,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       return;  // uniform
     }
     for (uint32_t i = lo; i < hi; i++) {
-      const uint32_t ent = slow_list[i];
+      const uint32_t ent = sm.slow[i];
       const uint32_t k = ent & 0xFFFu;
       const uint32_t sv = sm.seg_s[k];
       int wpos = static_cast<int>(sv & POS_MASK);
