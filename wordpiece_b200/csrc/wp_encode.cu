@@ -123,6 +123,8 @@ __device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return *reinterpr
 
 // One 32-byte table slot with ONE 256-bit load (sm_100: LDG.E.256) through the read-only path: half the
 // L1 wavefronts of two 16-byte gathers — the probes are the dominant L1 traffic of K2.
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void ld_slot(const uint4 *tab, uint32_t idx, uint4 *a, uint4 *b) {
   asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(a->x), "=r"(a->y), "=r"(a->z), "=r"(a->w), "=r"(b->x), "=r"(b->y), "=r"(b->z), "=r"(b->w)
@@ -1304,6 +1306,11 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams
     if (needm && cursor < cursor_end) {
       const uint32_t i = cursor + __popc(needm & ((1u << lane) - 1u));
       cursor += __popc(needm);  // may pass cursor_end; entries beyond it are simply not taken
+      if (cursor + lane < cursor_end) {
+        // the next 32 entries of this warp's share: by the time a lane takes one, it sits in L1
+        prefetch_l1(&P.slow[cursor + lane]);
+        prefetch_l1(P.slow_text + 2 * static_cast<size_t>(cursor + lane));
+      }
       if (!have && i < cursor_end) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(&P.slow[i]));
         const uint32_t meta = raw.y;
