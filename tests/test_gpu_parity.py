@@ -276,12 +276,29 @@ def test_host_buffer_pipeline(gpu_device, monkeypatch):
         n = v.encode_into(text, out)
         assert n == len(exp) and np.array_equal(out[:n], exp) and (out[n:] == -9).all(), chunk
         assert v.stats().kernel_launches >= 3 * (len(text) // chunk)
+    # the chunks of one call share the word memo: the first clears and warms it, later ones only use it
+    monkeypatch.setenv("WORDPIECE_B200_MEMO", "1")
+    monkeypatch.setenv("WORDPIECE_B200_PIPE_CHUNK", "30000")
+    for _ in range(2):
+        out[:] = -9
+        n = v.encode_into(text, out)
+        assert n == len(exp) and np.array_equal(out[:n], exp) and (out[n:] == -9).all()
+    monkeypatch.delenv("WORDPIECE_B200_MEMO")
     # too small a buffer: exact count reported
     from wordpiece_b200 import WordPieceError
 
     with pytest.raises(WordPieceError) as ei:
         v.encode_into(text, np.zeros(len(exp) // 3, np.int32))
     assert ei.value.status == 5
+    # pinned id buffer, also not 16-byte aligned
+    import torch
+
+    pin = torch.full((len(exp) + 5,), -9, dtype=torch.int32).pin_memory()
+    pout = pin.numpy()
+    for off in (0, 1, 3):
+        pout[:] = -9
+        n = v.encode_into(text, pout[off:])
+        assert n == len(exp) and np.array_equal(pout[off:off + n], exp) and (pout[:off] == -9).all()
     # no space within a chunk: falls back, same ids
     monkeypatch.setenv("WORDPIECE_B200_PIPE_CHUNK", "4096")
     glued = text[:50_000] + b"x" * 9000 + text[50_000:]

@@ -206,8 +206,10 @@ struct EnqueueInfo {
 
 // Enqueue the kernels for a whole text on `stream`: K1/K2/K3 per range of at most kRangeBytesMax bytes.
 // No synchronisation.  The running id count ends up in d_call->ids_total[n_ranges & 1].
+// `warm` = a later chunk of one pipelined call: the memo is neither cleared nor warmed up again.
 wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_t *d_ids, size_t capacity,
-                         cudaStream_t stream, size_t spill_ids, EnqueueInfo *info, bool memo_reset = true) {
+                         cudaStream_t stream, size_t spill_ids, EnqueueInfo *info, bool warm = false,
+                         size_t call_bytes = 0) {
   const size_t tile = wp::encode_tile_bytes();
   const size_t n_tiles = (n_bytes + tile - 1) / tile;
   if (n_tiles > 0x7FFFFFFFull) return fail(WP_ERR_INVALID_ARG, "text too large for one call (> 2^31 tiles)");
@@ -222,13 +224,13 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   if (st != WP_OK) return st;
   WP_CUDA(cudaMemsetAsync(v->d_call, 0, sizeof(wp::CallCounters), stream));
   v->timing_used = 0;
-  bool use_memo = n_bytes >= kMemoMinBytes;
+  bool use_memo = (call_bytes ? call_bytes : n_bytes) >= kMemoMinBytes;  // judged on the whole user call
   if (const char *e = std::getenv("WORDPIECE_B200_MEMO")) use_memo = std::atoi(e) != 0;  // 0 = off, 1 = on (tests)
   if (use_memo) {
     if (!v->d_memo) WP_CUDA(cudaMalloc(&v->d_memo, static_cast<size_t>(kMemoSlots) * 32));
     // every user call starts with an empty memo: results never depend on earlier calls (the chunks of one
     // pipelined host-buffer call share it)
-    if (memo_reset) WP_CUDA(cudaMemsetAsync(v->d_memo, 0, static_cast<size_t>(kMemoSlots) * 32, stream));
+    if (!warm) WP_CUDA(cudaMemsetAsync(v->d_memo, 0, static_cast<size_t>(kMemoSlots) * 32, stream));
   }
   wp::EncodeParams P{};
   P.vocab = device_view(v);
@@ -258,7 +260,7 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   // through K2 — the second shows whether the text repeats its words (memo_worthwhile), so that the bulk of
   // the text, in full ranges, either finds the frequent repeats in the memo or does not pay for it.
   size_t next_tiles = w.n_tiles;
-  if (use_memo) {
+  if (use_memo && !warm) {
     const size_t first_tiles = (size_t(2) << 20) / tile;
     if (first_tiles < next_tiles) next_tiles = first_tiles;
   }
@@ -268,7 +270,7 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
     P.first_tile = static_cast<uint32_t>(first);
     P.n_tiles = static_cast<uint32_t>(count);
     P.range_parity = range & 1u;
-    P.range_index = range;
+    P.range_index = warm ? range + 2 : range;
     cudaEvent_t *tev = nullptr;
     if (v->timing) {
       while (v->timing_events.size() < v->timing_used + 4) {
@@ -282,7 +284,7 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
     WP_CUDA(wp::launch_encode_range(P, v->sm_count, stream, &launches, tev));
     first += count;
     // 2 MiB, then 8 MiB (enough lookups to judge whether the memo pays on this text), then full ranges
-    next_tiles = (use_memo && range == 0 && ((size_t(8) << 20) / tile) < w.n_tiles) ? (size_t(8) << 20) / tile : w.n_tiles;
+    next_tiles = (use_memo && !warm && range == 0 && ((size_t(8) << 20) / tile) < w.n_tiles) ? (size_t(8) << 20) / tile : w.n_tiles;
   }
   g_launches.fetch_add(launches, std::memory_order_relaxed);
   info->n_tiles = static_cast<uint32_t>(n_tiles);
@@ -355,14 +357,24 @@ size_t pipe_chunk_bytes() {
   return kPipeChunk;
 }
 
+// The first chunks grow (chunk/8, /4, /2, then full) and the last ones shrink the same way: the pipeline's
+// fill (copy-in + encode of the first chunk) and drain (encode + copy-out of the last) are the only parts
+// of the call that do not overlap with a PCIe copy in the other direction.
 bool plan_chunks(const char *text, size_t n, size_t chunk, std::vector<size_t> *cuts) {
   cuts->clear();
   cuts->push_back(0);
   size_t start = 0;
-  while (n - start > chunk) {
-    size_t end = start + chunk;
+  const size_t small = chunk / 8 >= 64 ? chunk / 8 : chunk;
+  for (size_t j = 0;; j++) {
+    const size_t remaining = n - start;
+    size_t want = j < 3 ? small << j : chunk;
+    if (want > chunk) want = chunk;
+    const size_t tail = remaining / 2 > small ? remaining / 2 : small;
+    if (want > tail) want = tail;
+    if (remaining <= want) break;
+    size_t end = start + want;
     size_t cut = end;
-    const size_t floor = start + chunk / 2;
+    const size_t floor = start + want / 2;
     while (cut > floor && !is_ascii_space(static_cast<unsigned char>(text[cut - 1]))) cut--;
     if (cut <= floor) return false;
     cuts->push_back(cut);
@@ -421,7 +433,7 @@ wp_status encode_pipelined(wp_vocab *v, const char *text, size_t n_bytes, int32_
     WP_CUDA(cudaMemcpyAsync(sl.d_text, text + begin, len, cudaMemcpyHostToDevice, v->s_h2d));
     WP_CUDA(cudaEventRecord(sl.h2d_done, v->s_h2d));
     WP_CUDA(cudaStreamWaitEvent(v->stream, sl.h2d_done, 0));
-    st = enqueue_encode(v, sl.d_text, len, sl.d_ids, kPipeChunk, v->stream, 0, &infos[i], /*memo_reset=*/i == 0);
+    st = enqueue_encode(v, sl.d_text, len, sl.d_ids, kPipeChunk, v->stream, 0, &infos[i], /*warm=*/i != 0, n_bytes);
     if (st != WP_OK) return st;
     WP_CUDA(cudaMemcpyAsync(sl.h_call, v->d_call, sizeof(wp::CallCounters), cudaMemcpyDeviceToHost, v->stream));
     WP_CUDA(cudaEventRecord(sl.cmp_done, v->stream));
