@@ -47,9 +47,11 @@ struct DeviceGuard {
   }
 };
 
-constexpr size_t kRangeBytesMax = size_t(64) << 20;
+constexpr size_t kRangeBytesMax = size_t(64) << 20;  // text bytes encoded per K1/K2/K3 round (bounds the scratch)
 constexpr uint32_t kMemoSlots = 1u << 20;            // word memo: 32 MiB of 32-byte slots
-constexpr size_t kMemoMinBytes = size_t(4) << 20;    // texts below this skip the memo (it would only cost the reset)  // text bytes encoded per K1/K2/K3 round (bounds the scratch)
+constexpr size_t kMemoMinBytes = size_t(4) << 20;    // texts below this skip the memo (it would only cost the reset)
+static_assert(kRangeBytesMax / 2 + 1024 <= (size_t(1) << wp::SEG_SLOW_INDEX_BITS), "slow indices must fit seg_result");
+static_assert(kMemoSlots <= (1u << wp::SEG_MEMO_SLOT_BITS), "memo slots must fit seg_result");
 
 }  // namespace
 
@@ -216,7 +218,7 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   size_t range_max = kRangeBytesMax;
   if (const char *e = std::getenv("WORDPIECE_B200_RANGE_BYTES")) {  // test hook: force several ranges on small texts
     const long long x = std::atoll(e);
-    if (x > 0) range_max = (static_cast<size_t>(x) + tile - 1) / tile * tile;
+    if (x > 0 && static_cast<size_t>(x) < range_max) range_max = (static_cast<size_t>(x) + tile - 1) / tile * tile;
   }
   const size_t range_bytes = n_bytes < range_max ? n_bytes : range_max;
   const Workspace w = plan_workspace(range_bytes, spill_ids ? spill_ids : range_bytes + tile);

@@ -1103,7 +1103,8 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
           if (mb[u].x == 0) break;
           if ((mb[u].x & MEMO_READY) && (mb[u].x & 0xFFu) == mlen[u] && ma[u].x == mk[u][0] && ma[u].y == mk[u][1] &&
               ma[u].z == mk[u][2] && ma[u].w == mk[u][3]) {
-            P.seg_result[seg_base + (ent[u] & 0xFFFu)] = SEG_RESULT_MEMO | midx[u];
+            P.seg_result[seg_base + (ent[u] & 0xFFFu)] =
+                SEG_RESULT_MEMO | (((mb[u].x >> 8) & 3u) << SEG_MEMO_SLOT_BITS) | midx[u];
             keep[u] = false;
             break;
           }
@@ -1211,7 +1212,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       out.meta = static_cast<uint32_t>((pos >> 32) & 0xFFu) | (len << 8) | ((sv >> 14) << 24) |
                  ((ent & SLOW_FIRST_MISSED) ? SLOW_META_MISSED : 0u) | (walk ? SLOW_META_WALK : 0u);
       out.tok_off = tok_base + run;
-      out.cnt = 0;
+      out.seg = static_cast<uint32_t>(seg_base + k);
       run += len;
       if (!walk && len <= SLOW_TEXT_BYTES) {
         // K2 would otherwise fetch these bytes from DRAM again, one random sector per piece
@@ -1252,7 +1253,9 @@ __device__ __noinline__ void match_walk(const EncodeParams &P, uint32_t i, size_
   } else {
     P.call->overflow = 1u;
   }
+  const uint32_t seg = P.slow[i].seg;
   *reinterpret_cast<uint4 *>(&P.slow[i]) = make_uint4(written, off, 0u, 0u);  // result form, not inline
+  P.seg_result[seg] = SEG_RESULT_SLOW | (min(written, SEG_SLOW_COUNT_MAX) << SEG_SLOW_INDEX_BITS) | i;
 }
 
 // Every lane owns a long run of slow-list entries (its warp's share / 32), so
@@ -1321,6 +1324,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams
           ent_index = i;
           seg_len = (meta >> 8) & 0xFFFFu;
           tok_off = raw.z;
+          my_text[LANE_TEXT_WORDS - 1] = raw.w;  // the segment's number (a spare word of the lane buffer)
           in_smem = (meta & SLOW_META_TEXT) != 0;
           if (in_smem) {
             const uint4 ta = __ldg(P.slow_text + 2 * static_cast<size_t>(i));
@@ -1497,6 +1501,8 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams
           res = make_uint4(nid, tok_off, 0u, 0u);
         }
         *reinterpret_cast<uint4 *>(&P.slow[ent_index]) = res;
+        P.seg_result[my_text[LANE_TEXT_WORDS - 1]] =
+            SEG_RESULT_SLOW | (min(nid, SEG_SLOW_COUNT_MAX) << SEG_SLOW_INDEX_BITS) | ent_index;
         have = false;
         if (memo_on && in_smem && seg_len <= MEMO_KEY_BYTES && nid <= 3) {
           // record bytes -> ids in the word memo so that K1 settles every later occurrence itself
@@ -1537,13 +1543,36 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams
 
 struct ScatterSmem {
   int32_t stage[SCATTER_STAGE];
-  uint32_t desc_pos[SCATTER_SEGS];     // multi-id segments of the block: stage position << 16 | id count
-  uint32_t desc_off[SCATTER_SEGS];     // ... and where their ids sit in the id scratch
+  uint32_t desc_pos[SCATTER_SEGS];     // segments not settled by K1: stage position << 16 | id count
+  uint32_t desc_src[SCATTER_SEGS];     // ... and their seg_result word (where the ids are)
   uint32_t n_desc;
   uint32_t warp_sums[SCATTER_THREADS / 32];
   uint32_t block_index;
   unsigned long long base;
 };
+
+// ids of one segment that K1 did not settle -> dst[0..cnt): from the memo slot, inline in the slow entry, or
+// from the id scratch
+__device__ __forceinline__ void scatter_fetch(const EncodeParams &P, uint32_t res, uint32_t cnt, int32_t *dst) {
+  if (res & SEG_RESULT_SLOW) {
+    const uint32_t si = res & SEG_SLOW_INDEX_MASK;
+    if (si >= P.slow_capacity) return;
+    const uint4 e = *reinterpret_cast<const uint4 *>(&P.slow[si]);
+    if (e.x & SLOW_RESULT_INLINE) {
+      dst[0] = static_cast<int32_t>(e.y);
+      if (cnt > 1) dst[1] = static_cast<int32_t>(e.z);
+      if (cnt > 2) dst[2] = static_cast<int32_t>(e.w);
+    } else if (static_cast<unsigned long long>(e.y) + cnt <= P.tok_capacity) {
+      const int32_t *src = P.tok + e.y;
+      for (uint32_t t = 0; t < cnt; t++) dst[t] = src[t];
+    }
+  } else {
+    const uint4 e = *reinterpret_cast<const uint4 *>(P.memo + 2 * static_cast<size_t>(res & SEG_MEMO_SLOT_MASK) + 1);
+    dst[0] = static_cast<int32_t>(e.y);
+    if (cnt > 1) dst[1] = static_cast<int32_t>(e.z);
+    if (cnt > 2) dst[2] = static_cast<int32_t>(e.w);
+  }
+}
 
 __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParams P) {
   __shared__ ScatterSmem sm;
@@ -1569,8 +1598,8 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
     if (b >= n_blocks) break;
     const unsigned long long first = static_cast<unsigned long long>(b) * SCATTER_SEGS + tid * SCATTER_ITEMS;
 
-    // per-segment id counts (fast: 1; slow: from the entry K2 completed)
-    uint32_t res[SCATTER_ITEMS], cnt[SCATTER_ITEMS], off[SCATTER_ITEMS];
+    // per-segment id counts, straight from the seg_result words (K1: 1; memo and slow: count bits)
+    uint32_t res[SCATTER_ITEMS], cnt[SCATTER_ITEMS];
     if (first + SCATTER_ITEMS <= n_segs) {
       const uint4 a = *reinterpret_cast<const uint4 *>(P.seg_result + first);
       const uint4 c = *reinterpret_cast<const uint4 *>(P.seg_result + first + 4);
@@ -1578,31 +1607,21 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
       res[4] = c.x; res[5] = c.y; res[6] = c.z; res[7] = c.w;
     } else {
 #pragma unroll
-      for (int j = 0; j < SCATTER_ITEMS; j++) res[j] = first + j < n_segs ? P.seg_result[first + j] : 0xFFFFFFFFu;
+      for (int j = 0; j < SCATTER_ITEMS; j++) res[j] = first + j < n_segs ? P.seg_result[first + j] : 0u;
     }
     uint32_t mine = 0;
 #pragma unroll
     for (int j = 0; j < SCATTER_ITEMS; j++) {
-      cnt[j] = 1;
-      off[j] = 0;
-      if (first + j >= n_segs) {
-        cnt[j] = 0;
-      } else if (!(res[j] & SEG_RESULT_SLOW) && (res[j] & SEG_RESULT_MEMO)) {
-        const uint4 mb = *reinterpret_cast<const uint4 *>(P.memo + 2 * static_cast<size_t>(res[j] & ~SEG_RESULT_MEMO) + 1);
-        cnt[j] = (mb.x >> 8) & 0xFFu;
-        off[j] = 0xFFFFFFFEu;  // ids are in the memo slot
-      } else if (res[j] & SEG_RESULT_SLOW) {
-        const uint32_t si = res[j] & ~SEG_RESULT_SLOW;
-        if (si < P.slow_capacity) {
-          const uint4 e = *reinterpret_cast<const uint4 *>(&P.slow[si]);
-          cnt[j] = e.x & ~SLOW_RESULT_INLINE;
-          off[j] = (e.x & SLOW_RESULT_INLINE) ? 0xFFFFFFFFu : e.y;  // all ones: ids are inline in the entry
-          if (off[j] != 0xFFFFFFFFu && static_cast<unsigned long long>(e.y) + cnt[j] > P.tok_capacity) cnt[j] = 0;
-        } else {
-          cnt[j] = 0;
-        }
+      const uint32_t slow_cnt = (res[j] >> SEG_SLOW_INDEX_BITS) & SEG_SLOW_COUNT_MAX;
+      const uint32_t memo_cnt = (res[j] >> SEG_MEMO_SLOT_BITS) & 3u;
+      uint32_t c = (res[j] & SEG_RESULT_SLOW) ? slow_cnt : ((res[j] & SEG_RESULT_MEMO) ? memo_cnt : 1u);
+      if (first + j >= n_segs) c = 0;
+      if ((res[j] & SEG_RESULT_SLOW) && slow_cnt == SEG_SLOW_COUNT_MAX && c != 0) {  // rare: 31 ids or more
+        const uint32_t si = res[j] & SEG_SLOW_INDEX_MASK;
+        c = si < P.slow_capacity ? (P.slow[si].pos_lo & ~SLOW_RESULT_INLINE) : 0u;  // word 0 of the result form
       }
-      mine += cnt[j];
+      cnt[j] = c;
+      mine += c;
     }
     uint32_t total;
     uint32_t at = block_exclusive_scan<SCATTER_THREADS / 32>(sm.warp_sums, mine, &total);
@@ -1610,25 +1629,23 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
     if (tid == 0) lookback_publish(P.block_state, b, total);
 
     if (total <= SCATTER_STAGE) {
-      // stage in shared memory, then write out coalesced.  Single ids are placed at once; multi-id
-      // segments are first listed, then copied one segment per thread (few threads would otherwise
-      // loop while their warp waits).
+      // stage in shared memory, then write out coalesced.  Ids settled by K1 are placed at once; the other
+      // segments are listed and fetched one per thread, all lanes busy (inline they would leave most
+      // lanes of a warp idle behind the few that have one).
 #pragma unroll
       for (int j = 0; j < SCATTER_ITEMS; j++) {
-        if (cnt[j] == 0) continue;
-        if (off[j] >= 0xFFFFFFFEu) {  // up to three ids inline in the slow entry / in the memo slot (cached loads)
-          const uint4 e = off[j] == 0xFFFFFFFFu
-                              ? *reinterpret_cast<const uint4 *>(&P.slow[res[j] & ~SEG_RESULT_SLOW])
-                              : *reinterpret_cast<const uint4 *>(P.memo + 2 * static_cast<size_t>(res[j] & ~SEG_RESULT_MEMO) + 1);
-          sm.stage[at] = static_cast<int32_t>(e.y);
-          if (cnt[j] > 1) sm.stage[at + 1] = static_cast<int32_t>(e.z);
-          if (cnt[j] > 2) sm.stage[at + 2] = static_cast<int32_t>(e.w);
-        } else if (res[j] & SEG_RESULT_SLOW) {
-          const uint32_t d = atomicAdd(&sm.n_desc, 1u);
-          sm.desc_pos[d] = (at << 16) | cnt[j];
-          sm.desc_off[d] = off[j];
-        } else {
-          sm.stage[at] = static_cast<int32_t>(res[j]) - 1;
+        const bool other = (res[j] & (SEG_RESULT_SLOW | SEG_RESULT_MEMO)) != 0 && cnt[j] != 0;
+        if (cnt[j] != 0 && !other) sm.stage[at] = static_cast<int32_t>(res[j]) - 1;
+        const uint32_t om = __ballot_sync(FULL, other);
+        if (om) {
+          uint32_t d = 0;
+          const int leader = __ffs(om) - 1;
+          if (lane == leader) d = atomicAdd(&sm.n_desc, static_cast<uint32_t>(__popc(om)));
+          d = __shfl_sync(FULL, d, leader) + __popc(om & ((1u << lane) - 1u));
+          if (other) {
+            sm.desc_pos[d] = (at << 16) | cnt[j];
+            sm.desc_src[d] = res[j];
+          }
         }
         at += cnt[j];
       }
@@ -1636,10 +1653,7 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
       const uint32_t n_desc = sm.n_desc;
       for (uint32_t d = tid; d < n_desc; d += SCATTER_THREADS) {
         const uint32_t dp = sm.desc_pos[d];
-        const int32_t *src = P.tok + sm.desc_off[d];
-        int32_t *dst = sm.stage + (dp >> 16);
-        const uint32_t c = dp & 0xFFFFu;
-        for (uint32_t t = 0; t < c; t++) dst[t] = src[t];
+        scatter_fetch(P, sm.desc_src[d], dp & 0xFFFFu, sm.stage + (dp >> 16));
       }
       // the ids are staged; only now the block needs its place in the output
       if (warp == 0) {
@@ -1668,20 +1682,30 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
 #pragma unroll
       for (int j = 0; j < SCATTER_ITEMS; j++) {
         if (cnt[j] == 0) continue;
-        if (off[j] >= 0xFFFFFFFEu) {
-          const uint4 e = off[j] == 0xFFFFFFFFu
-                              ? *reinterpret_cast<const uint4 *>(&P.slow[res[j] & ~SEG_RESULT_SLOW])
-                              : *reinterpret_cast<const uint4 *>(P.memo + 2 * static_cast<size_t>(res[j] & ~SEG_RESULT_MEMO) + 1);
-          const int32_t v[3] = {static_cast<int32_t>(e.y), static_cast<int32_t>(e.z), static_cast<int32_t>(e.w)};
-          for (uint32_t t = 0; t < cnt[j]; t++) {
-            if (out0 + at + t < P.capacity) P.ids[out0 + at + t] = v[t];
+        const unsigned long long o = out0 + at;
+        if (!(res[j] & (SEG_RESULT_SLOW | SEG_RESULT_MEMO))) {
+          if (o < P.capacity) P.ids[o] = static_cast<int32_t>(res[j]) - 1;
+        } else if (o + cnt[j] <= P.capacity) {
+          scatter_fetch(P, res[j], cnt[j], P.ids + o);
+        } else {
+          // the caller's buffer ends inside this segment (the call reports WP_ERR_CAPACITY): id by id
+          int32_t tmp[3];
+          if (cnt[j] <= 3) {
+            scatter_fetch(P, res[j], cnt[j], tmp);
+            for (uint32_t t = 0; t < cnt[j]; t++) {
+              if (o + t < P.capacity) P.ids[o + t] = tmp[t];
+            }
+          } else {
+            const uint32_t si = res[j] & SEG_SLOW_INDEX_MASK;
+            if (si < P.slow_capacity) {
+              const uint4 e = *reinterpret_cast<const uint4 *>(&P.slow[si]);
+              if (static_cast<unsigned long long>(e.y) + cnt[j] <= P.tok_capacity) {
+                for (uint32_t t = 0; t < cnt[j]; t++) {
+                  if (o + t < P.capacity) P.ids[o + t] = P.tok[e.y + t];
+                }
+              }
+            }
           }
-        } else if (res[j] & SEG_RESULT_SLOW) {
-          for (uint32_t t = 0; t < cnt[j]; t++) {
-            if (out0 + at + t < P.capacity) P.ids[out0 + at + t] = P.tok[off[j] + t];
-          }
-        } else if (out0 + at < P.capacity) {
-          P.ids[out0 + at] = static_cast<int32_t>(res[j]) - 1;
         }
         at += cnt[j];
       }

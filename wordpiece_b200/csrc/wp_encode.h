@@ -26,7 +26,7 @@ struct SlowEntry {
   uint32_t meta;     // bits 0..7 pos high bits, 8..23 byte length (0 for WALK), 24..25 char class,
                      // bit 26 whole-window probe known to miss, bit 27 WALK (walk from global memory, see K2)
   uint32_t tok_off;  // where this segment's ids go in the id scratch (K1 for plain entries, K2 for WALK)
-  uint32_t cnt;      // number of ids (written by K2)
+  uint32_t seg;      // the segment's number within the range: K2 puts the id count into seg_result[seg]
 };
 static_assert(sizeof(SlowEntry) == 16, "slow entries are read as one 16-byte load");
 
@@ -35,8 +35,16 @@ constexpr uint32_t SLOW_META_WALK = 1u << 27;
 constexpr uint32_t SLOW_META_TEXT = 1u << 28;    // the segment's bytes (<= 32) were copied to slow_text[] by K1
 constexpr uint32_t SLOW_TEXT_BYTES = 32;
 constexpr uint32_t SLOW_RESULT_INLINE = 0x80000000u;  // result form of an entry (after K2): word 0 = id count | this
+// seg_result, one word per segment: settled by K1 = id + 1 (< 2^30); slow = SEG_RESULT_SLOW | id count << 26
+// (31 = 31 or more: the count is in the slow entry; filled in by K2) | slow index; memo = SEG_RESULT_MEMO |
+// id count << 20 | memo slot.  K3 so knows every segment's id count without a dependent load.
 constexpr uint32_t SEG_RESULT_SLOW = 0x80000000u;
-constexpr uint32_t SEG_RESULT_MEMO = 0x40000000u;  // seg_result: this | memo slot (ids read from the memo table)
+constexpr uint32_t SEG_RESULT_MEMO = 0x40000000u;
+constexpr uint32_t SEG_SLOW_INDEX_BITS = 26;
+constexpr uint32_t SEG_SLOW_INDEX_MASK = (1u << SEG_SLOW_INDEX_BITS) - 1u;
+constexpr uint32_t SEG_SLOW_COUNT_MAX = 31;
+constexpr uint32_t SEG_MEMO_SLOT_BITS = 20;
+constexpr uint32_t SEG_MEMO_SLOT_MASK = (1u << SEG_MEMO_SLOT_BITS) - 1u;
 
 // Word memo (per encode call): exact bytes of a short segment -> its ids.  Text repeats its rare words; the
 // first occurrence of a word that needs more than one probe is matched by K2, which records the result, and
@@ -54,7 +62,7 @@ constexpr uint32_t MEMO_SALT = 0x5BD1E995u;
 // unsettled word, an atomic insert per miss and a dependent read in K3 per hit cost about that much).  A heuristic on speed only: ids never depend on it.
 __host__ __device__ inline bool memo_worthwhile(unsigned long long lookups, unsigned long long hits) {
   return !(lookups > 20000ull && hits * 3ull < lookups);
-}  // seg_result: fast = id + 1, slow = this | slow index
+}
 
 // Counters in device memory, zeroed before every range.
 struct RangeCounters {
