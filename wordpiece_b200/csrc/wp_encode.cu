@@ -57,6 +57,7 @@ constexpr int OWNED_CHUNKS = TILE / CHUNK;       // 128
 constexpr int RAW_BYTES = LEFT + WINDOW + LOOKAHEAD;  // 4400
 constexpr int WARPS = THREADS / 32;
 constexpr int MAX_TILE_SLOW = TILE / 2 + 8;      // slow segments have >= 2 bytes
+constexpr int PREFETCH_TILES = 2 * 6 * 148;      // K1 pulls the text of the tile this far ahead into L2
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 constexpr uint32_t POS_MASK = 0x3FFFu;           // window positions fit 14 bits
 constexpr uint32_t SLOW_FIRST_MISSED = 0x8000u;  // tile slow-list flag: the whole-window probe already missed
@@ -124,6 +125,7 @@ __device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return *reinterpr
 // One 32-byte table slot with ONE 256-bit load (sm_100: LDG.E.256) through the read-only path: half the
 // L1 wavefronts of two 16-byte gathers — the probes are the dominant L1 traffic of K2.
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void ld_slot(const uint4 *tab, uint32_t idx, uint4 *a, uint4 *b) {
   asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -754,6 +756,12 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   const size_t avail = n - t0;  // > 0
   const bool more_text = avail > static_cast<size_t>(WINDOW);
   const TextView tv{P.text, n};
+  {
+    // tiles run in index order, about 6 x 148 at a time: pull the tile two such waves ahead into L2 so that
+    // its own loads do not wait on DRAM
+    const size_t pf = t0 + static_cast<size_t>(PREFETCH_TILES) * TILE + static_cast<size_t>(tid) * 128u;
+    if (tid < TILE / 128 && pf < n) prefetch_l2(P.text + pf);
+  }
 
   // ---- S1a: stage raw bytes [t0-LEFT, t0+WINDOW+LOOKAHEAD) in shared memory
   {
@@ -1597,6 +1605,11 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
     const uint32_t b = sm.block_index;
     if (b >= n_blocks) break;
     const unsigned long long first = static_cast<unsigned long long>(b) * SCATTER_SEGS + tid * SCATTER_ITEMS;
+    {
+      // blocks are handed out in order to gridDim.x CTAs: pull the words of the block two rounds ahead into L2
+      const unsigned long long pf = (static_cast<unsigned long long>(b) + 2ull * gridDim.x) * SCATTER_SEGS + tid * 32ull;
+      if (tid < SCATTER_SEGS / 32 && pf < n_segs) prefetch_l2(P.seg_result + pf);
+    }
 
     // per-segment id counts, straight from the seg_result words (K1: 1; memo and slow: count bits)
     uint32_t res[SCATTER_ITEMS], cnt[SCATTER_ITEMS];
