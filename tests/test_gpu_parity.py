@@ -450,3 +450,52 @@ def test_word_memo(gpu_device, monkeypatch):
     for _ in range(3):
         assert np.array_equal(exp, v.encode(text))
     v.close()
+
+
+def test_full_size_properties(gpu_device):
+    """BASELINE configs[1] at full size (1 GiB of English-like text, 29k vocabulary), checked through
+    properties that do not need the CPU oracle at that size: the call is deterministic; the text cut after
+    a space encodes piecewise to the same ids (the reference's own chunk + concat rule, fast.cpp:113-138);
+    the host-buffer pipeline returns the device-resident ids; head and tail agree with the oracle."""
+    import torch
+
+    from wordpiece_b200 import synth
+
+    mib = 1 << 20
+    n = 1024 * mib
+    g = synth.generator("en")
+    h_text = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    g.fill(h_text.numpy(), seed=2, first_block=0, n_threads=os.cpu_count() or 8)
+    dev = torch.device("cuda", gpu_device)
+    d_text = h_text.to(dev)
+    v = _vocab(g.spec.vocab, gpu_device)
+    cap = n // 2
+    ids_a = torch.empty(cap, dtype=torch.int32, device=dev)
+    _, n_a = v.encode_device(d_text, ids_a)
+    assert 0 < n_a <= cap and v.stats().n_tiles == n // 4096 and v.stats().dirty_tiles == 0
+    # deterministic
+    ids_b = torch.empty(cap, dtype=torch.int32, device=dev)
+    _, n_b = v.encode_device(d_text, ids_b)
+    assert n_b == n_a and torch.equal(ids_a[:n_a], ids_b[:n_a])
+    # piecewise: the generator's 1 MiB blocks end with a space, so any block boundary is a legal cut
+    cuts = [0, 1, 3, 4, 131, 400, 401, 777, 1023, 1024]
+    at = 0
+    for lo, hi in zip(cuts, cuts[1:]):
+        assert h_text[hi * mib - 1].item() in (0x20, 0x0A)
+        piece = torch.empty((hi - lo) * mib // 2, dtype=torch.int32, device=dev)
+        _, k = v.encode_device(d_text[lo * mib:hi * mib], piece)
+        assert torch.equal(piece[:k], ids_a[at:at + k]), (lo, hi)
+        at += k
+    assert at == n_a
+    del ids_b, piece
+    # host-buffer entry point (three-stage pipeline over PCIe)
+    h_ids = torch.empty(cap, dtype=torch.int32, pin_memory=True)
+    k = v.encode_into(h_text.numpy(), h_ids.numpy())
+    assert k == n_a and torch.equal(h_ids[:k], ids_a[:k].cpu())
+    # head and tail against the oracle
+    o = Oracle(g.spec.vocab)
+    head = o.encode(h_text[:8 * mib].numpy().tobytes())
+    assert np.array_equal(head, ids_a[:len(head)].cpu().numpy())
+    tail = o.encode(h_text[-4 * mib:].numpy().tobytes())
+    assert np.array_equal(tail, ids_a[n_a - len(tail):n_a].cpu().numpy())
+    v.close()
