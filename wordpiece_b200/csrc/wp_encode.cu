@@ -1301,7 +1301,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams
   bool have = false;       // this lane holds an unfinished segment
   // K1 of this range is done, so the counters are final: every lane reads the same verdict, and one thread
   // records it for the K1 tiles of the next range (in a cache line of its own: the counters' line is hot)
-  const bool worth = memo_worthwhile(P.call->memo_lookups, P.call->memo_hits);
+  const bool worth = memo_worthwhile(P.call->memo_lookups, P.call->memo_hits, P.range_index <= 1);
   if (blockIdx.x == 0 && tid == 0 && !worth) P.call->memo_off = 1u;
   bool memo_on = P.memo != nullptr && (P.range_index < 2 || worth);
   bool in_smem = false;    // ... whose bytes sit in this lane's shared-memory buffer
