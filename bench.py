@@ -209,11 +209,33 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that writes to fd 1 from here on (NCCL prints its
+    version banner there from C code, libraries may log) goes to stderr; emit() writes to the saved fd."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
     args = parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -233,7 +255,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("WP_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        if "WP_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["WP_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -394,7 +417,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
