@@ -100,6 +100,12 @@ size_t wp_vocab_device_bytes(const wp_vocab *v);
 /* Host text -> host ids.  *ids_out is malloc'd by the library (wp_free). */
 wp_status wp_encode(wp_vocab *v, const char *text, size_t n_bytes, int32_t **ids_out, size_t *n_ids);
 
+/* Host text -> the ids as decimal text, every id followed by one space ("id id id "): the wire format that
+ * encodeExternal appends to its output file (fast.cpp:214-216) and utils::writeToFile writes
+ * (utils.cpp:30-35).  Formatted on the device.  *out is malloc'd by the library (wp_free), NUL-terminated,
+ * *out_len excludes the NUL. */
+wp_status wp_encode_text(wp_vocab *v, const char *text, size_t n_bytes, char **out, size_t *out_len, size_t *n_ids);
+
 /* Host text -> caller's host buffer of `capacity` ids. */
 wp_status wp_encode_into(wp_vocab *v, const char *text, size_t n_bytes, int32_t *ids, size_t capacity,
                          size_t *n_ids);

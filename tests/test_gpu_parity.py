@@ -499,3 +499,35 @@ def test_full_size_properties(gpu_device):
     tail = o.encode(h_text[-4 * mib:].numpy().tobytes())
     assert np.array_equal(tail, ids_a[n_a - len(tail):n_a].cpu().numpy())
     v.close()
+
+
+def test_id_text_formatted_on_device(gpu_device):
+    """wp_encode_text: the ids as ``"id id id "`` (fast.cpp:214-216 / utils.cpp:30-35), formatted by a kernel.
+    Covers -1 (no [UNK] in the vocabulary), ids of every decimal length up to six digits, block borders of
+    the formatter, and the empty text."""
+    rng = random.Random(3)
+    alphabet = "abcdefghijklmnopqrstuvwxyz"
+    # 150 000 distinct tokens: ids span 1..6 decimal digits; no [UNK] => unknown words are -1
+    vocab, seen = [], set()
+    while len(vocab) < 150_000:
+        w = "".join(rng.choice(alphabet) for _ in range(rng.randint(1, 5)))
+        if w not in seen:
+            seen.add(w)
+            vocab.append(w)
+    words = [rng.choice(vocab) if rng.random() < 0.9 else "".join(rng.choice("XYZ") for _ in range(4))
+             for _ in range(120_000)]
+    text = " ".join(words).encode()
+    o = Oracle(vocab)
+    v = _vocab(vocab, gpu_device)
+    for cut in (len(text), 2048 * 3, 4096, 7, 1):
+        t = text[:cut]
+        while t and t[-1:] != b" " and cut != len(text):
+            t = t[:-1]
+        exp = o.encode(t) if t else np.zeros(0, np.int32)
+        want = b"".join(b"%d " % i for i in exp.tolist())
+        got = v.encode_text(t)
+        assert got == want, (cut, got[:60], want[:60])
+    exp = o.encode(text)
+    assert (exp == -1).any() and (exp >= 100_000).any() and (exp < 10).any()
+    assert v.encode_text(b"") == b""
+    v.close()

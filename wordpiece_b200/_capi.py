@@ -70,6 +70,7 @@ EXPORTED_SYMBOLS = [
     "wp_vocab_token_flags",
     "wp_vocab_device_bytes",
     "wp_encode",
+    "wp_encode_text",
     "wp_encode_into",
     "wp_encode_device",
     "wp_encode_device_async",
@@ -133,6 +134,8 @@ def load_library() -> C.CDLL:
     L.wp_last_stats.argtypes = [vp, C.POINTER(_StatsStruct)]
     L.wp_last_stats.restype = C.c_int
     L.wp_set_kernel_timing.argtypes = [vp, C.c_int]
+    L.wp_encode_text.argtypes = [vp, vp, sz, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
+    L.wp_encode_text.restype = C.c_int
     L.wp_set_kernel_timing.restype = C.c_int
     L.wp_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
     L.wp_last_kernel_ms.restype = C.c_int
@@ -285,6 +288,17 @@ class Vocab:
         self._L.wp_free(ids)
         return out
 
+    def encode_text(self, text) -> bytes:
+        """Host text -> the ids as decimal text ``b"id id id "`` (formatted on the device).  ``wp_encode_text``."""
+        addr, n, keep = _buffer_address(text)
+        out, out_len, cnt = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        _check(self._L.wp_encode_text(self._h, addr, n, C.byref(out), C.byref(out_len), C.byref(cnt)))
+        del keep
+        try:
+            return C.string_at(out.value, out_len.value)
+        finally:
+            self._L.wp_free(out)
+
     def encode_into(self, text, out: np.ndarray) -> int:
         """Host text -> caller's int32 numpy buffer; returns the id count.  ``wp_encode_into``."""
         assert out.dtype == np.int32 and out.flags.c_contiguous
@@ -427,7 +441,7 @@ def encode_external(text_file: str, vocab_file: str, out_file: str, memory_limit
     v = _cached_vocab(_read_vocab_lines(vocab_file), device)
     max_batch = memory_limit // 2
     size = os.path.getsize(text_file)
-    with open(out_file, "w") as fout:
+    with open(out_file, "wb") as fout:
         if size == 0:
             return
         with open(text_file, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as m:
@@ -440,9 +454,7 @@ def encode_external(text_file: str, vocab_file: str, out_file: str, memory_limit
                 else:
                     batch = size
                 a = np.frombuffer(m, dtype=np.uint8, count=batch, offset=begin)
-                ids = v.encode(a)
+                fout.write(v.encode_text(a))
                 del a
-                if ids.size:
-                    fout.write(" ".join(map(str, ids.tolist())) + " ")
                 begin += batch
                 size -= batch

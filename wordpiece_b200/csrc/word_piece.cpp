@@ -237,7 +237,6 @@ void encodeExternal(const std::string &text_file,
   const char *begin = map.data();
   size_t size = map.size();
   std::ofstream fout(out_file);
-  std::string line;
   while (size > 0) {
     size_t batch;
     if (size > max_text_batch) {  // fast.cpp:202-211: extend until the last byte of the batch starts a space
@@ -247,13 +246,17 @@ void encodeExternal(const std::string &text_file,
     } else {
       batch = size;
     }
-    const std::vector<int> ids = encode_buffer(v, begin, batch);
-    line.clear();
-    for (int id : ids) {  // fast.cpp:214-216
-      line += std::to_string(id);
-      line.push_back(' ');
-    }
-    fout << line;
+    // fast.cpp:212-216: encode the batch and append "id id id " — the ids are formatted on the device
+    char *txt = nullptr;
+    size_t len = 0, n = 0;
+    const wp_status st = wp_encode_text(v, begin, batch, &txt, &len, &n);
+    if (st != WP_OK) raise(st);
+    wp_stats stats{};
+    wp_last_stats(v, &stats);
+    if (stats.dirty_tiles > 0)  // utf8.cpp:143-145
+      std::cerr << "WARNING Input contains invalid unicode characters." << std::endl;
+    fout.write(txt, static_cast<std::streamsize>(len));
+    wp_free(txt);
     begin += batch;
     size -= batch;
   }

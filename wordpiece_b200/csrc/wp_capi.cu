@@ -77,6 +77,8 @@ struct wp_vocab {
   size_t text_cap = 0;
   int32_t *d_ids = nullptr;
   size_t ids_cap = 0;
+  char *d_fmt = nullptr;  // wp_encode_text: the ids as decimal text
+  size_t fmt_cap = 0;
   wp::CallCounters *h_call = nullptr;  // pinned
   // host-buffer pipeline (wp_encode_into on large texts): three chunks in flight
   struct PipeSlot {
@@ -566,6 +568,7 @@ void wp_vocab_destroy(wp_vocab *v) {
     if (v->s_h2d) cudaStreamDestroy(v->s_h2d);
     if (v->s_d2h) cudaStreamDestroy(v->s_d2h);
     cudaFree(v->d_call);
+    cudaFree(v->d_fmt);
     cudaFree(v->d_memo);
     if (v->stream) cudaStreamDestroy(v->stream);
   }
@@ -670,17 +673,8 @@ wp_status wp_encode_into(wp_vocab *v, const char *text, size_t n_bytes, int32_t 
   return WP_OK;
 }
 
-wp_status wp_encode(wp_vocab *v, const char *text, size_t n_bytes, int32_t **ids_out, size_t *n_ids) {
-  if (!v || ids_out == nullptr || n_ids == nullptr || (n_bytes > 0 && text == nullptr))
-    return fail(WP_ERR_INVALID_ARG, "null argument");
-  *ids_out = nullptr;
-  *n_ids = 0;
-  if (v->device < 0) return fail(WP_ERR_NO_DEVICE, kHostOnly);
-  if (n_bytes == 0) {
-    v->stats = wp_stats{};
-    return WP_OK;
-  }
-  DeviceGuard g(v->device);
+// Host text -> ids in the handle's device buffer v->d_ids (count in v->stats.n_ids).
+static wp_status encode_to_device_buffer(wp_vocab *v, const char *text, size_t n_bytes) {
   if (n_bytes > v->text_cap) {
     cudaFree(v->d_text);
     v->d_text = nullptr;
@@ -708,6 +702,22 @@ wp_status wp_encode(wp_vocab *v, const char *text, size_t n_bytes, int32_t **ids
     if (v->stats.n_ids <= v->ids_cap) break;
     guess = static_cast<size_t>(v->stats.n_ids);
   }
+  return WP_OK;
+}
+
+wp_status wp_encode(wp_vocab *v, const char *text, size_t n_bytes, int32_t **ids_out, size_t *n_ids) {
+  if (!v || ids_out == nullptr || n_ids == nullptr || (n_bytes > 0 && text == nullptr))
+    return fail(WP_ERR_INVALID_ARG, "null argument");
+  *ids_out = nullptr;
+  *n_ids = 0;
+  if (v->device < 0) return fail(WP_ERR_NO_DEVICE, kHostOnly);
+  if (n_bytes == 0) {
+    v->stats = wp_stats{};
+    return WP_OK;
+  }
+  DeviceGuard g(v->device);
+  const wp_status st = encode_to_device_buffer(v, text, n_bytes);
+  if (st != WP_OK) return st;
   const size_t cnt = static_cast<size_t>(v->stats.n_ids);
   int32_t *host = static_cast<int32_t *>(std::malloc(cnt ? cnt * sizeof(int32_t) : 1));
   if (!host) return fail(WP_ERR_NOMEM, "out of memory");
@@ -720,6 +730,68 @@ wp_status wp_encode(wp_vocab *v, const char *text, size_t n_bytes, int32_t **ids
     }
   }
   *ids_out = host;
+  *n_ids = cnt;
+  return WP_OK;
+}
+
+wp_status wp_encode_text(wp_vocab *v, const char *text, size_t n_bytes, char **out, size_t *out_len, size_t *n_ids) {
+  if (!v || out == nullptr || out_len == nullptr || n_ids == nullptr || (n_bytes > 0 && text == nullptr))
+    return fail(WP_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  *out_len = 0;
+  *n_ids = 0;
+  if (v->device < 0) return fail(WP_ERR_NO_DEVICE, kHostOnly);
+  if (n_bytes == 0) {
+    v->stats = wp_stats{};
+    *out = static_cast<char *>(std::malloc(1));
+    if (!*out) return fail(WP_ERR_NOMEM, "out of memory");
+    (*out)[0] = 0;
+    return WP_OK;
+  }
+  DeviceGuard g(v->device);
+  wp_status st = encode_to_device_buffer(v, text, n_bytes);
+  if (st != WP_OK) return st;
+  const size_t cnt = static_cast<size_t>(v->stats.n_ids);
+  unsigned long long total = 0;
+  char *host = nullptr;
+  if (cnt > 0) {
+    // the encode scratch is idle now: [0] total length, [1] ticket, then one look-back word per block
+    const size_t n_blocks = (cnt + wp::format_block_ids() - 1) / wp::format_block_ids();
+    const size_t need = (2 + n_blocks) * sizeof(unsigned long long);
+    st = ensure_work(v, need);
+    if (st != WP_OK) return st;
+    unsigned long long *w = reinterpret_cast<unsigned long long *>(v->d_work);
+    WP_CUDA(cudaMemsetAsync(w, 0, need, v->stream));
+    uint64_t launches = 0;
+    WP_CUDA(wp::launch_format_total(v->d_ids, cnt, w, v->sm_count, v->stream, &launches));
+    WP_CUDA(cudaMemcpyAsync(&total, w, sizeof(total), cudaMemcpyDeviceToHost, v->stream));
+    WP_CUDA(cudaStreamSynchronize(v->stream));
+    if (total > v->fmt_cap) {
+      cudaFree(v->d_fmt);
+      v->d_fmt = nullptr;
+      v->fmt_cap = 0;
+      const size_t cap = static_cast<size_t>(total) + static_cast<size_t>(total) / 8 + 256;
+      WP_CUDA(cudaMalloc(&v->d_fmt, cap));
+      v->fmt_cap = cap;
+    }
+    WP_CUDA(wp::launch_format(v->d_ids, cnt, v->d_fmt, w + 2, reinterpret_cast<unsigned int *>(w + 1), v->sm_count,
+                              v->stream, &launches));
+    g_launches.fetch_add(launches, std::memory_order_relaxed);
+    v->stats.kernel_launches += launches;
+  }
+  host = static_cast<char *>(std::malloc(static_cast<size_t>(total) + 1));
+  if (!host) return fail(WP_ERR_NOMEM, "out of memory");
+  if (total > 0) {
+    cudaError_t e = cudaMemcpyAsync(host, v->d_fmt, static_cast<size_t>(total), cudaMemcpyDeviceToHost, v->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(v->stream);
+    if (e != cudaSuccess) {
+      std::free(host);
+      return fail(WP_ERR_CUDA, std::string("copy id text: ") + cudaGetErrorString(e));
+    }
+  }
+  host[total] = 0;
+  *out = host;
+  *out_len = static_cast<size_t>(total);
   *n_ids = cnt;
   return WP_OK;
 }

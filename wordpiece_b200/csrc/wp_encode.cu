@@ -1726,6 +1726,125 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
   }
 }
 
+// ============================================================== K4: format
+//
+// ids -> the reference's output wire format, every id in decimal followed by one space (fast.cpp:214-216,
+// utils.cpp:30-35: `"id id id "`), for the streaming entry point (encodeExternal).  Two kernels: the total
+// length, then the text (per-block scan of the lengths, decoupled look-back, chars staged in shared memory).
+
+constexpr int FORMAT_THREADS = 256;
+constexpr int FORMAT_ITEMS = 8;
+constexpr int FORMAT_IDS = FORMAT_THREADS * FORMAT_ITEMS;  // 2048 ids per block iteration
+constexpr int FORMAT_MAX_CHARS = 12;                       // "-2147483648 "
+
+__device__ __forceinline__ uint32_t decimal_chars(int32_t v) {  // digits + sign + the trailing space
+  const uint32_t a = v < 0 ? 0u - static_cast<uint32_t>(v) : static_cast<uint32_t>(v);
+  uint32_t n = 2u + (v < 0 ? 1u : 0u);
+  n += a >= 10u;
+  n += a >= 100u;
+  n += a >= 1000u;
+  n += a >= 10000u;
+  n += a >= 100000u;
+  n += a >= 1000000u;
+  n += a >= 10000000u;
+  n += a >= 100000000u;
+  n += a >= 1000000000u;
+  return n;
+}
+
+__global__ void __launch_bounds__(FORMAT_THREADS) wp_format_total_kernel(const int32_t *__restrict__ ids,
+                                                                         unsigned long long n,
+                                                                         unsigned long long *total) {
+  __shared__ unsigned long long warp_sums[FORMAT_THREADS / 32];
+  unsigned long long mine = 0;
+  for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * FORMAT_THREADS + threadIdx.x; i < n;
+       i += static_cast<unsigned long long>(gridDim.x) * FORMAT_THREADS)
+    mine += decimal_chars(ids[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(FULL, mine, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long s = 0;
+    for (int w = 0; w < FORMAT_THREADS / 32; w++) s += warp_sums[w];
+    if (s) atomicAdd(total, s);
+  }
+}
+
+struct FormatSmem {
+  uint8_t stage[FORMAT_IDS * FORMAT_MAX_CHARS];
+  uint32_t warp_sums[FORMAT_THREADS / 32];
+  uint32_t block_index;
+  unsigned long long base;
+};
+
+__global__ void __launch_bounds__(FORMAT_THREADS) wp_format_kernel(const int32_t *__restrict__ ids, unsigned long long n,
+                                                                   char *__restrict__ out, unsigned long long *block_state,
+                                                                   unsigned int *ticket) {
+  __shared__ FormatSmem sm;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const uint32_t n_blocks = static_cast<uint32_t>((n + FORMAT_IDS - 1) / FORMAT_IDS);
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sm.block_index = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t b = sm.block_index;
+    if (b >= n_blocks) break;
+    const unsigned long long first = static_cast<unsigned long long>(b) * FORMAT_IDS + tid * FORMAT_ITEMS;
+    int32_t v[FORMAT_ITEMS];
+    uint32_t len[FORMAT_ITEMS], mine = 0;
+#pragma unroll
+    for (int j = 0; j < FORMAT_ITEMS; j++) {
+      v[j] = first + j < n ? ids[first + j] : 0;
+      len[j] = first + j < n ? decimal_chars(v[j]) : 0u;
+      mine += len[j];
+    }
+    uint32_t total;
+    uint32_t at = block_exclusive_scan<FORMAT_THREADS / 32>(sm.warp_sums, mine, &total);
+    if (tid == 0) lookback_publish(block_state, b, total);
+#pragma unroll
+    for (int j = 0; j < FORMAT_ITEMS; j++) {
+      if (len[j] == 0) continue;
+      uint32_t a = v[j] < 0 ? 0u - static_cast<uint32_t>(v[j]) : static_cast<uint32_t>(v[j]);
+      uint32_t p = at + len[j] - 1;
+      sm.stage[p--] = ' ';
+      do {
+        sm.stage[p--] = static_cast<uint8_t>('0' + a % 10u);
+        a /= 10u;
+      } while (a != 0u);
+      if (v[j] < 0) sm.stage[p] = '-';
+      at += len[j];
+    }
+    __syncthreads();
+    if (tid < 32) {
+      const unsigned long long base = lookback_walk(block_state, b, total, lane);
+      if (lane == 0) sm.base = base;
+    }
+    __syncthreads();
+    char *dst = out + sm.base;
+    for (uint32_t i = tid; i < total; i += FORMAT_THREADS) dst[i] = static_cast<char>(sm.stage[i]);
+  }
+}
+
+cudaError_t launch_format_total(const int32_t *ids, size_t n, unsigned long long *total, int sm_count,
+                                cudaStream_t stream, uint64_t *launches) {
+  if (sm_count <= 0) sm_count = 148;
+  wp_format_total_kernel<<<sm_count * 8, FORMAT_THREADS, 0, stream>>>(ids, n, total);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_format(const int32_t *ids, size_t n, char *out, unsigned long long *block_state, unsigned int *ticket,
+                          int sm_count, cudaStream_t stream, uint64_t *launches) {
+  if (sm_count <= 0) sm_count = 148;
+  wp_format_kernel<<<sm_count * 4, FORMAT_THREADS, 0, stream>>>(ids, n, out, block_state, ticket);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+uint32_t format_block_ids() { return FORMAT_IDS; }
+
 // -------------------------------------------------------------------- launch
 
 uint32_t encode_tile_bytes() { return TILE; }

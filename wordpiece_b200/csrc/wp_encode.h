@@ -130,4 +130,13 @@ uint32_t scatter_block_segments();
 cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_t stream, uint64_t *launches,
                                 cudaEvent_t *timing = nullptr);
 
+// ids -> "id id id " (decimal, one space after every id).  launch_format_total adds the text length to *total
+// (zeroed by the caller); launch_format writes it to `out` (block_state: one zeroed word per
+// format_block_ids() ids, ticket: one zeroed word).
+uint32_t format_block_ids();
+cudaError_t launch_format_total(const int32_t *ids, size_t n, unsigned long long *total, int sm_count, cudaStream_t stream,
+                                uint64_t *launches);
+cudaError_t launch_format(const int32_t *ids, size_t n, char *out, unsigned long long *block_state, unsigned int *ticket,
+                          int sm_count, cudaStream_t stream, uint64_t *launches);
+
 }  // namespace wp
