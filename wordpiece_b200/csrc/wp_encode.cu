@@ -124,6 +124,21 @@ __device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return *reinterpr
 
 // One 32-byte table slot with ONE 256-bit load (sm_100: LDG.E.256) through the read-only path: half the
 // L1 wavefronts of two 16-byte gathers — the probes are the dominant L1 traffic of K2.
+// Shared-memory add by ONE lane that already speaks for its warp (ballot + popc done by the caller).  Plain
+// atomicAdd() here makes the compiler wrap its own warp aggregation (vote, flo, popc, shfl: 16 instructions)
+// around the single active lane.
+__device__ __forceinline__ uint32_t smem_add(uint32_t *p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;"
+               : "=r"(old)
+               : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))), "r"(v)
+               : "memory");
+  return old;
+}
+__device__ __forceinline__ void smem_add_noret(uint32_t *p, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -500,40 +515,38 @@ __device__ __forceinline__ WordFlags word_flags(uint32_t w) {
 // structural error take the exact per-byte lane below.
 __device__ __forceinline__ void classify_chunk(TileSmem &sm, const uint8_t *buf, int c, int limit) {
   const uint8_t *cb = buf + c * CHUNK;
-  uint32_t w[8];
-  {
-    const uint4 a = *reinterpret_cast<const uint4 *>(cb);
-    const uint4 b = *reinterpret_cast<const uint4 *>(cb + 16);
-    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-  }
   uint32_t lead = 0xFFFFFFFFu, sp = 0, pu = 0, ha = 0, cover = 0xFFFFFFFFu, spill = 0;
   uint32_t any_high = 0;
-#pragma unroll
+  // (the loops over the chunk's eight words are deliberately NOT fully unrolled: K1's executed code must fit
+  // the SM's 32 KB instruction cache — six tiles in different phases share it — and these two loops alone
+  // were a sixth of it; the words are re-read from shared memory where they are needed)
+#pragma unroll 2
   for (int i = 0; i < 8; i++) {
-    const uint32_t w7 = w[i] & 0x7F7F7F7Fu;
-    const uint32_t asc = ~w[i] & 0x80808080u;
+    const uint32_t wi = ld_u32(cb + 4 * i);
+    const uint32_t w7 = wi & 0x7F7F7F7Fu;
+    const uint32_t asc = ~wi & 0x80808080u;
     const uint32_t s = (swar_range(w7, 0x09, 0x0D) | swar_range(w7, 0x20, 0x20)) & asc;
     const uint32_t q = (swar_range(w7, 0x21, 0x2F) | swar_range(w7, 0x3A, 0x40) | swar_range(w7, 0x5B, 0x60) |
                         swar_range(w7, 0x7B, 0x7E)) & asc;
     sp |= swar_nibble(s) << (4 * i);
     pu |= swar_nibble(q) << (4 * i);
-    any_high |= w[i];
+    any_high |= wi;
   }
   if (any_high & 0x80808080u) {
     // ---- structural validation in the byte-lane domain
     WordFlags prev = word_flags(ld_u32(cb - 4));
     uint32_t bad = prev.suspect, contm = 0, cand = 0;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 8; i++) {
-      const WordFlags f = word_flags(w[i]);
+      const uint32_t wi = ld_u32(cb + 4 * i);
+      const WordFlags f = word_flags(wi);
       const uint32_t expect = lanes_back(prev.m1, f.m1, 1) | lanes_back(prev.m2, f.m2, 2) | lanes_back(prev.m3, f.m3, 3);
       bad |= (expect ^ f.cont) | f.suspect;
       contm |= swar_nibble(f.cont) << (4 * i);
       // leads that may be a spacing char: C2 (Latin-1 punctuation), E2 (U+2010.., U+2581), E3..E9, EF (Han)
-      const uint32_t low = w[i] & 0x0F0F0F0Fu;
-      const uint32_t lead3 = f.m2 & ~(w[i] << 3);
-      const uint32_t cf = swar_zero(w[i] ^ 0xC2C2C2C2u) | (lead3 & (swar_range(low, 2, 9) | swar_zero(low ^ 0x0F0F0F0Fu)));
+      const uint32_t low = wi & 0x0F0F0F0Fu;
+      const uint32_t lead3 = f.m2 & ~(wi << 3);
+      const uint32_t cf = swar_zero(wi ^ 0xC2C2C2C2u) | (lead3 & (swar_range(low, 2, 9) | swar_zero(low ^ 0x0F0F0F0Fu)));
       cand |= swar_nibble(cf) << (4 * i);
       prev = f;
     }
@@ -1018,7 +1031,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       if (slowm) {
         uint32_t at = 0;
         const int leader = __ffs(slowm) - 1;
-        if (lane == leader) at = atomicAdd(&sm.n_slow, static_cast<uint32_t>(__popc(slowm)));
+        if (lane == leader) at = smem_add(&sm.n_slow, static_cast<uint32_t>(__popc(slowm)));
         at = __shfl_sync(FULL, at, leader);
         if (slow[u]) sm.slow[at + __popc(slowm & ((1u << lane) - 1u))] = static_cast<uint16_t>(kk[u] | (slow[u] & ~1u));
       }
@@ -1131,13 +1144,13 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
           uint32_t at = 0;
           const int leader = __ffs(keepm) - 1;
           if (lane == leader) {
-            at = atomicAdd(&sm.n_slow2, static_cast<uint32_t>(__popc(keepm)));
-            if (hitm) atomicAdd(&sm.memo_hits, static_cast<uint32_t>(__popc(hitm)));
+            at = smem_add(&sm.n_slow2, static_cast<uint32_t>(__popc(keepm)));
+            if (hitm) smem_add_noret(&sm.memo_hits, static_cast<uint32_t>(__popc(hitm)));
           }
           at = __shfl_sync(FULL, at, leader);
           if (keep[u]) sm.slow[at + __popc(keepm & ((1u << lane) - 1u))] = static_cast<uint16_t>(ent[u]);
         } else if (hitm && lane == 0) {
-          atomicAdd(&sm.memo_hits, static_cast<uint32_t>(__popc(hitm)));
+          smem_add_noret(&sm.memo_hits, static_cast<uint32_t>(__popc(hitm)));
         }
       }
     }
@@ -1653,7 +1666,7 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
         if (om) {
           uint32_t d = 0;
           const int leader = __ffs(om) - 1;
-          if (lane == leader) d = atomicAdd(&sm.n_desc, static_cast<uint32_t>(__popc(om)));
+          if (lane == leader) d = smem_add(&sm.n_desc, static_cast<uint32_t>(__popc(om)));
           d = __shfl_sync(FULL, d, leader) + __popc(om & ((1u << lane) - 1u));
           if (other) {
             sm.desc_pos[d] = (at << 16) | cnt[j];
