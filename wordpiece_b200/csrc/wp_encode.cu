@@ -628,6 +628,14 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t *warp_sums, ui
   return wbase + incl - v;
 }
 
+// K1 calls the scan from three places; one out-of-line copy keeps its executed code inside the instruction
+// cache (see classify_chunk).  Returns the exclusive prefix in the low and the total in the high 32 bits.
+__device__ __noinline__ unsigned long long tile_exclusive_scan(uint32_t *warp_sums, uint32_t v) {
+  uint32_t total;
+  const uint32_t at = block_exclusive_scan<WARPS>(warp_sums, v, &total);
+  return (static_cast<unsigned long long>(total) << 32) | at;
+}
+
 // Decoupled look-back over a chain of units (tiles of K1, blocks of K3).  state[i] = flag << 62 | value;
 // flag 1 = the unit's own total, 2 = inclusive prefix.  Units are handed out in launch order by a
 // ticket, so every predecessor is already running: the spin always ends.
@@ -779,6 +787,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   // ---- S1a: stage raw bytes [t0-LEFT, t0+WINDOW+LOOKAHEAD) in shared memory
   {
     const bool aligned = (reinterpret_cast<uintptr_t>(P.text) & 15u) == 0;
+#pragma unroll 1
     for (int u = tid; u < RAW_BYTES / 16; u += THREADS) {
       const long long g = static_cast<long long>(t0) - LEFT + 16ll * u;  // text offset of this unit
       uint4 v;
@@ -860,7 +869,9 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       sm.m_kept[tid] = kept;
     }
     uint32_t packed_len;
-    const uint32_t dst0 = block_exclusive_scan<WARPS>(sm.warp_sums, my_cnt, &packed_len);  // syncs: chunks are in registers
+    const unsigned long long sc0 = tile_exclusive_scan(sm.warp_sums, my_cnt);  // syncs: chunks are in registers
+    const uint32_t dst0 = static_cast<uint32_t>(sc0);
+    packed_len = static_cast<uint32_t>(sc0 >> 32);
     if (tid <= NCHUNK) {
       sm.kept_scan[tid] = dst0;
       if (tid == NCHUNK) sm.kept_scan[NCHUNK + 1] = packed_len;
@@ -924,7 +935,9 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       starts &= left >= CHUNK ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
     }
     uint32_t totals;
-    const uint32_t at = block_exclusive_scan<WARPS>(sm.warp_sums, __popc(starts) | (__popc(ends) << 16), &totals);
+    const unsigned long long sc1 = tile_exclusive_scan(sm.warp_sums, __popc(starts) | (__popc(ends) << 16));
+    const uint32_t at = static_cast<uint32_t>(sc1);
+    totals = static_cast<uint32_t>(sc1 >> 32);
     uint32_t at_s = at & 0xFFFFu, at_e = at >> 16;
     while (starts) {
       const int j = __ffs(starts) - 1;
@@ -1041,6 +1054,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
 
   // ---- (rare) single-char segments whose home slot holds another key: follow the probe sequence
   if (sm.any_single) {  // uniform
+#pragma unroll 1
     for (uint32_t k = tid; k < n_segs; k += THREADS) {
       if (!((sm.settled[k >> 5] >> (k & 31)) & 1u) || sm.seg_e[k + skip] != PARK_PENDING) continue;
       uint32_t r[6], key[6];
@@ -1067,6 +1081,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     if (tid == 0) P.call->overflow = 1u;
     return;  // uniform
   }
+#pragma unroll 1
   for (uint32_t k = tid; k < n_segs; k += THREADS) {
     if ((sm.settled[k >> 5] >> (k & 31)) & 1u)
       P.seg_result[seg_base + k] = static_cast<uint32_t>(sm.seg_s[k]) | (static_cast<uint32_t>(sm.seg_e[k + skip]) << 16);
@@ -1173,6 +1188,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     const uint32_t lo = min(n_slow, static_cast<uint32_t>(tid) * per);
     const uint32_t hi = min(n_slow, lo + per);
     uint32_t my_len = 0, n_walk = 0;
+#pragma unroll 1
     for (uint32_t i = lo; i < hi; i++) {
       const uint32_t ent = sm.slow[i];
       const uint32_t k = ent & 0xFFFu;
@@ -1185,7 +1201,9 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       my_len += static_cast<uint32_t>(e - static_cast<int>(sm.seg_s[k] & POS_MASK));
     }
     uint32_t total_len;
-    uint32_t run = block_exclusive_scan<WARPS>(sm.warp_sums, my_len, &total_len);
+    const unsigned long long sc2 = tile_exclusive_scan(sm.warp_sums, my_len);
+    uint32_t run = static_cast<uint32_t>(sc2);
+    total_len = static_cast<uint32_t>(sc2 >> 32);
     if (tid == 0) {
       // n_slow and tok_reserved sit side by side: one 64-bit atomic reserves both (one round trip to L2)
       static_assert(offsetof(RangeCounters, tok_reserved) == offsetof(RangeCounters, n_slow) + 4 &&
@@ -1205,6 +1223,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       if (tid == 0) P.call->overflow = 1u;
       return;  // uniform
     }
+#pragma unroll 1
     for (uint32_t i = lo; i < hi; i++) {
       const uint32_t ent = sm.slow[i];
       const uint32_t k = ent & 0xFFFu;
