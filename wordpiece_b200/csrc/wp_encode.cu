@@ -1587,7 +1587,7 @@ struct ScatterSmem {
   uint32_t desc_src[SCATTER_SEGS];     // ... and their seg_result word (where the ids are)
   uint32_t n_desc;
   uint32_t warp_sums[SCATTER_THREADS / 32];
-  uint32_t block_index;
+  uint32_t block_index[2];
   unsigned long long base;
 };
 
@@ -1627,15 +1627,18 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
     if (blockIdx.x == 0 && tid == 0) P.call->ids_total[P.range_parity ^ 1u] = ids_in;
     return;
   }
-  for (;;) {
+  // The ticket of the NEXT block is taken at the start of an iteration, so that its round trip is hidden
+  // behind the work on this one (two slots, used alternately).  A CTA that holds a ticket while it still
+  // works on an earlier block cannot stall the chain: its current block only waits for smaller indices.
+  if (tid == 0) sm.block_index[0] = atomicAdd(&P.counters->scatter_ticket, 1u);
+  for (uint32_t it = 0;; it++) {
     __syncthreads();
+    const uint32_t b = sm.block_index[it & 1u];
+    if (b >= n_blocks) break;
     if (tid == 0) {
-      sm.block_index = atomicAdd(&P.counters->scatter_ticket, 1u);
+      sm.block_index[(it + 1u) & 1u] = atomicAdd(&P.counters->scatter_ticket, 1u);
       sm.n_desc = 0;
     }
-    __syncthreads();
-    const uint32_t b = sm.block_index;
-    if (b >= n_blocks) break;
     const unsigned long long first = static_cast<unsigned long long>(b) * SCATTER_SEGS + tid * SCATTER_ITEMS;
     {
       // blocks are handed out in order to gridDim.x CTAs: pull the words of the block two rounds ahead into L2
