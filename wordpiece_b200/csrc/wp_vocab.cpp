@@ -9,29 +9,22 @@
 
 #include <algorithm>
 #include <cstring>
-#include <unordered_map>
 
 namespace wp {
 namespace {
 
 struct Node {
-  std::string bytes;  // prefix bytes
-  uint32_t kind = 0;
+  uint32_t kw[6];  // the node's key: its bytes (<= WP_KEY_BYTES, zero padded), length and kind, as in the table
   int32_t term_id = WP_NO_ID;
   uint32_t best_len = 0;
   int32_t best_id = WP_NO_ID;
-  bool has_long = false;
+  int32_t long_list = -1;  // index into the side table of long-token lists (tokens longer than WP_KEY_BYTES)
+};
+
+struct LongList {
   std::vector<LongEntry> longs;               // byte_off filled at emission
   std::vector<const std::string *> long_str;  // parallel to longs
 };
-
-inline std::string node_key(uint32_t kind, const char *b, size_t k) {
-  std::string s;
-  s.reserve(k + 1);
-  s.push_back(static_cast<char>('0' + kind));
-  s.append(b, k);
-  return s;
-}
 
 inline void key_words(const uint8_t *b, uint32_t len, uint32_t kind, uint32_t kw[6]) {
   uint8_t buf[24] = {0};
@@ -49,17 +42,39 @@ bool build_host_vocab(const char *const *tokens, const size_t *lens, size_t n, H
   hv = HostVocab();
   hv.tokens.resize(n);
 
-  std::unordered_map<std::string, size_t> index;  // node key -> nodes[]
+  // node key -> nodes[]: a flat open-addressed map on the key words themselves (no strings, no allocations;
+  // the per-prefix std::string keys of the first version made a 120k vocabulary take 0.8 s to build)
+  size_t bound = 0;
+  for (size_t i = 0; i < n; i++) bound += std::min<size_t>(lens[i], WP_KEY_BYTES);
+  size_t map_size = 64;
+  while (map_size < 2 * bound + 2) map_size <<= 1;
+  std::vector<uint32_t> index(map_size, 0u);  // node index + 1, 0 = empty
+  const uint32_t map_mask = static_cast<uint32_t>(map_size - 1);
   std::vector<Node> nodes;
-  auto get_node = [&](uint32_t kind, const char *b, size_t k) -> size_t {
-    std::string key = node_key(kind, b, k);
-    auto it = index.find(key);
-    if (it != index.end()) return it->second;
+  nodes.reserve(bound);
+  std::vector<LongList> long_lists;
+  auto same_key = [](const uint32_t a[6], const uint32_t b[6]) {
+    return a[0] == b[0] && a[1] == b[1] && a[2] == b[2] && a[3] == b[3] && a[4] == b[4] && a[5] == b[5];
+  };
+  // find (create = false: SIZE_MAX if absent) / find-or-create the node with key kw
+  auto get_node_kw = [&](const uint32_t kw[6], bool create) -> size_t {
+    uint32_t h = key_hash(kw[0], kw[1], kw[2], kw[3], kw[4], kw[5]) & map_mask;
+    for (;;) {
+      const uint32_t e = index[h];
+      if (e == 0) break;
+      if (same_key(nodes[e - 1].kw, kw)) return e - 1;
+      h = (h + 1) & map_mask;
+    }
+    if (!create) return static_cast<size_t>(-1);
     nodes.emplace_back();
-    nodes.back().bytes.assign(b, k);
-    nodes.back().kind = kind;
-    index.emplace(std::move(key), nodes.size() - 1);
+    for (int q = 0; q < 6; q++) nodes.back().kw[q] = kw[q];
+    index[h] = static_cast<uint32_t>(nodes.size());
     return nodes.size() - 1;
+  };
+  auto get_node = [&](uint32_t kind, const char *b, size_t k) -> size_t {
+    uint32_t kw[6];
+    key_words(reinterpret_cast<const uint8_t *>(b), static_cast<uint32_t>(k), kind, kw);
+    return get_node_kw(kw, true);
   };
 
   for (size_t i = 0; i < n; i++) {
@@ -116,36 +131,42 @@ bool build_host_vocab(const char *const *tokens, const size_t *lens, size_t n, H
     if (L <= WP_KEY_BYTES) {
       nodes[ni].term_id = static_cast<int32_t>(i);  // fast.cpp:34: assignment => last duplicate wins
     } else {
-      Node &nd = nodes[ni];
-      nd.has_long = true;
+      if (nodes[ni].long_list < 0) {
+        nodes[ni].long_list = static_cast<int32_t>(long_lists.size());
+        long_lists.emplace_back();
+      }
+      LongList &ll = long_lists[nodes[ni].long_list];
       bool replaced = false;
-      for (size_t e = 0; e < nd.longs.size(); e++) {
-        if (*nd.long_str[e] == t.word) {
-          nd.longs[e].id = static_cast<int32_t>(i);
+      for (size_t e = 0; e < ll.longs.size(); e++) {
+        if (*ll.long_str[e] == t.word) {
+          ll.longs[e].id = static_cast<int32_t>(i);
           replaced = true;
           break;
         }
       }
       if (!replaced) {
-        nd.longs.push_back(LongEntry{static_cast<uint32_t>(L), static_cast<int32_t>(i), 0});
-        nd.long_str.push_back(&t.word);
+        ll.longs.push_back(LongEntry{static_cast<uint32_t>(L), static_cast<int32_t>(i), 0});
+        ll.long_str.push_back(&t.word);
       }
     }
   }
 
-  // best_len / best_id: longest token that is a PROPER prefix of the node.
-  // Parents first (by length), so one lookup per node.
-  std::vector<size_t> order(nodes.size());
-  for (size_t i = 0; i < order.size(); i++) order[i] = i;
-  std::sort(order.begin(), order.end(),
-            [&](size_t a, size_t b) { return nodes[a].bytes.size() < nodes[b].bytes.size(); });
-  for (size_t oi : order) {
+  // best_len / best_id: longest token that is a PROPER prefix of the node.  A node is created after all its
+  // shorter prefixes (get_node is called with k = 1, 2, ...), so index order has parents first.
+  for (size_t oi = 0; oi < nodes.size(); oi++) {
     Node &nd = nodes[oi];
-    const size_t k = nd.bytes.size();
+    const uint32_t k = slot_len(nd.kw[5]);
     if (k <= 1) continue;
-    const Node &par = nodes[index.at(node_key(nd.kind, nd.bytes.data(), k - 1))];
+    // the parent's key: the same bytes without the last one
+    uint32_t pk[6];
+    for (int q = 0; q < 6; q++) pk[q] = nd.kw[q];
+    const uint32_t last = k - 1;  // index of the byte to clear
+    if (last < 20) pk[last >> 2] &= ~(0xFFu << (8 * (last & 3)));
+    else pk[5] &= ~(0xFFu << (8 * (last - 20)));
+    pk[5] = (pk[5] & ~(0xFFu << 16)) | (last << 16);
+    const Node &par = nodes[get_node_kw(pk, false)];
     if (par.term_id != WP_NO_ID) {
-      nd.best_len = static_cast<uint32_t>(k - 1);
+      nd.best_len = k - 1;
       nd.best_id = par.term_id;
     } else {
       nd.best_len = par.best_len;
@@ -165,26 +186,27 @@ bool build_host_vocab(const char *const *tokens, const size_t *lens, size_t n, H
   hv.long_bytes.clear();
   const uint32_t mask = static_cast<uint32_t>(n_slots - 1);
   for (Node &nd : nodes) {
-    uint32_t kw[6];
-    key_words(reinterpret_cast<const uint8_t *>(nd.bytes.data()), static_cast<uint32_t>(nd.bytes.size()), nd.kind, kw);
+    const uint32_t *kw = nd.kw;
+    const bool has_long = nd.long_list >= 0;
     uint32_t idx = key_hash(kw[0], kw[1], kw[2], kw[3], kw[4], kw[5]) & mask;
     while (slot_len(hv.slots[idx].w[5]) != 0) idx = (idx + 1) & mask;
     Slot &s = hv.slots[idx];
     for (int i = 0; i < 5; i++) s.w[i] = kw[i];
-    s.w[5] = kw[5] | (nd.has_long ? (1u << 25) : 0u) | (nd.best_len << 26);
+    s.w[5] = kw[5] | (has_long ? (1u << 25) : 0u) | (nd.best_len << 26);
     s.w[6] = static_cast<uint32_t>(nd.term_id);
     s.w[7] = static_cast<uint32_t>(nd.best_id);
-    if (nd.has_long) {
+    if (has_long) {
       // longest first, so the first full match is the longest (fast.cpp:66-77 probes longest first)
-      std::vector<size_t> ord(nd.longs.size());
+      const LongList &ll = long_lists[nd.long_list];
+      std::vector<size_t> ord(ll.longs.size());
       for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
-      std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return nd.longs[a].len > nd.longs[b].len; });
+      std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return ll.longs[a].len > ll.longs[b].len; });
       hv.long_ref[idx] = static_cast<uint32_t>(hv.long_entries.size());
       hv.long_entries.push_back(static_cast<uint32_t>(ord.size()));
       for (size_t oi : ord) {
-        LongEntry e = nd.longs[oi];
+        LongEntry e = ll.longs[oi];
         e.byte_off = static_cast<uint32_t>(hv.long_bytes.size());
-        hv.long_bytes.insert(hv.long_bytes.end(), nd.long_str[oi]->begin(), nd.long_str[oi]->end());
+        hv.long_bytes.insert(hv.long_bytes.end(), ll.long_str[oi]->begin(), ll.long_str[oi]->end());
         hv.long_entries.push_back(e.len);
         hv.long_entries.push_back(static_cast<uint32_t>(e.id));
         hv.long_entries.push_back(e.byte_off);
