@@ -153,6 +153,8 @@ wp_status wp_debug_longest_match(const wp_vocab *v, const char *text, size_t win
 size_t wp_debug_table_slots(const wp_vocab *v);
 size_t wp_debug_table_nodes(const wp_vocab *v);
 size_t wp_debug_long_tokens(const wp_vocab *v);
+/* chunk plan of the host-buffer pipeline (cut offsets, first 0, last n); 0 if the text cannot be cut */
+size_t wp_debug_plan_chunks(const char *text, size_t n, size_t chunk, size_t *cuts, size_t cap);
 /* code points of single-char word-initial nodes displaced from their home slot; returns their number */
 size_t wp_debug_displaced_singles(const wp_vocab *v, uint32_t *out, size_t cap);
 

@@ -192,3 +192,34 @@ def test_shard_plan_preserves_ids():
             for off, p in zip(offs, parts):
                 out[off:off + p.size] = p
             assert np.array_equal(out, whole), (seed, n_shards)
+
+
+def test_pipeline_chunk_plan():
+    """Host-buffer pipeline (wp_encode_into on large texts): chunks end right after an ASCII space — the
+    reference's serial state is reset there (fast.cpp:89-91,113-115) — cover the text exactly, ramp up from
+    chunk/8 at the start and down again at the end, and a stretch without a space makes the plan fail (the
+    caller then encodes in one shot)."""
+    import random
+
+    from wordpiece_b200._capi import debug_plan_chunks
+
+    rng = random.Random(4)
+    words = ["".join(rng.choice("abcdefgh") for _ in range(rng.randint(1, 12))) for _ in range(400)]
+    text = " ".join(rng.choice(words) for _ in range(200_000)).encode()
+    for chunk in (4096, 30_000, 150_000):
+        cuts = debug_plan_chunks(text, chunk)
+        assert cuts[0] == 0 and cuts[-1] == len(text) and cuts == sorted(set(cuts))
+        sizes = [b - a for a, b in zip(cuts, cuts[1:])]
+        assert max(sizes) <= chunk
+        for c in cuts[1:-1]:
+            assert text[c - 1:c] == b" "
+        small = chunk // 8
+        # ramp up: about chunk/8, /4, /2, then full chunks; and the mirror image at the end
+        assert sizes[0] <= small < sizes[1] <= 2 * small < sizes[2] <= 4 * small < sizes[3]
+        assert sizes[-1] <= small + 1 and sizes[-2] <= 2 * small + 16
+        assert sum(1 for s in sizes if s > chunk // 2) >= len(sizes) - 10
+    # a text shorter than the smallest chunk is one piece
+    assert debug_plan_chunks(text[:300], 4096) == [0, 300]
+    # no space to cut at within half a chunk: no plan
+    glued = text[:50_000] + b"x" * 9000 + text[50_000:]
+    assert debug_plan_chunks(glued, 4096) == []

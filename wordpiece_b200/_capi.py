@@ -84,6 +84,7 @@ EXPORTED_SYMBOLS = [
     "wp_debug_table_nodes",
     "wp_debug_long_tokens",
     "wp_debug_displaced_singles",
+    "wp_debug_plan_chunks",
 ]
 
 _lib = None
@@ -148,6 +149,8 @@ def load_library() -> C.CDLL:
     for f in ("wp_debug_table_slots", "wp_debug_table_nodes", "wp_debug_long_tokens"):
         getattr(L, f).argtypes = [vp]
         getattr(L, f).restype = sz
+    L.wp_debug_plan_chunks.argtypes = [vp, sz, sz, C.POINTER(sz), sz]
+    L.wp_debug_plan_chunks.restype = sz
     L.wp_debug_displaced_singles.argtypes = [vp, C.POINTER(C.c_uint32), sz]
     L.wp_debug_displaced_singles.restype = sz
     _lib = L
@@ -378,6 +381,15 @@ _cache: dict = {}
 
 def _default_device() -> int:
     return int(os.environ.get("WORDPIECE_B200_DEVICE", "0"))
+
+
+def debug_plan_chunks(text: bytes, chunk: int) -> list:
+    """Cut offsets of the host-buffer pipeline for `text` with `chunk`-byte chunks (test hook, no device)."""
+    L = load_library()
+    cap = len(text) // max(chunk // 16, 1) + 64
+    buf = (C.c_size_t * cap)()
+    n = int(L.wp_debug_plan_chunks(text, len(text), chunk, buf, cap))
+    return [int(buf[i]) for i in range(min(n, cap))]
 
 
 def _cached_vocab(tokens: Sequence[Union[str, bytes]], device: Optional[int]) -> Vocab:

@@ -882,6 +882,15 @@ size_t wp_debug_table_slots(const wp_vocab *v) { return v ? v->host.slots.size()
 size_t wp_debug_table_nodes(const wp_vocab *v) { return v ? v->host.n_nodes : 0; }
 size_t wp_debug_long_tokens(const wp_vocab *v) { return v ? v->host.n_long : 0; }
 
+/* The chunk plan of the host-buffer pipeline for a text (no device needed): writes up to `cap` cut offsets
+ * (first 0, last n) to `cuts`, returns their number, or 0 if some stretch has no ASCII space to cut at. */
+size_t wp_debug_plan_chunks(const char *text, size_t n, size_t chunk, size_t *cuts, size_t cap) {
+  std::vector<size_t> c;
+  if (!text || chunk < 64 || !plan_chunks(text, n, chunk, &c)) return 0;
+  for (size_t i = 0; i < c.size() && i < cap; i++) cuts[i] = c[i];
+  return c.size();
+}
+
 /* Fills out[0..cap) with the code points of single-char word-initial nodes that do NOT sit in their home
  * slot (another key got there first); returns how many there are.  Lets a test aim at K1's rare pass. */
 size_t wp_debug_displaced_singles(const wp_vocab *v, uint32_t *out, size_t cap) {
