@@ -50,9 +50,9 @@ typedef struct wp_stats {
   uint64_t n_ids;          /* ids produced */
   uint64_t n_tiles;        /* text tiles processed */
   uint64_t dirty_tiles;    /* tiles that held invalid UTF-8 (bytes dropped, utf8.cpp:130-147) */
-  uint64_t long_segments;  /* segments longer than a tile's window (walked from global memory) */
+  uint64_t long_segments;  /* segments longer than 256 bytes / a tile's window (matched from the raw text) */
   uint64_t kernel_launches;/* kernels launched by this call */
-  uint64_t memo_hits;      /* segments settled by the per-call word memo (repeats of a word matched earlier) */
+  uint64_t memo_hits;      /* segments settled by a word recorded earlier in the call (repeats of a word K2 matched) */
 } wp_stats;
 
 /* Message for the last non-OK status returned on the calling thread. */
@@ -89,7 +89,7 @@ size_t wp_vocab_max_len(const wp_vocab *v);     /* max code points over matchabl
 int wp_vocab_device(const wp_vocab *v);
 /* bit0 is_prefix, bit1 is_special, bit2 is_malformed (utils.hpp:23-25); bit3: token held invalid UTF-8 */
 int wp_vocab_token_flags(const wp_vocab *v, size_t index);
-/* Size in bytes of the device-resident table (slots + long-token lists). */
+/* Size in bytes of the device-resident tables (edge trie + static word table). */
 size_t wp_vocab_device_bytes(const wp_vocab *v);
 
 /* ---- encode -------------------------------------------------------------
@@ -123,11 +123,44 @@ wp_status wp_encode_device(wp_vocab *v, const void *d_text, size_t n_bytes, int3
 wp_status wp_encode_device_async(wp_vocab *v, const void *d_text, size_t n_bytes, int32_t *d_ids, size_t capacity,
                                  uint64_t *d_n_ids, void *stream);
 
+/* ---- several GPUs ---------------------------------------------------------
+ * The path shards with no exchange step: the reference itself cuts the code points into ranges at is_space
+ * chars, encodes them on its pool threads and concatenates (fast.cpp:101-138).  Here the ranges are byte
+ * ranges of the UTF-8 text, one per GPU, with a replicated vocabulary (one handle per device). */
+
+/* Cuts of [0, n_bytes) into n_shards contiguous ranges of near-equal size: cuts[0] = 0, cuts[i] = the first
+ * safe cut at or after n_bytes * i / n_shards, cuts[n_shards] = n_bytes (n_shards + 1 values; returns that
+ * number).  Safe cuts: right after an is_space char (fast.cpp:113-115), and — for space-free CJK text — at a
+ * punctuation char, right after one, or at a Han char.  Pure host code. */
+size_t wp_plan_shards(const char *text, size_t n_bytes, size_t n_shards, size_t *cuts);
+
+typedef struct wp_shard {
+  size_t begin, end;    /* byte range of the text */
+  uint64_t n_ids;       /* ids of this shard */
+  uint64_t id_offset;   /* exclusive scan of n_ids: where this shard's ids start in the global array */
+  int device;           /* CUDA ordinal that encoded it */
+  float encode_ms;      /* host wall clock of this shard's copy-in + kernels */
+} wp_shard;
+
+/* Host text -> host ids over n_handles GPUs (one handle per device, same vocabulary): wp_plan_shards, one
+ * host thread per device (H2D + kernels, ids stay on the device), host exclusive scan of the counts, then
+ * every device copies its ids to ids[id_offset ...).  `shards` (optional) receives n_handles entries.
+ * The result is the id array of the whole text (fast.cpp:125-137). */
+wp_status wp_encode_sharded(wp_vocab *const *handles, size_t n_handles, const char *text, size_t n_bytes, int32_t *ids,
+                            size_t capacity, size_t *n_ids, wp_shard *shards);
+
+/* Same, but the ids are gathered in DEVICE memory of handles[gather_index]'s GPU (d_ids, capacity ids): each
+ * shard's ids travel peer to peer (NVLink) to d_ids + id_offset.  *gather_ms (optional): wall clock of the
+ * gather alone. */
+wp_status wp_encode_sharded_gather(wp_vocab *const *handles, size_t n_handles, const char *text, size_t n_bytes,
+                                   size_t gather_index, int32_t *d_ids, size_t capacity, size_t *n_ids, wp_shard *shards,
+                                   float *gather_ms);
+
 /* Counters of the last completed wp_encode / wp_encode_into / wp_encode_device call. */
 wp_status wp_last_stats(wp_vocab *v, wp_stats *out);
 
 /* Per-kernel device time (diagnostics for bench.py's roofline): when enabled, every following encode call
- * on the handle records CUDA events around its three kernels — K1 split + whole-window probe, K2 match,
+ * on the handle records CUDA events around its three kernels — K1 split + word-table lookup, K2 match,
  * K3 scan + scatter — on the stream the kernels are launched on.  wp_last_kernel_ms waits for the last
  * call and returns the summed milliseconds of each kernel over the call's ranges. */
 wp_status wp_set_kernel_timing(wp_vocab *v, int enabled);
@@ -155,8 +188,14 @@ size_t wp_debug_table_nodes(const wp_vocab *v);
 size_t wp_debug_long_tokens(const wp_vocab *v);
 /* chunk plan of the host-buffer pipeline (cut offsets, first 0, last n); 0 if the text cannot be cut */
 size_t wp_debug_plan_chunks(const char *text, size_t n, size_t chunk, size_t *cuts, size_t cap);
-/* code points of single-char word-initial nodes displaced from their home slot; returns their number */
-size_t wp_debug_displaced_singles(const wp_vocab *v, uint32_t *out, size_t cap);
+/* code points of single-char word-initial tokens whose word-table slot lies at least min_displacement slots
+ * from its home slot; returns their number */
+size_t wp_debug_displaced_singles(const wp_vocab *v, uint32_t min_displacement, uint32_t *out, size_t cap);
+/* word table: slots, static words, and the host mirror of K1's whole-segment lookup in the static image
+ * (returns the id count, 0 = absent; ids_out takes up to 11 ids) */
+size_t wp_debug_word_slots(const wp_vocab *v);
+size_t wp_debug_static_words(const wp_vocab *v);
+uint32_t wp_debug_word_lookup(const wp_vocab *v, const char *text, size_t len, int32_t *ids_out, uint32_t *displacement);
 
 #ifdef __cplusplus
 }

@@ -101,3 +101,13 @@ def model_encode(vocab_handle, text: bytes) -> List[int]:
         out.extend(seg)
         i = e
     return out
+
+
+def word_hash_py(word: bytes, slots_log2: int) -> int:
+    """wp_table.h word_hash: home slot of a word (<= 16 bytes) in a word table of 2**slots_log2 slots."""
+    b = word + b"\0" * (16 - len(word))
+    k = [int.from_bytes(b[4 * i:4 * i + 4], "little") for i in range(4)]
+    m = 0xFFFFFFFF
+    h = (k[0] * 0x9E3779B1 + k[1] * 0x85EBCA77 + k[2] * 0xC2B2AE3D + k[3] * 0x27D4EB2F + len(word) * 0x165667B1) & m
+    h ^= h >> 15
+    return ((h * 0x2C1B3C6D) & m) >> (32 - slots_log2)

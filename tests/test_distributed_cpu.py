@@ -30,7 +30,7 @@ def _worker(rank: int, world: int, port: int, result_path: str):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from _oracle import Oracle
     from wordpiece_b200 import synth
-    from wordpiece_b200.sharding import global_offsets
+    from wordpiece_b200 import global_offsets
 
     g = synth.generator("en")
     blocks = 2

@@ -352,29 +352,45 @@ def test_cpp_drop_in_runner(gpu_device, tmp_path):
     assert bad.returncode != 0
 
 
-def test_displaced_single_char_nodes(gpu_device, monkeypatch):
-    """A single-char segment whose table node is not in its home slot (another key got there first) is
-    settled by K1's rare pass, never handed to K2: the slow-list capacities assume >= 2 bytes per entry.
-    Worst case: a text of nothing but such a char (one segment per byte)."""
+def test_displaced_single_char_words(gpu_device, monkeypatch):
+    """A single-char segment is always settled by K1 (the slow-list capacities assume >= 2 bytes per entry):
+    a word-table hit, "absent => UNK" (the static part is complete), or — when its slot lies further from
+    home than K1's lookup looks — the rare probe-sequence walk.  The vocabulary is built so that some
+    single chars are displaced by 1..3 slots and one by more than that.
+    Worst case text: nothing but such a char (one segment per byte)."""
     import string
     import wordpiece_b200
+    from _model import word_hash_py
 
     rng = random.Random(0)
     words = list(dict.fromkeys("".join(rng.choice(string.ascii_lowercase) for _ in range(rng.randint(2, 6)))
                                for _ in range(3000)))
-    vocab = ["[UNK]"] + words + ["##" + w for w in words[:500]] + list(string.punctuation)
+    singles = list(string.ascii_lowercase) + list(string.punctuation)
+    n_short = len(words) + len(singles) + 8
+    log2 = 6
+    while (1 << log2) < 4 * n_short:
+        log2 += 1
+    # six words that hash to the home slot of "q" and come BEFORE it in the vocabulary: "q" ends up >= 6 away
+    home = word_hash_py(b"q", log2)
+    crowd = []
+    while len(crowd) < 6:
+        w = "".join(rng.choice(string.ascii_lowercase) for _ in range(rng.randint(7, 12)))
+        if word_hash_py(w.encode(), log2) == home and w not in words:
+            crowd.append(w)
+    vocab = ["[UNK]"] + crowd + words + ["##" + w for w in words[:500]] + singles
     v = _vocab(vocab, gpu_device)
-    displaced = [chr(c) for c in v.debug_displaced_singles() if c < 128]
-    assert len(displaced) >= 3, displaced
+    assert v.table_info["word_slots"] == 1 << log2
+    near = [chr(c) for c in v.debug_displaced_singles(1) if c < 128]
+    far = [chr(c) for c in v.debug_displaced_singles(4) if c < 128]
+    assert "q" in far and len(near) >= 2, (near, far)
     ora = Oracle(vocab)
     tile = wordpiece_b200.tile_bytes()
-    # every byte its own segment, all displaced; then mixed with at-home punctuation, words and spaces
-    texts = [(displaced[0] * (5 * tile + 17)).encode(), ("".join(displaced) * (tile // 2)).encode()]
+    texts = [("q" * (5 * tile + 17)).encode(), ("".join(near) * (tile // 2)).encode()]
     parts = []
     for _ in range(60000):
         x = rng.random()
-        parts.append(rng.choice(displaced) if x < 0.3 else rng.choice(string.punctuation) if x < 0.4
-                     else rng.choice(words) if x < 0.8 else " ")
+        parts.append(rng.choice(near) if x < 0.3 else rng.choice(string.punctuation) if x < 0.4
+                     else rng.choice(words + crowd) if x < 0.8 else " ")
     texts.append("".join(parts).encode())
     for memo in ("0", "1"):
         monkeypatch.setenv("WORDPIECE_B200_MEMO", memo)
@@ -382,12 +398,22 @@ def test_displaced_single_char_nodes(gpu_device, monkeypatch):
         for t in texts:
             assert np.array_equal(ora.encode(t), v.encode(t)), (memo, len(t))
     v.close()
-    # multi-byte chars: the displaced nodes of the 120k vocabulary (CJK, their own segments) in running text
+    # a crowded working table (no larger than the static image): recorded words and static words share
+    # probe sequences, lookups run past WORD_PROBES slots, inserts fail — not one id may change
+    monkeypatch.setenv("WORDPIECE_B200_WORD_SLOTS_LOG2", "6")
+    monkeypatch.setenv("WORDPIECE_B200_MEMO", "1")
+    monkeypatch.setenv("WORDPIECE_B200_RANGE_BYTES", str(2 * tile))
+    text, vocab2 = textgen.case(91, 60 * tile)
+    v = _vocab(vocab2, gpu_device)
+    assert np.array_equal(Oracle(vocab2).encode(text), v.encode(text))
+    v.close()
+    monkeypatch.delenv("WORDPIECE_B200_WORD_SLOTS_LOG2")
+    # multi-byte chars: the displaced single chars of the 120k vocabulary (CJK, their own segments) in running text
     from wordpiece_b200 import synth
 
     g = synth.generator("zh")
     v = _vocab(g.spec.vocab, gpu_device)
-    d = [chr(c) for c in v.debug_displaced_singles()]
+    d = [chr(c) for c in v.debug_displaced_singles(1)]
     assert d
     base = g.generate(1 << 20, seed=5).tobytes().decode("utf-8", "ignore")
     mixed = []
@@ -401,8 +427,8 @@ def test_displaced_single_char_nodes(gpu_device, monkeypatch):
 
 
 def test_word_memo(gpu_device, monkeypatch):
-    """The per-call word memo (K2 records bytes -> ids of short unsettled segments, K1 of later ranges
-    settles repeats with one lookup) must not change a single id.  Small ranges maximise the traffic
+    """The dynamic part of the word table (K2 records bytes -> ids of short unsettled segments, K1 of later
+    ranges settles repeats with its one lookup) must not change a single id.  Small ranges maximise the traffic
     through it; dirty tiles, walked segments and Han-led segments ride along."""
     import wordpiece_b200
 
@@ -419,9 +445,8 @@ def test_word_memo(gpu_device, monkeypatch):
             got = v.encode(text)
             assert np.array_equal(exp, got), (seed, range_bytes)
             hits.append(v.stats().memo_hits)
-        # one range: nothing to look up yet; many ranges: repeats hit (tiles with invalid bytes bypass the memo,
-        # and at this rate every tile of case 82 has some)
-        assert hits[2] == 0 and (hits[0] > 0 or seed == 82), hits
+        # one range: nothing recorded yet when K1 runs; many ranges: repeats hit (also in tiles with invalid bytes)
+        assert hits[2] == 0 and hits[0] > 0, hits
         # the memo is reset per call: same ids and same hit count when the call is repeated
         monkeypatch.setenv("WORDPIECE_B200_RANGE_BYTES", str(tile))
         assert np.array_equal(exp, v.encode(text)) and v.stats().memo_hits == hits[0]

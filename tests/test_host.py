@@ -174,24 +174,36 @@ def test_synthetic_corpus_is_deterministic_and_shardable():
 
 
 def test_shard_plan_preserves_ids():
-    """Cuts after a space leave the concatenated ids unchanged (fast.cpp:113-115)."""
-    from wordpiece_b200.sharding import global_offsets, plan_shards
+    """wp_plan_shards: cuts at safe starts leave the concatenated ids unchanged (fast.cpp:113-115, SURVEY
+    8(e)) — on mixed text, on text with invalid bytes, and on space-free CJK text, where the cuts fall at
+    punctuation and Han chars."""
+    from wordpiece_b200 import global_offsets, plan_shards, shard_ranges
 
-    for seed, kw in ((51, {}), (52, dict(invalid_rate=0.02)), (53, dict(long_run_rate=0.05, long_tokens=10))):
-        text, vocab = textgen.case(seed, 70000, **kw)
+    texts = [textgen.case(seed, 70000, **kw) for seed, kw in
+             ((51, {}), (52, dict(invalid_rate=0.02)), (53, dict(long_run_rate=0.05, long_tokens=10)))]
+    rng = __import__("random").Random(54)
+    _, vocab = texts[0]
+    cjk = "".join(rng.choice("中文字漢語日本人大小山川田かなあいうえお。、abc-") for _ in range(40000)).encode()
+    texts.append((cjk, vocab))
+    texts.append((cjk[:30000] + b"\xe4\xb8" + cjk[30000:33000] + b"\xff\xe5" + cjk[33000:], vocab))
+    for ti, (text, vocab) in enumerate(texts):
         o = Oracle(vocab)
         whole = o.encode(text)
-        arr = np.frombuffer(text, dtype=np.uint8)
-        for n_shards in (2, 3, 8):
-            plan = plan_shards(arr, n_shards)
-            assert plan[0][0] == 0 and plan[-1][1] == arr.size
-            assert all(plan[i][1] == plan[i + 1][0] for i in range(n_shards - 1))
-            parts = [o.encode(text[a:b]) for a, b in plan]
+        for n_shards in (2, 3, 8, 64):
+            cuts = plan_shards(text, n_shards)
+            assert cuts[0] == 0 and cuts[-1] == len(text) and cuts == sorted(cuts) and len(cuts) == n_shards + 1
+            sizes = [b - a for a, b in shard_ranges(text, n_shards)]
+            assert max(sizes) - min(sizes) < 2000, (ti, n_shards, sizes)
+            parts = [o.encode(text[a:b]) for a, b in shard_ranges(text, n_shards)]
             offs = global_offsets([p.size for p in parts])
             out = np.empty(sum(p.size for p in parts), np.int32)
             for off, p in zip(offs, parts):
                 out[off:off + p.size] = p
-            assert np.array_equal(out, whole), (seed, n_shards)
+            assert np.array_equal(out, whole), (ti, n_shards)
+    # a text without any safe cut is one shard plus empty ones; tiny texts give empty shards
+    assert plan_shards(b"x" * 1000, 4) == [0, 1000, 1000, 1000, 1000]
+    assert plan_shards(b"", 3) == [0, 0, 0, 0]
+    assert plan_shards(b"a b", 8)[-1] == 3
 
 
 def test_pipeline_chunk_plan():

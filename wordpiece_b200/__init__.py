@@ -35,6 +35,14 @@ from ._capi import (  # noqa: F401
     load_library,
     tile_bytes,
 )
+from .sharding import (  # noqa: F401
+    Shard,
+    encode_sharded,
+    encode_sharded_gather,
+    global_offsets,
+    plan_shards,
+    shard_ranges,
+)
 
 __all__ = [
     "LIB_PATH",
@@ -48,4 +56,10 @@ __all__ = [
     "kernel_launch_count",
     "load_library",
     "tile_bytes",
+    "Shard",
+    "encode_sharded",
+    "encode_sharded_gather",
+    "global_offsets",
+    "plan_shards",
+    "shard_ranges",
 ]

@@ -74,6 +74,9 @@ EXPORTED_SYMBOLS = [
     "wp_encode_into",
     "wp_encode_device",
     "wp_encode_device_async",
+    "wp_plan_shards",
+    "wp_encode_sharded",
+    "wp_encode_sharded_gather",
     "wp_last_stats",
     "wp_set_kernel_timing",
     "wp_last_kernel_ms",
@@ -84,6 +87,9 @@ EXPORTED_SYMBOLS = [
     "wp_debug_table_nodes",
     "wp_debug_long_tokens",
     "wp_debug_displaced_singles",
+    "wp_debug_word_slots",
+    "wp_debug_static_words",
+    "wp_debug_word_lookup",
     "wp_debug_plan_chunks",
 ]
 
@@ -132,6 +138,12 @@ def load_library() -> C.CDLL:
     L.wp_encode_device.restype = C.c_int
     L.wp_encode_device_async.argtypes = [vp, vp, sz, vp, sz, vp, vp]
     L.wp_encode_device_async.restype = C.c_int
+    L.wp_plan_shards.argtypes = [vp, sz, sz, C.POINTER(sz)]
+    L.wp_plan_shards.restype = sz
+    L.wp_encode_sharded.argtypes = [vp, sz, vp, sz, vp, sz, C.POINTER(sz), vp]
+    L.wp_encode_sharded.restype = C.c_int
+    L.wp_encode_sharded_gather.argtypes = [vp, sz, vp, sz, sz, vp, sz, C.POINTER(sz), vp, C.POINTER(C.c_float)]
+    L.wp_encode_sharded_gather.restype = C.c_int
     L.wp_last_stats.argtypes = [vp, C.POINTER(_StatsStruct)]
     L.wp_last_stats.restype = C.c_int
     L.wp_set_kernel_timing.argtypes = [vp, C.c_int]
@@ -146,13 +158,16 @@ def load_library() -> C.CDLL:
     L.wp_free.restype = None
     L.wp_debug_longest_match.argtypes = [vp, C.c_char_p, sz, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
     L.wp_debug_longest_match.restype = C.c_int
-    for f in ("wp_debug_table_slots", "wp_debug_table_nodes", "wp_debug_long_tokens"):
+    for f in ("wp_debug_table_slots", "wp_debug_table_nodes", "wp_debug_long_tokens", "wp_debug_word_slots",
+              "wp_debug_static_words"):
         getattr(L, f).argtypes = [vp]
         getattr(L, f).restype = sz
     L.wp_debug_plan_chunks.argtypes = [vp, sz, sz, C.POINTER(sz), sz]
     L.wp_debug_plan_chunks.restype = sz
-    L.wp_debug_displaced_singles.argtypes = [vp, C.POINTER(C.c_uint32), sz]
+    L.wp_debug_displaced_singles.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint32), sz]
     L.wp_debug_displaced_singles.restype = sz
+    L.wp_debug_word_lookup.argtypes = [vp, C.c_char_p, sz, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]
+    L.wp_debug_word_lookup.restype = C.c_uint32
     _lib = L
     return L
 
@@ -259,14 +274,24 @@ class Vocab:
             "slots": int(self._L.wp_debug_table_slots(self._h)),
             "nodes": int(self._L.wp_debug_table_nodes(self._h)),
             "long_tokens": int(self._L.wp_debug_long_tokens(self._h)),
+            "word_slots": int(self._L.wp_debug_word_slots(self._h)),
+            "static_words": int(self._L.wp_debug_static_words(self._h)),
         }
 
-    def debug_displaced_singles(self) -> list:
-        """Code points of single-char word-initial table nodes that are not in their home slot (test hook)."""
-        n = int(self._L.wp_debug_displaced_singles(self._h, None, 0))
+    def debug_displaced_singles(self, min_displacement: int = 1) -> list:
+        """Code points of single-char word-initial tokens whose word-table slot lies at least
+        ``min_displacement`` slots from its home slot (test hook)."""
+        n = int(self._L.wp_debug_displaced_singles(self._h, min_displacement, None, 0))
         buf = (C.c_uint32 * max(n, 1))()
-        self._L.wp_debug_displaced_singles(self._h, buf, n)
+        self._L.wp_debug_displaced_singles(self._h, min_displacement, buf, n)
         return [int(buf[i]) for i in range(n)]
+
+    def debug_word_lookup(self, word: bytes):
+        """Host mirror of K1's whole-segment lookup in the static word table: (ids, displacement) or None."""
+        ids = (C.c_int32 * 11)()
+        disp = C.c_uint32()
+        n = int(self._L.wp_debug_word_lookup(self._h, word, len(word), ids, C.byref(disp)))
+        return ([int(ids[i]) for i in range(n)], int(disp.value)) if n else None
 
     def debug_longest_match(self, text: bytes, kind: int):
         ln, tid = C.c_uint32(), C.c_int32()

@@ -5,12 +5,14 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/wordpiece_b200.h"
@@ -48,10 +50,10 @@ struct DeviceGuard {
 };
 
 constexpr size_t kRangeBytesMax = size_t(64) << 20;  // text bytes encoded per K1/K2/K3 round (bounds the scratch)
-constexpr uint32_t kMemoSlots = 1u << 20;            // word memo: 32 MiB of 32-byte slots
-constexpr size_t kMemoMinBytes = size_t(4) << 20;    // texts below this skip the memo (it would only cost the reset)
+constexpr uint32_t kWorkWordSlotsLog2 = 20;          // working word table of a large call: 2^20 slots of 64 bytes = 64 MiB
+constexpr size_t kMemoMinBytes = size_t(4) << 20;    // texts below this use the static word table as it is: recording
+                                                     // words into a working copy would only cost the copy
 static_assert(kRangeBytesMax / 2 + 1024 <= (size_t(1) << wp::SEG_SLOW_INDEX_BITS), "slow indices must fit seg_result");
-static_assert(kMemoSlots <= (1u << wp::SEG_MEMO_SLOT_BITS), "memo slots must fit seg_result");
 
 }  // namespace
 
@@ -59,20 +61,20 @@ struct wp_vocab {
   wp::HostVocab host;
   int device = 0;
   cudaStream_t stream = nullptr;
-  // device table
-  wp::Slot *d_slots = nullptr;
-  uint32_t *d_long_ref = nullptr;
-  uint32_t *d_long_entries = nullptr;
-  uint8_t *d_long_bytes = nullptr;
+  // device tables
+  wp::Edge *d_edges = nullptr;
+  wp::WordSlot *d_words_static = nullptr;  // image built from the vocabulary, never written by a kernel
+  wp::WordSlot *d_words_work = nullptr;    // per-call working table K2 records into (allocated on the first large call)
+  uint32_t work_words_log2 = 0;
   size_t device_bytes = 0;
   // scratch, grown on demand (layout: see Workspace below)
   uint8_t *d_work = nullptr;
   size_t work_bytes = 0;
   wp::CallCounters *d_call = nullptr;
-  uint4 *d_memo = nullptr;  // word memo (wp_encode.h), allocated on the first large call
   int sm_count = 0;
-  size_t persist_bytes = 0;  // L2 access-policy window over the slot array
-  float persist_ratio = 0.f;
+  size_t persist_words_bytes = 0, persist_edges_bytes = 0, persist_work_bytes = 0;  // L2 access-policy windows
+  float persist_words_ratio = 0.f, persist_edges_ratio = 0.f, persist_work_ratio = 0.f;
+  size_t set_aside = 0, max_window = 0;
   uint8_t *d_text = nullptr;  // staging for the host-buffer entry points
   size_t text_cap = 0;
   int32_t *d_ids = nullptr;
@@ -98,51 +100,58 @@ struct wp_vocab {
 
 namespace {
 
+uint32_t log2_of(size_t pow2) {
+  uint32_t l = 0;
+  while ((size_t(1) << l) < pow2) l++;
+  return l;
+}
+
 wp::DeviceVocab device_view(const wp_vocab *v) {
   wp::DeviceVocab d{};
-  d.slots = v->d_slots;
-  d.slot_mask = static_cast<uint32_t>(v->host.slots.size() - 1);
-  d.long_ref = v->d_long_ref;
-  d.long_entries = v->d_long_entries;
-  d.long_bytes = v->d_long_bytes;
+  d.edges = v->d_edges;
+  d.edge_mask = static_cast<uint32_t>(v->host.edges.size() - 1);
+  d.edge_shift = 32 - log2_of(v->host.edges.size());
   d.unk_id = v->host.unk_id;
   d.han_swallow = v->host.max_len >= 2 ? 1u : 0u;
-  d.probe_pairs = v->host.slots.size() * sizeof(wp::Slot) <= (size_t(16) << 20) ? 1u : 0u;
   return d;
 }
 
 wp_status upload(wp_vocab *v) {
   const wp::HostVocab &h = v->host;
-  const size_t b_slots = h.slots.size() * sizeof(wp::Slot);
-  const size_t b_ref = h.long_ref.size() * sizeof(uint32_t);
-  const size_t b_ent = h.long_entries.size() * sizeof(uint32_t);
-  const size_t b_bytes = h.long_bytes.size();
-  WP_CUDA(cudaMalloc(&v->d_slots, b_slots));
-  WP_CUDA(cudaMalloc(&v->d_long_ref, b_ref));
-  WP_CUDA(cudaMalloc(&v->d_long_entries, b_ent));
-  WP_CUDA(cudaMalloc(&v->d_long_bytes, b_bytes));
-  WP_CUDA(cudaMemcpy(v->d_slots, h.slots.data(), b_slots, cudaMemcpyHostToDevice));
-  WP_CUDA(cudaMemcpy(v->d_long_ref, h.long_ref.data(), b_ref, cudaMemcpyHostToDevice));
-  WP_CUDA(cudaMemcpy(v->d_long_entries, h.long_entries.data(), b_ent, cudaMemcpyHostToDevice));
-  WP_CUDA(cudaMemcpy(v->d_long_bytes, h.long_bytes.data(), b_bytes, cudaMemcpyHostToDevice));
-  v->device_bytes = b_slots + b_ref + b_ent + b_bytes;
+  const size_t b_edges = h.edges.size() * sizeof(wp::Edge);
+  const size_t b_words = h.words.size() * sizeof(wp::WordSlot);
+  WP_CUDA(cudaMalloc(&v->d_edges, b_edges));
+  WP_CUDA(cudaMalloc(&v->d_words_static, b_words));
+  WP_CUDA(cudaMemcpy(v->d_edges, h.edges.data(), b_edges, cudaMemcpyHostToDevice));
+  WP_CUDA(cudaMemcpy(v->d_words_static, h.words.data(), b_words, cudaMemcpyHostToDevice));
+  v->device_bytes = b_edges + b_words;
   WP_CUDA(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
   WP_CUDA(cudaMallocHost(&v->h_call, sizeof(wp::CallCounters)));
   WP_CUDA(cudaMalloc(&v->d_call, sizeof(wp::CallCounters)));
   WP_CUDA(cudaDeviceGetAttribute(&v->sm_count, cudaDevAttrMultiProcessorCount, v->device));
   {
-    // keep the probed table resident in L2 (best effort: an unsupported attribute only costs the hint)
+    // keep the table a kernel reads at random resident in L2 (best effort: an unsupported attribute only
+    // costs the hint).  The set-aside is sized for the word table; the hit ratio scales a window down to it.
     int max_persist = 0, max_window = 0;
     if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, v->device) == cudaSuccess &&
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, v->device) == cudaSuccess &&
         max_persist > 0 && max_window > 0) {
-      size_t set_aside = b_slots < static_cast<size_t>(max_persist) ? b_slots : static_cast<size_t>(max_persist);
+      size_t want = b_words > b_edges ? b_words : b_edges;
+      if (want < (size_t(1) << kWorkWordSlotsLog2) * sizeof(wp::WordSlot)) want = (size_t(1) << kWorkWordSlotsLog2) * sizeof(wp::WordSlot);
+      size_t set_aside = want < static_cast<size_t>(max_persist) ? want : static_cast<size_t>(max_persist);
       size_t current = 0;
       cudaDeviceGetLimit(&current, cudaLimitPersistingL2CacheSize);
       if (current >= set_aside || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside) == cudaSuccess) {
-        v->persist_bytes = b_slots < static_cast<size_t>(max_window) ? b_slots : static_cast<size_t>(max_window);
-        v->persist_ratio = static_cast<float>(set_aside) / static_cast<float>(v->persist_bytes);
-        if (v->persist_ratio > 1.f) v->persist_ratio = 1.f;
+        if (current > set_aside) set_aside = current;
+        auto fit = [&](size_t bytes, size_t *win, float *ratio) {
+          *win = bytes < static_cast<size_t>(max_window) ? bytes : static_cast<size_t>(max_window);
+          *ratio = static_cast<float>(set_aside) / static_cast<float>(*win);
+          if (*ratio > 1.f) *ratio = 1.f;
+        };
+        fit(b_words, &v->persist_words_bytes, &v->persist_words_ratio);
+        fit(b_edges, &v->persist_edges_bytes, &v->persist_edges_ratio);
+        v->set_aside = set_aside;
+        v->max_window = static_cast<size_t>(max_window);
       }
     }
     cudaGetLastError();
@@ -155,8 +164,8 @@ wp_status upload(wp_vocab *v) {
 // tile's window may be arbitrarily long); `spill_ids` bounds that part and the caller retries with more.
 struct Workspace {
   size_t zero_bytes;     // counters + look-back words, zeroed before every range
-  size_t off_tile_state, off_block_state, off_seg, off_slow, off_slow_text, off_tok, total;
-  uint32_t n_tiles, n_scatter_blocks, seg_cap, slow_cap, tok_cap;
+  size_t off_tile_state, off_block_state, off_seg, off_slow, off_long, off_arena, total;
+  uint32_t n_tiles, n_scatter_blocks, seg_cap, slow_cap, long_cap, arena_cap;
 };
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -168,9 +177,11 @@ Workspace plan_workspace(size_t range_bytes, size_t spill_ids) {
   const size_t padded = static_cast<size_t>(w.n_tiles) * tile;
   w.seg_cap = static_cast<uint32_t>(padded);                  // a segment has at least one byte
   w.slow_cap = static_cast<uint32_t>(padded / 2 + 1024);      // an unsettled segment has at least two
-  size_t tok = padded + 4096 + spill_ids;                     // ids <= bytes of the unsettled segments, + spill
-  if (tok > 0xFFFFFFF0ull) tok = 0xFFFFFFF0ull;
-  w.tok_cap = static_cast<uint32_t>(tok);
+  // arena words per tile: its slow segments lie inside the window (tile + 256 bytes) and each takes
+  // len + ceil(len / 4) words => at most 1.25 x window + 0.75 x (tile / 2 + 8) < 7000; + the spill of LONG segments
+  size_t arena = static_cast<size_t>(w.n_tiles) * 7000 + 4096 + spill_ids;
+  if (arena > 0xFFFFFFF0ull) arena = 0xFFFFFFF0ull;
+  w.arena_cap = static_cast<uint32_t>(arena);
   w.n_scatter_blocks = static_cast<uint32_t>((w.seg_cap + wp::scatter_block_segments() - 1) / wp::scatter_block_segments());
   size_t off = align_up(sizeof(wp::RangeCounters), 256);
   w.off_tile_state = off;
@@ -183,10 +194,11 @@ Workspace plan_workspace(size_t range_bytes, size_t spill_ids) {
   off = align_up(off + static_cast<size_t>(w.seg_cap) * 4, 256);
   w.off_slow = off;
   off = align_up(off + static_cast<size_t>(w.slow_cap) * sizeof(wp::SlowEntry), 256);
-  w.off_slow_text = off;
-  off = align_up(off + static_cast<size_t>(w.slow_cap) * 32, 256);
-  w.off_tok = off;
-  off = align_up(off + static_cast<size_t>(w.tok_cap) * 4, 256);
+  w.off_long = off;
+  w.long_cap = w.n_tiles * 18 + 16;  // per tile: segments of more than 256 bytes (<= 17) and one that leaves the window
+  off = align_up(off + static_cast<size_t>(w.long_cap) * 4, 256);
+  w.off_arena = off;
+  off = align_up(off + static_cast<size_t>(w.arena_cap) * 4, 256);
   w.total = off;
   return w;
 }
@@ -230,11 +242,30 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   v->timing_used = 0;
   bool use_memo = (call_bytes ? call_bytes : n_bytes) >= kMemoMinBytes;  // judged on the whole user call
   if (const char *e = std::getenv("WORDPIECE_B200_MEMO")) use_memo = std::atoi(e) != 0;  // 0 = off, 1 = on (tests)
+  uint64_t launches = 0;
   if (use_memo) {
-    if (!v->d_memo) WP_CUDA(cudaMalloc(&v->d_memo, static_cast<size_t>(kMemoSlots) * 32));
-    // every user call starts with an empty memo: results never depend on earlier calls (the chunks of one
-    // pipelined host-buffer call share it)
-    if (!warm) WP_CUDA(cudaMemsetAsync(v->d_memo, 0, static_cast<size_t>(kMemoSlots) * 32, stream));
+    if (!v->d_words_work) {
+      uint32_t lg = kWorkWordSlotsLog2;
+      if (const char *e = std::getenv("WORDPIECE_B200_WORD_SLOTS_LOG2")) {  // test hook: a small, crowded table
+        const int x = std::atoi(e);
+        if (x >= 6 && x <= 26) lg = static_cast<uint32_t>(x);
+      }
+      const uint32_t static_lg = log2_of(v->host.words.size());
+      if (lg < static_lg) lg = static_lg;  // the static words must fit with room to spare
+      WP_CUDA(cudaMalloc(&v->d_words_work, (size_t(1) << lg) * sizeof(wp::WordSlot)));
+      v->work_words_log2 = lg;
+      if (v->persist_words_bytes) {
+        const size_t b = (size_t(1) << lg) * sizeof(wp::WordSlot);
+        v->persist_work_bytes = b < v->max_window ? b : v->max_window;
+        v->persist_work_ratio = static_cast<float>(v->set_aside) / static_cast<float>(v->persist_work_bytes);
+        if (v->persist_work_ratio > 1.f) v->persist_work_ratio = 1.f;
+      }
+    }
+    // every user call starts from the static words only: what K2 records never outlives the call (the chunks
+    // of one pipelined host-buffer call share it), so neither ids nor timing depend on earlier calls
+    if (!warm)
+      WP_CUDA(wp::launch_seed_words(v->d_words_static, static_cast<uint32_t>(v->host.words.size()), v->d_words_work,
+                                    v->work_words_log2, stream, &launches));
   }
   wp::EncodeParams P{};
   P.vocab = device_view(v);
@@ -249,16 +280,21 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   P.seg_result = reinterpret_cast<uint32_t *>(v->d_work + w.off_seg);
   P.seg_capacity = w.seg_cap;
   P.slow = reinterpret_cast<wp::SlowEntry *>(v->d_work + w.off_slow);
-  P.slow_text = reinterpret_cast<uint4 *>(v->d_work + w.off_slow_text);
   P.slow_capacity = w.slow_cap;
-  P.tok = reinterpret_cast<int32_t *>(v->d_work + w.off_tok);
-  P.tok_capacity = w.tok_cap;
+  P.long_list = reinterpret_cast<uint32_t *>(v->d_work + w.off_long);
+  P.long_capacity = w.long_cap;
+  P.arena = reinterpret_cast<uint32_t *>(v->d_work + w.off_arena);
+  P.arena_capacity = w.arena_cap;
   P.n_scatter_blocks = w.n_scatter_blocks;
-  P.memo = use_memo ? v->d_memo : nullptr;
-  P.memo_mask = kMemoSlots - 1;
-  P.persist_bytes = v->persist_bytes;
-  P.persist_ratio = v->persist_ratio;
-  uint64_t launches = 0;
+  P.words = use_memo ? v->d_words_work : v->d_words_static;
+  const uint32_t words_log2 = use_memo ? v->work_words_log2 : log2_of(v->host.words.size());
+  P.word_mask = (1u << words_log2) - 1u;
+  P.word_shift = 32 - words_log2;
+  P.record_words = use_memo ? 1u : 0u;
+  P.persist_words_bytes = use_memo ? v->persist_work_bytes : v->persist_words_bytes;
+  P.persist_words_ratio = use_memo ? v->persist_work_ratio : v->persist_words_ratio;
+  P.persist_edges_bytes = v->persist_edges_bytes;
+  P.persist_edges_ratio = v->persist_edges_ratio;
   uint32_t range = 0;
   // Two small ranges first (2 MiB, 8 MiB): the first fills the word memo — its own unsettled words all go
   // through K2 — the second shows whether the text repeats its words (memo_worthwhile), so that the bulk of
@@ -349,10 +385,47 @@ wp_status ensure_pipeline(wp_vocab *v) {
 }
 
 inline bool is_ascii_space(unsigned char c) { return (c >= 0x09 && c <= 0x0D) || c == 0x20; }
+inline bool is_ascii_punct(unsigned char c) {
+  return (c >= 0x21 && c <= 0x2F) || (c >= 0x3A && c <= 0x40) || (c >= 0x5B && c <= 0x60) || (c >= 0x7B && c <= 0x7E);
+}
+inline bool is_cont(unsigned char c) { return (c & 0xC0) == 0x80; }
 
-// Cut [0, n) into chunks of at most kPipeChunk bytes, each ending right after an ASCII space: the
-// reference's serial state is reset at every is_space code point (fast.cpp:89-91,113-115), so the chunks
-// encode independently and their ids concatenate.  Returns false if some stretch has no space to cut at.
+// Is byte offset c a SAFE CUT of the text: do [0, c) and [c, n) encode independently, so that their ids
+// concatenate to the ids of the whole?  The reference's serial state is reset at every is_space code point
+// (fast.cpp:89-91) and its own chunking cuts there (fast.cpp:113-115); SURVEY A.2 lists the other safe
+// starts, which matter for space-free CJK text: a punctuation position, the position right after a
+// punctuation char (a punctuation window is one char, fast.cpp:55), and a Han position.  Only byte patterns
+// that are certain whatever surrounds them are accepted: ASCII bytes are always whole chars, E2 96 81 is
+// always U+2581, and a lead E4 B8..BF / E5..E9 followed by two continuation bytes is always a Han char
+// U+4E00..U+9FFF (lead bytes are always decode starts, utf8.cpp:130-147).
+bool safe_cut(const unsigned char *t, size_t n, size_t c) {
+  if (c == 0 || c >= n) return true;
+  const unsigned char prev = t[c - 1], cur = t[c];
+  if (is_ascii_space(prev) || is_ascii_punct(prev) || is_ascii_punct(cur)) return true;
+  if (c >= 3 && t[c - 3] == 0xE2 && t[c - 2] == 0x96 && prev == 0x81) return true;  // after U+2581
+  if (c + 2 < n && is_cont(t[c + 1]) && is_cont(t[c + 2])) {
+    if (cur >= 0xE5 && cur <= 0xE9) return true;
+    if (cur == 0xE4 && t[c + 1] >= 0xB8) return true;
+  }
+  return false;
+}
+
+// Cuts of [0, n) into k contiguous shards of near-equal size (BASELINE configs[3]): cut i is the first safe
+// cut at or after n * i / k.  cuts[0] = 0, cuts[k] = n; shards may be empty when the text is tiny or has no
+// safe cut for a long stretch.
+void plan_shards(const unsigned char *t, size_t n, size_t k, size_t *cuts) {
+  cuts[0] = 0;
+  for (size_t i = 1; i < k; i++) {
+    size_t c = static_cast<size_t>((static_cast<unsigned __int128>(n) * i) / k);
+    if (c < cuts[i - 1]) c = cuts[i - 1];
+    while (c < n && !safe_cut(t, n, c)) c++;
+    cuts[i] = c;
+  }
+  cuts[k] = n;
+}
+
+// Cut [0, n) into chunks of at most kPipeChunk bytes, each ending at a safe cut (see safe_cut): the chunks
+// encode independently and their ids concatenate.  Returns false if some stretch has no safe cut.
 size_t pipe_chunk_bytes() {
   if (const char *e = std::getenv("WORDPIECE_B200_PIPE_CHUNK")) {  // test hook: pipeline small texts
     const long long x = std::atoll(e);
@@ -379,7 +452,7 @@ bool plan_chunks(const char *text, size_t n, size_t chunk, std::vector<size_t> *
     size_t end = start + want;
     size_t cut = end;
     const size_t floor = start + want / 2;
-    while (cut > floor && !is_ascii_space(static_cast<unsigned char>(text[cut - 1]))) cut--;
+    while (cut > floor && !safe_cut(reinterpret_cast<const unsigned char *>(text), n, cut)) cut--;
     if (cut <= floor) return false;
     cuts->push_back(cut);
     start = cut;
@@ -548,10 +621,9 @@ void wp_vocab_destroy(wp_vocab *v) {
   if (v->device >= 0) {
     DeviceGuard g(v->device);
     if (v->stream) cudaStreamSynchronize(v->stream);
-    cudaFree(v->d_slots);
-    cudaFree(v->d_long_ref);
-    cudaFree(v->d_long_entries);
-    cudaFree(v->d_long_bytes);
+    cudaFree(v->d_edges);
+    cudaFree(v->d_words_static);
+    cudaFree(v->d_words_work);
     cudaFree(v->d_work);
     cudaFree(v->d_text);
     cudaFree(v->d_ids);
@@ -569,7 +641,6 @@ void wp_vocab_destroy(wp_vocab *v) {
     if (v->s_d2h) cudaStreamDestroy(v->s_d2h);
     cudaFree(v->d_call);
     cudaFree(v->d_fmt);
-    cudaFree(v->d_memo);
     if (v->stream) cudaStreamDestroy(v->stream);
   }
   delete v;
@@ -734,6 +805,114 @@ wp_status wp_encode(wp_vocab *v, const char *text, size_t n_bytes, int32_t **ids
   return WP_OK;
 }
 
+size_t wp_plan_shards(const char *text, size_t n_bytes, size_t n_shards, size_t *cuts) {
+  if (!cuts || n_shards == 0 || (n_bytes > 0 && !text)) return 0;
+  plan_shards(reinterpret_cast<const unsigned char *>(text), n_bytes, n_shards, cuts);
+  return n_shards + 1;
+}
+
+// Shared body of wp_encode_sharded / wp_encode_sharded_gather.  Phase 1: one host thread per handle copies
+// its shard in and encodes it, ids staying on that device.  Host: exclusive scan of the counts.  Phase 2: one
+// host thread per handle copies its ids to their global offset — into the caller's host array, or peer to
+// peer into device memory of the gathering handle.
+static wp_status encode_sharded(wp_vocab *const *handles, size_t n, const char *text, size_t n_bytes, int32_t *h_ids,
+                                int32_t *d_gather, int gather_device, size_t capacity, size_t *n_ids, wp_shard *shards,
+                                float *copy_ms) {
+  if (!handles || n == 0 || !n_ids || (n_bytes > 0 && !text)) return fail(WP_ERR_INVALID_ARG, "null argument");
+  for (size_t i = 0; i < n; i++) {
+    if (!handles[i]) return fail(WP_ERR_INVALID_ARG, "null handle");
+    if (handles[i]->device < 0) return fail(WP_ERR_NO_DEVICE, kHostOnly);
+    for (size_t j = 0; j < i; j++)
+      if (handles[j] == handles[i]) return fail(WP_ERR_INVALID_ARG, "the same handle appears twice");
+  }
+  *n_ids = 0;
+  std::vector<size_t> cuts(n + 1);
+  plan_shards(reinterpret_cast<const unsigned char *>(text), n_bytes, n, cuts.data());
+  std::vector<wp_shard> info(n);
+  std::vector<wp_status> status(n, WP_OK);
+  std::vector<std::string> errors(n);
+  auto run = [&](auto &&body) {
+    std::vector<std::thread> threads;
+    for (size_t i = 1; i < n; i++) threads.emplace_back([&, i] {
+      status[i] = body(i);
+      if (status[i] != WP_OK) errors[i] = g_error;
+    });
+    status[0] = body(0);
+    if (status[0] != WP_OK) errors[0] = g_error;
+    for (auto &t : threads) t.join();
+    for (size_t i = 0; i < n; i++)
+      if (status[i] != WP_OK) return fail(status[i], "shard " + std::to_string(i) + ": " + errors[i]);
+    return WP_OK;
+  };
+  wp_status st = run([&](size_t i) -> wp_status {
+    wp_vocab *v = handles[i];
+    info[i] = wp_shard{};
+    info[i].begin = cuts[i];
+    info[i].end = cuts[i + 1];
+    info[i].device = v->device;
+    const size_t len = cuts[i + 1] - cuts[i];
+    if (len == 0) return WP_OK;  // fast.cpp:145
+    DeviceGuard g(v->device);
+    if (!g.ok) return fail(WP_ERR_CUDA, "cudaSetDevice failed");
+    const auto t0 = std::chrono::steady_clock::now();
+    const wp_status s1 = encode_to_device_buffer(v, text + cuts[i], len);
+    if (s1 != WP_OK) return s1;
+    info[i].n_ids = v->stats.n_ids;
+    info[i].encode_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return WP_OK;
+  });
+  if (st != WP_OK) return st;
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; i++) {  // host-side exclusive scan: the only "exchange" of the sharded path
+    info[i].id_offset = total;
+    total += info[i].n_ids;
+  }
+  *n_ids = static_cast<size_t>(total);
+  if (shards) std::memcpy(shards, info.data(), n * sizeof(wp_shard));
+  if (total > capacity) return fail(WP_ERR_CAPACITY, "id buffer too small");
+  const auto t0 = std::chrono::steady_clock::now();
+  st = run([&](size_t i) -> wp_status {
+    wp_vocab *v = handles[i];
+    const size_t cnt = static_cast<size_t>(info[i].n_ids);
+    if (cnt == 0) return WP_OK;
+    DeviceGuard g(v->device);
+    if (!g.ok) return fail(WP_ERR_CUDA, "cudaSetDevice failed");
+    if (d_gather) {
+      if (v->device != gather_device) {
+        cudaDeviceEnablePeerAccess(gather_device, 0);  // best effort: without it the copy is staged through the host
+        cudaGetLastError();
+        WP_CUDA(cudaMemcpyPeerAsync(d_gather + info[i].id_offset, gather_device, v->d_ids, v->device,
+                                    cnt * sizeof(int32_t), v->stream));
+      } else {
+        WP_CUDA(cudaMemcpyAsync(d_gather + info[i].id_offset, v->d_ids, cnt * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+                                v->stream));
+      }
+    } else {
+      WP_CUDA(cudaMemcpyAsync(h_ids + info[i].id_offset, v->d_ids, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                              v->stream));
+    }
+    WP_CUDA(cudaStreamSynchronize(v->stream));
+    return WP_OK;
+  });
+  if (copy_ms) *copy_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return st;
+}
+
+wp_status wp_encode_sharded(wp_vocab *const *handles, size_t n_handles, const char *text, size_t n_bytes, int32_t *ids,
+                            size_t capacity, size_t *n_ids, wp_shard *shards) {
+  if (capacity > 0 && !ids) return fail(WP_ERR_INVALID_ARG, "null argument");
+  return encode_sharded(handles, n_handles, text, n_bytes, ids, nullptr, -1, capacity, n_ids, shards, nullptr);
+}
+
+wp_status wp_encode_sharded_gather(wp_vocab *const *handles, size_t n_handles, const char *text, size_t n_bytes,
+                                   size_t gather_index, int32_t *d_ids, size_t capacity, size_t *n_ids, wp_shard *shards,
+                                   float *gather_ms) {
+  if (!handles || gather_index >= n_handles || !handles[gather_index] || (capacity > 0 && !d_ids))
+    return fail(WP_ERR_INVALID_ARG, "bad gather target");
+  return encode_sharded(handles, n_handles, text, n_bytes, nullptr, d_ids, handles[gather_index]->device, capacity,
+                        n_ids, shards, gather_ms);
+}
+
 wp_status wp_encode_text(wp_vocab *v, const char *text, size_t n_bytes, char **out, size_t *out_len, size_t *n_ids) {
   if (!v || out == nullptr || out_len == nullptr || n_ids == nullptr || (n_bytes > 0 && text == nullptr))
     return fail(WP_ERR_INVALID_ARG, "null argument");
@@ -878,9 +1057,27 @@ wp_status wp_debug_longest_match(const wp_vocab *v, const char *text, size_t win
   return WP_OK;
 }
 
-size_t wp_debug_table_slots(const wp_vocab *v) { return v ? v->host.slots.size() : 0; }
+size_t wp_debug_table_slots(const wp_vocab *v) { return v ? v->host.edges.size() : 0; }
 size_t wp_debug_table_nodes(const wp_vocab *v) { return v ? v->host.n_nodes : 0; }
 size_t wp_debug_long_tokens(const wp_vocab *v) { return v ? v->host.n_long : 0; }
+size_t wp_debug_word_slots(const wp_vocab *v) { return v ? v->host.words.size() : 0; }
+size_t wp_debug_static_words(const wp_vocab *v) { return v ? v->host.n_static_words : 0; }
+
+/* Test hook: whole-segment lookup in the STATIC word-table image (host mirror of K1's lookup): returns the
+ * id count (0 = absent) and writes the ids (at most 11) and the slot's distance from its home slot. */
+uint32_t wp_debug_word_lookup(const wp_vocab *v, const char *text, size_t len, int32_t *ids_out, uint32_t *displacement) {
+  if (!v || !text || !ids_out) return 0;
+  uint32_t slot = 0;
+  const uint32_t cnt = wp::host_word_lookup(v->host, reinterpret_cast<const uint8_t *>(text), len, ids_out, &slot);
+  if (cnt && displacement) {
+    const wp::WordSlot &s = v->host.words[slot];
+    const uint32_t mask = static_cast<uint32_t>(v->host.words.size() - 1);
+    const uint32_t home = wp::word_hash(s.key[0], s.key[1], s.key[2], s.key[3], static_cast<uint32_t>(len),
+                                        32 - log2_of(v->host.words.size()));
+    *displacement = (slot - home) & mask;
+  }
+  return cnt;
+}
 
 /* The chunk plan of the host-buffer pipeline for a text (no device needed): writes up to `cap` cut offsets
  * (first 0, last n) to `cuts`, returns their number, or 0 if some stretch has no ASCII space to cut at. */
@@ -891,21 +1088,23 @@ size_t wp_debug_plan_chunks(const char *text, size_t n, size_t chunk, size_t *cu
   return c.size();
 }
 
-/* Fills out[0..cap) with the code points of single-char word-initial nodes that do NOT sit in their home
- * slot (another key got there first); returns how many there are.  Lets a test aim at K1's rare pass. */
-size_t wp_debug_displaced_singles(const wp_vocab *v, uint32_t *out, size_t cap) {
+/* Fills out[0..cap) with the code points of single-char word-initial tokens whose word-table slot is at least
+ * `min_displacement` slots away from its home slot; returns how many there are.  Lets a test aim at K1's
+ * second-slot lookups (1..3) and its rare probe-sequence walk (>= 4). */
+size_t wp_debug_displaced_singles(const wp_vocab *v, uint32_t min_displacement, uint32_t *out, size_t cap) {
   if (!v) return 0;
   size_t n = 0;
-  const uint32_t mask = static_cast<uint32_t>(v->host.slots.size() - 1);
-  for (size_t i = 0; i < v->host.slots.size(); i++) {
-    const wp::Slot &s = v->host.slots[i];
-    const uint32_t len = wp::slot_len(s.w[5]);
-    if (len == 0 || len > 4 || ((s.w[5] >> 24) & 1u) != wp::WP_KIND_PREFIX) continue;
-    if (wp::utf8_lead_len(s.w[0] & 0xFFu) != len) continue;  // more than one char
-    if ((wp::key_hash(s.w[0], s.w[1], s.w[2], s.w[3], s.w[4], s.w[5] & wp::WP_W5_KEYMASK) & mask) == i) continue;
+  const uint32_t mask = static_cast<uint32_t>(v->host.words.size() - 1);
+  const uint32_t shift = 32 - log2_of(v->host.words.size());
+  for (size_t i = 0; i < v->host.words.size(); i++) {
+    const wp::WordSlot &s = v->host.words[i];
+    const uint32_t len = wp::word_meta_len(s.meta);
+    if (s.meta == 0 || len > 4 || wp::utf8_lead_len(s.key[0] & 0xFFu) != len) continue;  // empty / more than one char
+    const uint32_t home = wp::word_hash(s.key[0], s.key[1], s.key[2], s.key[3], len, shift);
+    if (((static_cast<uint32_t>(i) - home) & mask) < (min_displacement ? min_displacement : 1u)) continue;
     uint32_t cp = 0;
-    if (len == 1) cp = s.w[0] & 0xFFu;
-    else wp::utf8_decode(s.w[0] & 0xFFu, (s.w[0] >> 8) & 0xFFu, (s.w[0] >> 16) & 0xFFu, s.w[0] >> 24, 4u, &cp);
+    if (len == 1) cp = s.key[0] & 0xFFu;
+    else wp::utf8_decode(s.key[0] & 0xFFu, (s.key[0] >> 8) & 0xFFu, (s.key[0] >> 16) & 0xFFu, s.key[0] >> 24, 4u, &cp);
     if (n < cap && out) out[n] = cp;
     n++;
   }

@@ -19,19 +19,19 @@
 //              UTF-8 are compacted in shared memory; segment starts and ends
 //              ("safe starts") fall out of mask operations and are
 //              compacted into lists in text order.
-//   S2a probe: one whole-window probe per segment into the hashed-trie table
-//              (wp_table.h), uniform work for every lane.  It settles every
-//              segment that is a single token (~80 % of English words) — its id
-//              goes straight to seg_result[] — and appends the rest to the
-//              global slow list.
+//   S2 lookup: one lookup per segment (<= 16 bytes) in the WORD TABLE
+//              (wp_table.h): whole segment bytes -> ids.  Its static part holds
+//              every word-initial token (a segment that is a token is that token,
+//              ~80 % of English words), its dynamic part the words K2 matched
+//              earlier in this call.  Uniform work for every lane.  The rest go
+//              to the global slow list together with their clean bytes.
 // K2 wp_match_kernel (whole GPU, no tiles, no barriers)
 //   S2b match: every lane owns many slow segments and runs the greedy matcher as
-//              a FLATTENED state machine — one table probe per loop iteration,
-//              whatever the lane is doing (binary-search step, next piece,
-//              collision) — so a warp stays converged on the probe and chains of
-//              very different length average out over a lane's share.  Segments
-//              that left their tile's window or hold invalid UTF-8 are walked
-//              from global memory by the exact byte-wise lane (walk_segment).
+//              a FLATTENED state machine over the EDGE TRIE — one trie step (a
+//              16-byte load) per loop iteration — so a warp stays converged on
+//              the step and chains of very different length average out over a
+//              lane's share.  Segments that left their tile's window or are very
+//              long are matched from the raw text in global memory.
 // K3 wp_scatter_kernel
 //   S3 scatter: per-segment id counts -> block scan -> decoupled look-back ->
 //              ids staged in shared memory and written out coalesced.
@@ -60,13 +60,7 @@ constexpr int MAX_TILE_SLOW = TILE / 2 + 8;      // slow segments have >= 2 byte
 constexpr int PREFETCH_TILES = 2 * 6 * 148;      // K1 pulls the text of the tile this far ahead into L2
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 constexpr uint32_t POS_MASK = 0x3FFFu;           // window positions fit 14 bits
-constexpr uint32_t SLOW_FIRST_MISSED = 0x8000u;  // tile slow-list flag: the whole-window probe already missed
-constexpr uint32_t SLOW_WALK = 0x4000u;          // tile slow-list flag: segment leaves the window
-
-// Rows of the key-mask table are 48 bytes apart (32 used): lanes read rows by their own k, and with this
-// stride the rows of k = 1..8 — nearly all probes — start in eight different groups of four banks, so the
-// two 16-byte loads of a probe do not serialise on bank conflicts.
-constexpr int KEY_MASK_ROW = 3;                  // in uint4 units
+constexpr uint32_t SLOW_LONG = 0x8000u;          // tile slow-list flag: matched from the raw text (leaves the window / very long)
 
 constexpr int MATCH_THREADS = 256;               // K2
 constexpr int SCATTER_THREADS = 256;             // K3
@@ -75,7 +69,8 @@ constexpr int SCATTER_SEGS = SCATTER_THREADS * SCATTER_ITEMS;  // 2048
 constexpr int SCATTER_STAGE = 6144;              // ids staged in shared memory per block iteration
 
 static_assert(RAW_BYTES % 16 == 0, "raw buffer is loaded in 16-byte units");
-static_assert(WP_KEY_BYTES + 4 <= LOOKAHEAD, "key window reads stay inside the loaded bytes");
+static_assert(WORD_KEY_BYTES + 4 <= LOOKAHEAD, "key window reads stay inside the loaded bytes");
+static_assert(LONG_SEGMENT_BYTES <= HALO, "a segment that starts in the tile and is not LONG ends inside the window");
 static_assert(NCHUNK + 1 <= THREADS, "one thread per chunk in the classification and compaction passes");
 static_assert(WINDOW <= static_cast<int>(POS_MASK), "positions must fit the packed list entries");
 static_assert(TILE <= 4096, "segment ordinals must fit 12 bits of the tile slow list");
@@ -86,10 +81,9 @@ struct __align__(16) TileSmem {
   uint16_t seg_e[WINDOW + 64];         // j-th segment end in the window
   uint16_t slow[MAX_TILE_SLOW];        // segments the whole-window probe did not settle: ordinal | flags
   uint32_t settled[TILE / 32];         // bit k: segment k was settled by S2a (its result is parked in seg_s/seg_e)
-  uint32_t n_slow2;                    // entries of slow[] left after the word memo settled its share
-  uint32_t memo_hits;
-  uint32_t memo_use;                   // this tile runs the memo phase (decided by one thread)
-  uint32_t any_single;                 // some single-char segment is still to be settled (see S2a)
+  uint32_t dyn_hits;                   // segments settled by a word K2 recorded during this call
+  uint32_t n_eligible;                 // slow segments short enough for the word table (recording statistics)
+  uint32_t any_single;                 // some single-char segment is still to be settled (see S2)
   uint32_t m_lead[NCHUNK + 1];         // valid lead bytes
   uint32_t m_space[NCHUNK + 1];
   uint32_t m_punct[NCHUNK + 1];
@@ -98,7 +92,7 @@ struct __align__(16) TileSmem {
   uint32_t m_kept[NCHUNK + 1];         // bytes of the RAW window that survive the strict decoder (dirty tiles)
   uint32_t kept_scan[NCHUNK + 2];      // exclusive scan of kept bytes per chunk (dirty tiles)
   uint8_t spill[NCHUNK + 1];           // bytes by which the chunk's last sequence runs into the next chunk
-  uint4 key_mask[KEY_MASK_ROW * (WP_KEY_BYTES + 1)];  // row k: masks of the six key words for a k-byte key, then k << 16
+  uint4 key_mask[WORD_KEY_BYTES + 1];  // row k: byte masks of the four key words for a k-byte key
   uint32_t warp_sums[WARPS];
   uint32_t prev_class;                 // class of the last valid char before the tile
   uint32_t left_spill;                 // bytes of the tile start covered by a sequence that began before it
@@ -106,7 +100,7 @@ struct __align__(16) TileSmem {
   uint32_t n_ends;                     // segment ends found in the window
   uint32_t n_slow;                     // entries of slow[]
   uint32_t slow_base;                  // first global slow index of this tile
-  uint32_t tok_base;                   // first id-scratch slot reserved for this tile
+  uint32_t arena_base;                 // first arena word reserved for this tile
   unsigned long long seg_base;         // segments of all earlier tiles of the range
 };
 
@@ -122,8 +116,6 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
 
 __device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
 
-// One 32-byte table slot with ONE 256-bit load (sm_100: LDG.E.256) through the read-only path: half the
-// L1 wavefronts of two 16-byte gathers — the probes are the dominant L1 traffic of K2.
 // Shared-memory add by ONE lane that already speaks for its warp (ballot + popc done by the caller).  Plain
 // atomicAdd() here makes the compiler wrap its own warp aggregation (vote, flo, popc, shfl: 16 instructions)
 // around the single active lane.
@@ -142,10 +134,12 @@ __device__ __forceinline__ void smem_add_noret(uint32_t *p, uint32_t v) {
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-__device__ __forceinline__ void ld_slot(const uint4 *tab, uint32_t idx, uint4 *a, uint4 *b) {
+// The first 32 bytes of a word-table slot (key, meta, ids 0..2) with ONE 256-bit load (sm_100: LDG.E.256)
+// through the read-only path.  Writers (K2) and readers (K1, K3) of a slot run in different kernels.
+__device__ __forceinline__ void ld_word_slot(const WordSlot *tab, uint32_t idx, uint4 *a, uint4 *b) {
   asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(a->x), "=r"(a->y), "=r"(a->z), "=r"(a->w), "=r"(b->x), "=r"(b->y), "=r"(b->z), "=r"(b->w)
-               : "l"(tab + 2 * static_cast<size_t>(idx)));
+               : "l"(tab + idx));
 }
 
 // 0x80 in every byte lane whose (7-bit) value lies in [lo, hi]; lanes must be < 0x80.
@@ -161,106 +155,25 @@ __device__ __forceinline__ uint32_t swar_nibble(uint32_t flags) { return (((flag
 // Class of a decoded char from its UTF-8 bytes (valid sequence of length len).
 __device__ __forceinline__ uint32_t class_of(uint32_t cp) { return cp_class(cp); }
 
-// ---------------------------------------------------------------- table probe
+// ------------------------------------------------------------------ trie step
 
-// Outcome of looking at two consecutive slots (idx, idx+1) for one key: with linear probing at load <= 0.25
-// the key, or the empty slot that proves its absence, is in this pair for all but ~1 % of the probes, so a
-// probe is one turn (two 256-bit loads issued together) instead of a chain of dependent single-slot turns.
-enum PairOutcome : uint32_t { PAIR_MISS = 0, PAIR_HIT0 = 1, PAIR_HIT1 = 2, PAIR_BOTH_OTHER = 3 };
-
-__device__ __forceinline__ bool slot_matches(const uint4 &a, const uint4 &b, const uint32_t kw[6]) {
-  return a.x == kw[0] && a.y == kw[1] && a.z == kw[2] && a.w == kw[3] && b.x == kw[4] &&
-         ((b.y ^ kw[5]) & WP_W5_KEYMASK) == 0;
-}
-
-__device__ __forceinline__ uint32_t pair_outcome(const uint4 &a0, const uint4 &b0, const uint4 &a1, const uint4 &b1,
-                                                 const uint32_t kw[6]) {
-  if (slot_len(b0.y) == 0) return PAIR_MISS;
-  if (slot_matches(a0, b0, kw)) return PAIR_HIT0;
-  if (slot_len(b1.y) == 0) return PAIR_MISS;
-  if (slot_matches(a1, b1, kw)) return PAIR_HIT1;
-  return PAIR_BOTH_OTHER;
-}
-
-struct NodeHit {
-  uint32_t w5;
-  int32_t term_id;
-  int32_t best_id;
-  uint32_t slot;
-};
-
-__device__ __forceinline__ bool probe_node(const DeviceVocab &V, const uint32_t kw[6], NodeHit *hit) {
-  uint32_t idx = key_hash(kw[0], kw[1], kw[2], kw[3], kw[4], kw[5]) & V.slot_mask;
-  const uint4 *tab = reinterpret_cast<const uint4 *>(V.slots);
-  for (;;) {
-    const uint4 a = __ldg(tab + 2 * idx);
-    const uint4 b = __ldg(tab + 2 * idx + 1);
-    if (slot_len(b.y) == 0) return false;
-    if (a.x == kw[0] && a.y == kw[1] && a.z == kw[2] && a.w == kw[3] && b.x == kw[4] &&
-        ((b.y ^ kw[5]) & WP_W5_KEYMASK) == 0) {
-      hit->w5 = b.y;
-      hit->term_id = static_cast<int32_t>(b.z);
-      hit->best_id = static_cast<int32_t>(b.w);
-      hit->slot = idx;
-      return true;
-    }
-    idx = (idx + 1) & V.slot_mask;
+// One descent step: the edge (node, byte), or false.  e = {key, child, term_id, flags}.
+__device__ __forceinline__ bool trie_step(const DeviceVocab &V, uint32_t node, uint32_t byte, uint4 *e) {
+  const uint32_t key = edge_key(node, byte);
+  const uint4 *tab = reinterpret_cast<const uint4 *>(V.edges);
+  uint32_t idx = edge_hash(key, V.edge_shift);
+  uint4 v = __ldg(tab + idx);
+  while (v.x != key && v.x != EDGE_EMPTY) {  // linear probing, load factor <= 0.5
+    idx = (idx + 1) & V.edge_mask;
+    v = __ldg(tab + idx);
   }
+  *e = v;
+  return v.x == key;
 }
 
-// Key words for the first k (1..22) bytes of the 24 raw window bytes r[0..5].
-__device__ __forceinline__ void make_key(const uint32_t r[6], uint32_t k, uint32_t kind, uint32_t kw[6]) {
-#pragma unroll
-  for (int i = 0; i < 5; i++) {
-    const int nb = static_cast<int>(k) - 4 * i;
-    kw[i] = nb >= 4 ? r[i] : (nb <= 0 ? 0u : (r[i] & ((1u << (8 * nb)) - 1u)));
-  }
-  const int nb5 = static_cast<int>(k) - 20;
-  const uint32_t tail = nb5 <= 0 ? 0u : (r[5] & ((1u << (8 * nb5)) - 1u));
-  kw[5] = make_w5(tail, k, kind);
-}
-
-// Same, with the byte masks read from a row of a shared-memory table
-// (two 16-byte loads and six ANDs instead of a compare/select chain per word).
-__device__ __forceinline__ void make_key_tab(const uint4 *key_mask, const uint32_t r[6], uint32_t k, uint32_t kind,
-                                             uint32_t kw[6]) {
-  const uint4 ma = key_mask[KEY_MASK_ROW * k];
-  const uint4 mb = key_mask[KEY_MASK_ROW * k + 1];
-  kw[0] = r[0] & ma.x;
-  kw[1] = r[1] & ma.y;
-  kw[2] = r[2] & ma.z;
-  kw[3] = r[3] & ma.w;
-  kw[4] = r[4] & mb.x;
-  kw[5] = (r[5] & mb.y) | mb.z | (kind << 24);
-}
-
-// Deepest trie node along the window whose first min(window,22) bytes are r[];
-// returns its depth (0 = none).  Node existence is monotone in the depth, so
-// after the whole-window probe a binary search suffices.
-__device__ __forceinline__ uint32_t deepest_node(const DeviceVocab &V, const uint32_t r[6], uint32_t k0, uint32_t kind,
-                                                 NodeHit *node) {
-  uint32_t kw[6];
-  make_key(r, k0, kind, kw);
-  if (probe_node(V, kw, node)) return k0;
-  uint32_t lo = 0, hi = k0;
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    NodeHit h;
-    make_key(r, mid, kind, kw);
-    if (probe_node(V, kw, &h)) {
-      lo = mid;
-      *node = h;
-    } else {
-      hi = mid;
-    }
-  }
-  return lo;
-}
-
-// --------------------------------------------- global-memory walker (slow lane)
-// Walks ONE segment straight from the text in global memory, dropping invalid
-// bytes on the fly.  Used for the (at most one per tile) segment that does not
-// end inside the tile's window.  Single thread; two passes: count, then emit.
+// ------------------------------------------- raw-text lane (long segments, K2L)
+// Decoding and matching straight from the text in global memory, dropping invalid
+// bytes on the fly: for segments that leave their tile's window or are very long.
 
 struct TextView {
   const uint8_t *t;
@@ -315,158 +228,32 @@ __device__ uint32_t gprev_class(const TextView &tv, size_t pos) {
 }
 
 // Longest match for the window that starts at the valid lead `p` (first char of
-// any non-space class, then ordinary chars only).
-__device__ uint32_t longest_match_global(const DeviceVocab &V, const TextView &tv, size_t p, uint32_t kind,
-                                         int32_t *id) {
-  uint8_t kb[24];
-#pragma unroll
-  for (int i = 0; i < 24; i++) kb[i] = 0;
-  uint32_t klen = 0;
-  bool more = false;
-  {
-    size_t q = p;
-    bool first = true;
-    while (q < tv.n) {
-      uint32_t len, cls;
-      q = gnext(tv, q, &len, &cls);
-      if (q >= tv.n) break;
-      if (!first && cls != CLS_OTHER) break;
-      for (uint32_t i = 0; i < len; i++) {
-        if (klen < WP_KEY_BYTES) {
-          kb[klen++] = tv.t[q + i];
-        } else {
-          more = true;
-        }
-      }
-      if (more) break;
-      if (first && cls == CLS_PUNCT) break;
-      first = false;
-      q += len;
+// any non-space class, then ordinary chars only).  Returns the raw text position
+// right behind the match (p itself: no match) and the token id.
+__device__ size_t longest_match_global(const DeviceVocab &V, const TextView &tv, size_t p, uint32_t kind, int32_t *id) {
+  uint32_t node = kind;
+  size_t q = p, best = p;
+  bool first = true;
+  while (q < tv.n) {
+    uint32_t len, cls;
+    q = gnext(tv, q, &len, &cls);
+    if (q >= tv.n || (!first && cls != CLS_OTHER)) break;
+    uint4 e = make_uint4(0, 0, 0, 0);
+    bool ok = true;
+    for (uint32_t i = 0; i < len && ok; i++) {
+      ok = trie_step(V, node, tv.t[q + i], &e);
+      node = e.y;
     }
-    if (!more && klen == WP_KEY_BYTES && q < tv.n) {
-      // exactly 22 bytes gathered: does the window go on?
-      uint32_t len, cls;
-      const size_t q2 = gnext(tv, q, &len, &cls);
-      more = q2 < tv.n && cls == CLS_OTHER;
+    if (!ok) break;
+    q += len;
+    if (static_cast<int32_t>(e.z) != WP_NO_ID) {  // tokens are whole chars: terminals sit at char ends
+      best = q;
+      *id = static_cast<int32_t>(e.z);
     }
+    if (!(e.w & EDGE_HAS_CHILDREN) || (first && cls == CLS_PUNCT)) break;
+    first = false;
   }
-  uint32_t r[6];
-#pragma unroll
-  for (int i = 0; i < 6; i++)
-    r[i] = uint32_t(kb[4 * i]) | (uint32_t(kb[4 * i + 1]) << 8) | (uint32_t(kb[4 * i + 2]) << 16) |
-           (uint32_t(kb[4 * i + 3]) << 24);
-  NodeHit node;
-  const uint32_t d = deepest_node(V, r, klen, kind, &node);
-  if (d == 0) return 0;
-  if (d == WP_KEY_BYTES && slot_has_long(node.w5) && more) {
-    const uint32_t ref = V.long_ref[node.slot];
-    const uint32_t cnt = V.long_entries[ref];
-    for (uint32_t e = 0; e < cnt; e++) {
-      const uint32_t len = V.long_entries[ref + 1 + 3 * e];
-      const uint8_t *tok = V.long_bytes + V.long_entries[ref + 3 + 3 * e];
-      // compare clean bytes [0,len) of the window with the token
-      uint32_t o = 0;
-      size_t q = p;
-      bool ok = true, first = true;
-      while (o < len) {
-        uint32_t clen, cls;
-        q = gnext(tv, q, &clen, &cls);
-        if (q >= tv.n || (!first && cls != CLS_OTHER)) {
-          ok = false;
-          break;
-        }
-        for (uint32_t i = 0; i < clen && ok; i++) {
-          if (o >= len || tv.t[q + i] != tok[o]) ok = false;
-          o++;
-        }
-        if (!ok) break;
-        first = false;
-        q += clen;
-      }
-      if (ok && o == len) {
-        *id = static_cast<int32_t>(V.long_entries[ref + 2 + 3 * e]);
-        return len;
-      }
-    }
-  }
-  if (node.term_id != WP_NO_ID) {
-    *id = node.term_id;
-    return d;
-  }
-  const uint32_t bl = slot_best_len(node.w5);
-  if (bl != 0) {
-    *id = node.best_id;
-    return bl;
-  }
-  return 0;
-}
-
-// Walk the segment that starts at the valid, non-space lead gs.  out == nullptr:
-// count only.  Otherwise ids go to out[0..) (bounded by cap_left); ids at
-// indices >= unk_at are not written (they are rolled back, fast.cpp:80-84) and
-// the UNK id is written at unk_at.  Returns the id count; *unk_at_out = index
-// of the final UNK or -1.
-__device__ uint32_t walk_segment(const DeviceVocab &V, const TextView &tv, size_t gs, int32_t *out,
-                                 unsigned long long cap_left, int32_t unk_at, int32_t *unk_at_out) {
-  uint32_t len0, cls0;
-  gnext(tv, gs, &len0, &cls0);
-  int32_t id = 0;
-  auto emit = [&](uint32_t index, int32_t v, bool is_unk) {
-    if (out == nullptr) return;
-    if (!is_unk && unk_at >= 0 && index >= static_cast<uint32_t>(unk_at)) return;
-    if (index < cap_left) out[index] = v;
-  };
-  *unk_at_out = -1;
-  if (cls0 == CLS_PUNCT) {
-    const uint32_t k = longest_match_global(V, tv, gs, WP_KIND_PREFIX, &id);
-    if (k == len0) {
-      emit(0, id, false);
-    } else {
-      *unk_at_out = 0;
-      emit(0, V.unk_id, true);
-    }
-    return 1;
-  }
-  size_t p = gs;
-  uint32_t n = 0, word_first = 0, kind = WP_KIND_PREFIX;
-  bool at_han = (cls0 == CLS_HAN);
-  for (;;) {
-    const uint32_t k = longest_match_global(V, tv, p, kind, &id);
-    if (k == 0) {
-      if (at_han && !V.han_swallow) {
-        // max_len < 2: the Han char alone is UNK, the run after it is a new word
-        emit(n, V.unk_id, true);  // not rolled back later: word_first moves past it
-        n += 1;
-        word_first = n;
-        at_han = false;
-        uint32_t l, c;
-        p = gnext(tv, p + len0, &l, &c);
-        if (p >= tv.n || c != CLS_OTHER) return n;
-        continue;
-      }
-      *unk_at_out = static_cast<int32_t>(word_first);
-      emit(word_first, V.unk_id, true);
-      return word_first + 1;
-    }
-    emit(n, id, false);
-    n += 1;
-    // advance k clean bytes
-    uint32_t o = 0, l = 0, c = CLS_SPACE;
-    while (o < k) {
-      p = gnext(tv, p, &l, &c);
-      o += l;
-      p += l;
-    }
-    p = gnext(tv, p, &l, &c);
-    if (p >= tv.n || c != CLS_OTHER) return n;
-    if (at_han && k == len0) {
-      word_first = n;
-      kind = WP_KIND_PREFIX;
-    } else {
-      kind = WP_KIND_SUFFIX;
-    }
-    at_han = false;
-  }
+  return best;
 }
 
 // ------------------------------------------------------------- classification
@@ -676,75 +463,49 @@ __device__ __forceinline__ unsigned long long lookback_walk(volatile unsigned lo
   return base;
 }
 
-// 24 window bytes starting at p (any alignment) as six little-endian words
-__device__ __forceinline__ void load_window(const uint8_t *buf, int p, uint32_t r[6]) {
+// 16 window bytes starting at p (any alignment) as four little-endian words
+__device__ __forceinline__ void load_window(const uint8_t *buf, int p, uint32_t r[4]) {
   const int a = p & ~3;
   const uint32_t sh = (p & 3) * 8;
-  uint32_t x[7];
+  uint32_t x[5];
 #pragma unroll
-  for (int i = 0; i < 7; i++) x[i] = ld_u32(buf + a + 4 * i);
+  for (int i = 0; i < 5; i++) x[i] = ld_u32(buf + a + 4 * i);
 #pragma unroll
-  for (int i = 0; i < 6; i++) r[i] = __funnelshift_r(x[i], x[i + 1], sh);
+  for (int i = 0; i < 4; i++) r[i] = __funnelshift_r(x[i], x[i + 1], sh);
 }
 
-// the same from the text in global memory (bytes past the end read as spaces)
-__device__ __forceinline__ void load_window_global(const uint8_t *text, size_t n_bytes, size_t pos, uint32_t r[6]) {
-  const uint8_t *addr = text + pos;
-  if (pos + 32 <= n_bytes) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(addr) & ~static_cast<uintptr_t>(3);
-    const uint32_t sh = (reinterpret_cast<uintptr_t>(addr) & 3u) * 8u;
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(a);
-    uint32_t x[7];
-#pragma unroll
-    for (int i = 0; i < 7; i++) x[i] = __ldg(w + i);
-#pragma unroll
-    for (int i = 0; i < 6; i++) r[i] = __funnelshift_r(x[i], x[i + 1], sh);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-      uint32_t v = 0;
-#pragma unroll
-      for (int b = 0; b < 4; b++) {
-        const size_t q = pos + 4 * i + b;
-        v |= (q < n_bytes ? static_cast<uint32_t>(text[q]) : 0x20u) << (8 * b);
-      }
-      r[i] = v;
-    }
-  }
-}
-
+// Row k (0..16) of the key-mask table: byte masks of the four key words of a k-byte key.  Rows are 16 bytes
+// apart and lanes read the row of their own length: rows 1..8 — nearly all segments — lie in eight different
+// groups of four banks, so a quarter warp's 16-byte loads do not collide.
 __device__ __forceinline__ void init_key_mask(uint4 *key_mask, int tid) {
-  if (tid <= static_cast<int>(WP_KEY_BYTES)) {
-    const uint32_t k = tid;  // row k of the key mask table
-    uint32_t m[6];
+  if (tid <= static_cast<int>(WORD_KEY_BYTES)) {
+    uint32_t m[4];
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-      const int nb = static_cast<int>(k) - 4 * i;
+    for (int i = 0; i < 4; i++) {
+      const int nb = tid - 4 * i;
       m[i] = nb >= 4 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
     }
-    key_mask[KEY_MASK_ROW * k] = make_uint4(m[0], m[1], m[2], m[3]);
-    key_mask[KEY_MASK_ROW * k + 1] = make_uint4(m[4], m[5] & 0xFFFFu, k << 16, 0u);
+    key_mask[tid] = make_uint4(m[0], m[1], m[2], m[3]);
   }
 }
 
 // ================================================================ K1: split
 
-// A single-char segment whose home slot holds another key: walk the probe sequence to the key or to an
-// empty slot.  Rare (a few lanes per tile at most), so kept out of line; returns the node's term id
-// (possibly WP_NO_ID) or SINGLE_WALK_MISS.
+// A single-char segment whose lookup ran past WORD_PROBES slots: follow the probe sequence to the word or to
+// an empty slot (the static part is complete, so absence means no such token).  Rare, so kept out of line;
+// returns the id or SINGLE_WALK_MISS.
 constexpr int32_t SINGLE_WALK_MISS = WP_NO_ID - 1;
-constexpr uint16_t PARK_PENDING = 0xFFFFu;  // parked high half of a result is < 0x4000 (results are < 2^30)
-__device__ __noinline__ int32_t single_char_walk(const uint4 *tab, uint32_t slot_mask, uint32_t k0, uint32_t k1,
-                                                 uint32_t k2, uint32_t k3, uint32_t k4, uint32_t k5) {
-  const uint32_t kw[6] = {k0, k1, k2, k3, k4, k5};
-  uint32_t idx = (key_hash(k0, k1, k2, k3, k4, k5) + 1) & slot_mask;
-  for (;;) {
+constexpr uint16_t PARK_PENDING = 0xFFFFu;  // parked high half of a result is < 0x8000
+__device__ __noinline__ int32_t single_char_walk(const WordSlot *tab, uint32_t mask, uint32_t idx, uint32_t k0,
+                                                 uint32_t len) {
+  for (uint32_t n = 0; n <= mask; n++) {  // (a working table that K2 has filled to the last slot has no empty one)
     uint4 a, b;
-    ld_slot(tab, idx, &a, &b);
-    if (slot_len(b.y) == 0) return SINGLE_WALK_MISS;
-    if (slot_matches(a, b, kw)) return static_cast<int32_t>(b.z);
-    idx = (idx + 1) & slot_mask;
+    ld_word_slot(tab, idx, &a, &b);
+    if (b.x == 0) break;
+    if ((b.x & WORD_READY) && word_meta_len(b.x) == len && a.x == k0) return static_cast<int32_t>(b.y);
+    idx = (idx + 1) & mask;
   }
+  return SINGLE_WALK_MISS;
 }
 
 __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
@@ -760,14 +521,9 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   if (tid == 0) {
     sm.left_spill = 0;
     sm.n_slow = 0;
-    sm.n_slow2 = 0;
-    sm.memo_hits = 0;
+    sm.dyn_hits = 0;
+    sm.n_eligible = 0;
     sm.any_single = 0;
-  }
-  if (tid == 32) {
-    // whether the memo is still worth its lookups was decided by K2 of the previous range (uniform over this
-    // range: the phase has barriers); read here, next to the ticket, so that the round trip is hidden
-    sm.memo_use = P.memo != nullptr && (P.range_index < 2 || P.call->memo_off == 0u);
   }
   init_key_mask(sm.key_mask, tid);
   __syncthreads();
@@ -966,66 +722,90 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     lookback_publish(P.tile_state, rel_tile, n_segs);
     if (dirty) atomicAdd(&P.call->dirty_tiles, 1ull);
   }
-  const uint4 *tab = reinterpret_cast<const uint4 *>(V.slots);
+  const WordSlot *wtab = P.words;
 
-  // ---- S2a: one whole-window probe per segment, statically assigned (uniform
-  // work: every lane does the same thing; two segments per lane and turn so that
-  // two table loads are in flight).  It settles every segment that is a single
-  // token (fast.cpp:66-72 hit on the first, longest candidate) and every
-  // single-char segment; the rest — and the rare probe that lands on another
-  // key's slot — go to the slow list.
+  // ---- S2: one word-table lookup per segment of at most 16 bytes, statically assigned (uniform work: every
+  // lane does the same thing; two segments per lane and turn so that two table loads are in flight).  A hit
+  // settles the segment — with the token it is (static part, fast.cpp:66-72: the longest candidate is the
+  // whole window) or with the ids K2 recorded for these bytes earlier in this call.  A single-char segment
+  // that is absent is UNK.  The rest go to the slow list.
   constexpr int PER_TURN = 2;
+  uint32_t my_dyn = 0, my_elig = 0;
   for (uint32_t base = 0; base < n_segs; base += PER_TURN * THREADS) {
-    uint32_t kk[PER_TURN], slow[PER_TURN], wlen[PER_TURN], first_len[PER_TURN], kw[PER_TURN][6];
+    uint32_t kk[PER_TURN], state[PER_TURN], wlen[PER_TURN], idx[PER_TURN], key[PER_TURN][4];
     uint4 sa[PER_TURN], sb[PER_TURN];
 #pragma unroll
     for (int u = 0; u < PER_TURN; u++) {
       const uint32_t k = base + u * THREADS + tid;
       kk[u] = k;
-      slow[u] = 0;  // 0 = settled (or no segment), else the flags of the tile slow-list entry | 1
+      state[u] = 0;  // 0 = no segment, 1 = looked up, 2 = slow, 3 = slow and LONG
       wlen[u] = 0;
-      first_len[u] = 0;
+      idx[u] = 0;
       sa[u] = make_uint4(0, 0, 0, 0);
       sb[u] = make_uint4(0, 0, 0, 0);
       if (k < n_segs) {
-        const uint32_t sv = sm.seg_s[k];
-        const int s = static_cast<int>(sv & POS_MASK);
+        const int s = static_cast<int>(sm.seg_s[k] & POS_MASK);
         const uint32_t j = k + skip;
         int e = limit;
+        bool leaves = false;
         if (j < n_ends) {
           e = sm.seg_e[j];
-        } else if (more_text) {  // leaves the window: walked from global memory in K2
-          slow[u] = SLOW_WALK | 1u;
+        } else {
+          leaves = more_text;  // no end inside the window
         }
-        if (!slow[u]) {
-          wlen[u] = static_cast<uint32_t>(e - s);
-          first_len[u] = utf8_lead_len(buf[s]);
-          const uint32_t k0 = wlen[u] < WP_KEY_BYTES ? wlen[u] : WP_KEY_BYTES;
-          uint32_t r[6];
+        const uint32_t len = static_cast<uint32_t>(e - s);
+        wlen[u] = len;
+        if (leaves || len > LONG_SEGMENT_BYTES) {
+          state[u] = 3;
+        } else if (len > WORD_KEY_BYTES) {
+          state[u] = 2;
+        } else {
+          state[u] = 1;
+          uint32_t r[4];
           load_window(buf, s, r);
-          make_key_tab(sm.key_mask, r, k0, WP_KIND_PREFIX, kw[u]);
-          const uint32_t idx = key_hash(kw[u][0], kw[u][1], kw[u][2], kw[u][3], kw[u][4], kw[u][5]) & V.slot_mask;
-          ld_slot(tab, idx, &sa[u], &sb[u]);
+          const uint4 km = sm.key_mask[len];
+          key[u][0] = r[0] & km.x;
+          key[u][1] = r[1] & km.y;
+          key[u][2] = r[2] & km.z;
+          key[u][3] = r[3] & km.w;
+          idx[u] = word_hash(key[u][0], key[u][1], key[u][2], key[u][3], len, P.word_shift);
+          ld_word_slot(wtab, idx[u], &sa[u], &sb[u]);
         }
       }
     }
 #pragma unroll
     for (int u = 0; u < PER_TURN; u++) {
       bool settled = false;
-      if (wlen[u] != 0) {
-        // one slot only here (K2 looks at pairs): a probe that lands on another key's slot is left to K2 —
-        // except for single-char segments: every segment handed to K2 must have at least two bytes (the
-        // slow-list capacities rely on it), so those are marked and settled by the pass below (rare)
-        const bool empty = slot_len(sb[u].y) == 0;
-        const bool match = !empty && slot_matches(sa[u], sb[u], kw[u]);
-        const int32_t term = static_cast<int32_t>(sb[u].z);
-        const bool hit = match && term != WP_NO_ID && wlen[u] <= WP_KEY_BYTES;
-        const bool single = wlen[u] == first_len[u];  // no token (empty), only a prefix of tokens, or a collision
-        if (hit || single) {
-          // settled: park the result (id + 1) in the two list entries of the segment, which are no longer
-          // needed, until the tile knows its first global segment number
-          const uint32_t res = static_cast<uint32_t>((hit ? term : V.unk_id) + 1);
-          if (single && !empty && !match) {
+      if (state[u] == 1) {
+        uint32_t outcome = 2;  // 0 = absent, 1 = hit, 2 = not decided within WORD_PROBES slots
+        for (uint32_t t = 0;; t++) {
+          const uint32_t meta = sb[u].x;
+          if (meta == 0) {
+            outcome = 0;
+            break;
+          }
+          if ((meta & WORD_READY) && word_meta_len(meta) == wlen[u] && sa[u].x == key[u][0] && sa[u].y == key[u][1] &&
+              sa[u].z == key[u][2] && sa[u].w == key[u][3]) {
+            outcome = 1;
+            break;
+          }
+          if (t == WORD_PROBES - 1) break;
+          idx[u] = (idx[u] + 1) & P.word_mask;
+          ld_word_slot(wtab, idx[u], &sa[u], &sb[u]);
+        }
+        const bool single = wlen[u] == utf8_lead_len(key[u][0] & 0xFFu);
+        if (outcome == 1 || single) {
+          // settled: park the result in the two list entries of the segment, which are no longer needed, until
+          // the tile knows its first global segment number
+          uint32_t res;
+          if (outcome == 1) {
+            const uint32_t cnt = word_meta_count(sb[u].x);
+            res = cnt == 1 ? sb[u].y + 1u : (SEG_RESULT_WORD | (cnt << SEG_WORD_SLOT_BITS) | idx[u]);
+            my_dyn += (sb[u].x & WORD_DYNAMIC) ? 1u : 0u;
+          } else {
+            res = static_cast<uint32_t>(V.unk_id + 1);
+          }
+          if (outcome == 2) {
             sm.seg_e[kk[u] + skip] = PARK_PENDING;  // seg_s keeps the position for the pass below
             sm.any_single = 1u;
           } else {
@@ -1034,34 +814,46 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
           }
           settled = true;
         } else {
-          // miss on an empty slot: K2 may skip the whole-window probe; match or collision: K2 redoes it
-          slow[u] = (empty ? SLOW_FIRST_MISSED : 0u) | 1u;
+          state[u] = 2;
+          my_elig++;
         }
       }
       const uint32_t settledm = __ballot_sync(FULL, settled);
       if (lane == 0 && base + u * THREADS + (tid & ~31) < n_segs) sm.settled[(base + u * THREADS + tid) >> 5] = settledm;
-      const uint32_t slowm = __ballot_sync(FULL, slow[u] != 0);
+      const uint32_t slowm = __ballot_sync(FULL, state[u] >= 2);
       if (slowm) {
         uint32_t at = 0;
         const int leader = __ffs(slowm) - 1;
         if (lane == leader) at = smem_add(&sm.n_slow, static_cast<uint32_t>(__popc(slowm)));
         at = __shfl_sync(FULL, at, leader);
-        if (slow[u]) sm.slow[at + __popc(slowm & ((1u << lane) - 1u))] = static_cast<uint16_t>(kk[u] | (slow[u] & ~1u));
+        if (state[u] >= 2)
+          sm.slow[at + __popc(slowm & ((1u << lane) - 1u))] = static_cast<uint16_t>(kk[u] | (state[u] == 3 ? SLOW_LONG : 0u));
       }
     }
   }
+  if (P.record_words) {
+    // statistics for K2's decision whether recording words still pays (memo_worthwhile)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      my_dyn += __shfl_xor_sync(FULL, my_dyn, o);
+      my_elig += __shfl_xor_sync(FULL, my_elig, o);
+    }
+    if (lane == 0 && my_dyn) smem_add_noret(&sm.dyn_hits, my_dyn);
+    if (lane == 0 && my_elig) smem_add_noret(&sm.n_eligible, my_elig);
+  }
   __syncthreads();
 
-  // ---- (rare) single-char segments whose home slot holds another key: follow the probe sequence
+  // ---- (rare) single-char segments whose lookup was not decided within WORD_PROBES slots
   if (sm.any_single) {  // uniform
 #pragma unroll 1
     for (uint32_t k = tid; k < n_segs; k += THREADS) {
       if (!((sm.settled[k >> 5] >> (k & 31)) & 1u) || sm.seg_e[k + skip] != PARK_PENDING) continue;
-      uint32_t r[6], key[6];
+      uint32_t r[4];
       load_window(buf, static_cast<int>(sm.seg_s[k] & POS_MASK), r);
-      make_key_tab(sm.key_mask, r, utf8_lead_len(r[0] & 0xFFu), WP_KIND_PREFIX, key);
-      const int32_t term = single_char_walk(tab, V.slot_mask, key[0], key[1], key[2], key[3], key[4], key[5]);
-      const uint32_t res = static_cast<uint32_t>((term >= 0 ? term : V.unk_id) + 1);
+      const uint32_t len = utf8_lead_len(r[0] & 0xFFu);
+      const uint32_t k0 = r[0] & sm.key_mask[len].x;
+      const int32_t id = single_char_walk(wtab, P.word_mask, word_hash(k0, 0u, 0u, 0u, len, P.word_shift), k0, len);
+      const uint32_t res = static_cast<uint32_t>((id != SINGLE_WALK_MISS ? id : V.unk_id) + 1);
       sm.seg_s[k] = static_cast<uint16_t>(res);
       sm.seg_e[k + skip] = static_cast<uint16_t>(res >> 16);
     }
@@ -1086,140 +878,57 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     if ((sm.settled[k >> 5] >> (k & 31)) & 1u)
       P.seg_result[seg_base + k] = static_cast<uint32_t>(sm.seg_s[k]) | (static_cast<uint32_t>(sm.seg_e[k + skip]) << 16);
   }
-
-  // ---- word memo: an unsettled segment of at most 16 bytes whose exact bytes were matched before (by K2,
-  // in an earlier range of this call) is settled here with one lookup; the rest form the final slow list
-  uint32_t n_slow = sm.n_slow;
-  if (n_slow == 0) return;  // uniform
-  if (sm.memo_use && !dirty) {  // uniform
-    // two entries per lane and round, all lookups of a round in flight together; the list is compacted in
-    // place (a round's survivors land below the entries the next round reads)
-    constexpr int MP = 2;
-    uint32_t my_lookups = 0;
-    for (uint32_t base = 0; base < n_slow; base += MP * THREADS) {
-      uint32_t ent[MP], mlen[MP], midx[MP], mk[MP][4];
-      uint4 ma[MP], mb[MP];
-      bool keep[MP], have[MP];
-#pragma unroll
-      for (int u = 0; u < MP; u++) {
-        const uint32_t i = base + u * THREADS + tid;
-        have[u] = i < n_slow;
-        keep[u] = have[u];
-        ent[u] = 0;
-        mlen[u] = 0;
-        midx[u] = 0;
-        ma[u] = make_uint4(0, 0, 0, 0);
-        mb[u] = make_uint4(0, 0, 0, 0);
-        if (have[u]) {
-          ent[u] = sm.slow[i];
-          my_lookups++;  // counted per unsettled segment, eligible or not: the memo must pay for the whole slow lane
-          if (!(ent[u] & SLOW_WALK)) {
-            const uint32_t k = ent[u] & 0xFFFu;
-            const int s = static_cast<int>(sm.seg_s[k] & POS_MASK);
-            const uint32_t j = k + skip;
-            const int e = j < n_ends ? static_cast<int>(sm.seg_e[j]) : limit;
-            const uint32_t len = static_cast<uint32_t>(e - s);
-            if (len <= MEMO_KEY_BYTES) {
-              uint32_t r[6];
-              load_window(buf, s, r);
-              const uint4 km = sm.key_mask[KEY_MASK_ROW * len];
-              mk[u][0] = r[0] & km.x; mk[u][1] = r[1] & km.y; mk[u][2] = r[2] & km.z; mk[u][3] = r[3] & km.w;
-              midx[u] = key_hash(mk[u][0], mk[u][1], mk[u][2], mk[u][3], len, MEMO_SALT) & P.memo_mask;
-              ma[u] = __ldg(P.memo + 2 * static_cast<size_t>(midx[u]));
-              mb[u] = __ldg(P.memo + 2 * static_cast<size_t>(midx[u]) + 1);
-              mlen[u] = len;
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < MP; u++) {
-        if (mlen[u] == 0) continue;
-        for (int t = 0;; t++) {
-          if (mb[u].x == 0) break;
-          if ((mb[u].x & MEMO_READY) && (mb[u].x & 0xFFu) == mlen[u] && ma[u].x == mk[u][0] && ma[u].y == mk[u][1] &&
-              ma[u].z == mk[u][2] && ma[u].w == mk[u][3]) {
-            P.seg_result[seg_base + (ent[u] & 0xFFFu)] =
-                SEG_RESULT_MEMO | (((mb[u].x >> 8) & 3u) << SEG_MEMO_SLOT_BITS) | midx[u];
-            keep[u] = false;
-            break;
-          }
-          if (t == 1) break;  // K2 inserts within a few slots of home; two are looked at here
-          midx[u] = (midx[u] + 1) & P.memo_mask;
-          ma[u] = __ldg(P.memo + 2 * static_cast<size_t>(midx[u]));
-          mb[u] = __ldg(P.memo + 2 * static_cast<size_t>(midx[u]) + 1);
-        }
-      }
-      __syncthreads();  // every entry of this round has been read
-#pragma unroll
-      for (int u = 0; u < MP; u++) {
-        const uint32_t keepm = __ballot_sync(FULL, keep[u]);
-        const uint32_t hitm = __ballot_sync(FULL, have[u] && !keep[u]);
-        if (keepm) {
-          uint32_t at = 0;
-          const int leader = __ffs(keepm) - 1;
-          if (lane == leader) {
-            at = smem_add(&sm.n_slow2, static_cast<uint32_t>(__popc(keepm)));
-            if (hitm) smem_add_noret(&sm.memo_hits, static_cast<uint32_t>(__popc(hitm)));
-          }
-          at = __shfl_sync(FULL, at, leader);
-          if (keep[u]) sm.slow[at + __popc(keepm & ((1u << lane) - 1u))] = static_cast<uint16_t>(ent[u]);
-        } else if (hitm && lane == 0) {
-          smem_add_noret(&sm.memo_hits, static_cast<uint32_t>(__popc(hitm)));
-        }
-      }
-    }
-    __syncthreads();
-    n_slow = sm.n_slow2;
-    if (tid == 0 && sm.memo_hits) atomicAdd(&P.call->memo_hits, static_cast<unsigned long long>(sm.memo_hits));
-    if (P.range_index >= 1) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) my_lookups += __shfl_xor_sync(FULL, my_lookups, o);
-      if (lane == 0 && my_lookups) atomicAdd(&P.call->memo_lookups, static_cast<unsigned long long>(my_lookups));
-    }
-    if (n_slow == 0) return;  // uniform
+  if (tid == 0 && P.record_words && P.range_index >= 1) {
+    const uint32_t h = sm.dyn_hits, l = sm.dyn_hits + sm.n_eligible;
+    if (h) atomicAdd(&P.call->memo_hits, static_cast<unsigned long long>(h));
+    if (l) atomicAdd(&P.call->memo_lookups, static_cast<unsigned long long>(l));
   }
 
-  // ---- hand the unsettled segments to K2: 16-byte entries in the global slow
-  // list (one reservation per tile), id-scratch space reserved by byte length
-  // (a segment never has more ids than bytes).
+  // ---- hand the unsettled segments to K2: 16-byte entries in the global slow list and, per entry, an area
+  // of the arena (one reservation per tile): `len` words for its ids (a segment never has more ids than
+  // bytes), then its clean bytes, so that K2 never goes back to the text
+  const uint32_t n_slow = sm.n_slow;
+  if (n_slow == 0) return;  // uniform
   {
     const uint32_t per = (n_slow + THREADS - 1) / THREADS;
     const uint32_t lo = min(n_slow, static_cast<uint32_t>(tid) * per);
     const uint32_t hi = min(n_slow, lo + per);
-    uint32_t my_len = 0, n_walk = 0;
+    uint32_t my_words = 0, n_long = 0;
 #pragma unroll 1
     for (uint32_t i = lo; i < hi; i++) {
       const uint32_t ent = sm.slow[i];
       const uint32_t k = ent & 0xFFFu;
-      if (dirty || (ent & SLOW_WALK)) {
-        n_walk += (ent & SLOW_WALK) ? 1u : 0u;
+      if (ent & SLOW_LONG) {
+        n_long++;
         continue;
       }
-      const uint32_t j = k + skip;
-      const int e = j < n_ends ? static_cast<int>(sm.seg_e[j]) : limit;
-      my_len += static_cast<uint32_t>(e - static_cast<int>(sm.seg_s[k] & POS_MASK));
+      const int e = k + skip < n_ends ? static_cast<int>(sm.seg_e[k + skip]) : limit;
+      const uint32_t len = static_cast<uint32_t>(e - static_cast<int>(sm.seg_s[k] & POS_MASK));
+      my_words += len + ((len + 3u) >> 2);
     }
-    uint32_t total_len;
-    const unsigned long long sc2 = tile_exclusive_scan(sm.warp_sums, my_len);
+    const unsigned long long sc2 = tile_exclusive_scan(sm.warp_sums, my_words);
     uint32_t run = static_cast<uint32_t>(sc2);
-    total_len = static_cast<uint32_t>(sc2 >> 32);
+    const uint32_t total_words = static_cast<uint32_t>(sc2 >> 32);
     if (tid == 0) {
-      // n_slow and tok_reserved sit side by side: one 64-bit atomic reserves both (one round trip to L2)
-      static_assert(offsetof(RangeCounters, tok_reserved) == offsetof(RangeCounters, n_slow) + 4 &&
+      // n_slow and arena_reserved sit side by side: one 64-bit atomic reserves both (one round trip to L2)
+      static_assert(offsetof(RangeCounters, arena_reserved) == offsetof(RangeCounters, n_slow) + 4 &&
                         offsetof(RangeCounters, n_slow) % 8 == 0,
-                    "n_slow / tok_reserved must form one aligned 64-bit word");
+                    "n_slow / arena_reserved must form one aligned 64-bit word");
       const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(&P.counters->n_slow),
-                                               (static_cast<unsigned long long>(total_len) << 32) | n_slow);
+                                               (static_cast<unsigned long long>(total_words) << 32) | n_slow);
       sm.slow_base = static_cast<uint32_t>(old);
-      sm.tok_base = static_cast<uint32_t>(old >> 32);
+      sm.arena_base = static_cast<uint32_t>(old >> 32);
     }
-    if (n_walk) atomicAdd(&P.call->long_segments, static_cast<unsigned long long>(n_walk));
+    uint32_t long_at = 0;
+    if (n_long) {
+      atomicAdd(&P.call->long_segments, static_cast<unsigned long long>(n_long));
+      long_at = atomicAdd(&P.counters->n_long, n_long);
+    }
     __syncthreads();
     const uint32_t slow_base = sm.slow_base;
-    const uint32_t tok_base = sm.tok_base;
+    const uint32_t arena_base = sm.arena_base;
     if (static_cast<unsigned long long>(slow_base) + n_slow > P.slow_capacity ||
-        static_cast<unsigned long long>(tok_base) + total_len > P.tok_capacity) {
+        static_cast<unsigned long long>(arena_base) + total_words > P.arena_capacity) {
       if (tid == 0) P.call->overflow = 1u;
       return;  // uniform
     }
@@ -1229,45 +938,45 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       const uint32_t k = ent & 0xFFFu;
       const uint32_t sv = sm.seg_s[k];
       int wpos = static_cast<int>(sv & POS_MASK);
-      const bool walk = dirty || (ent & SLOW_WALK);
-      uint32_t len = 0;
-      if (!walk) {
-        const uint32_t j = k + skip;
-        const int e = j < n_ends ? static_cast<int>(sm.seg_e[j]) : limit;
-        len = static_cast<uint32_t>(e - wpos);
-      }
-      if (dirty) {
-        // window position -> raw window position: undo the compaction
-        int a = 0, b = NCHUNK;  // last chunk whose first surviving byte is at or before wpos
-        while (a < b) {
-          const int m = (a + b + 1) >> 1;
-          if (sm.kept_scan[m] <= static_cast<uint32_t>(wpos)) a = m; else b = m - 1;
-        }
-        const uint32_t kk = static_cast<uint32_t>(wpos) - sm.kept_scan[a];
-        wpos = a * CHUNK + static_cast<int>(__fns(sm.m_kept[a], 0, static_cast<int>(kk) + 1));
-      }
-      const size_t pos = t0 + static_cast<size_t>(wpos);
       SlowEntry out;
-      out.pos_lo = static_cast<uint32_t>(pos);
-      out.meta = static_cast<uint32_t>((pos >> 32) & 0xFFu) | (len << 8) | ((sv >> 14) << 24) |
-                 ((ent & SLOW_FIRST_MISSED) ? SLOW_META_MISSED : 0u) | (walk ? SLOW_META_WALK : 0u);
-      out.tok_off = tok_base + run;
       out.seg = static_cast<uint32_t>(seg_base + k);
-      run += len;
-      if (!walk && len <= SLOW_TEXT_BYTES) {
-        // K2 would otherwise fetch these bytes from DRAM again, one random sector per piece
-        out.meta |= SLOW_META_TEXT;
-        const int a = wpos & ~3;
+      if (ent & SLOW_LONG) {
+        if (dirty) {
+          // window position -> raw window position: undo the compaction
+          int a = 0, b = NCHUNK;  // last chunk whose first surviving byte is at or before wpos
+          while (a < b) {
+            const int m = (a + b + 1) >> 1;
+            if (sm.kept_scan[m] <= static_cast<uint32_t>(wpos)) a = m; else b = m - 1;
+          }
+          const uint32_t kk = static_cast<uint32_t>(wpos) - sm.kept_scan[a];
+          wpos = a * CHUNK + static_cast<int>(__fns(sm.m_kept[a], 0, static_cast<int>(kk) + 1));
+        }
+        const size_t pos = t0 + static_cast<size_t>(wpos);
+        out.off = 0;
+        out.meta = ((sv >> 14) << 16) | SLOW_META_LONG | (static_cast<uint32_t>((pos >> 32) & 0xFFu) << 24);
+        out.pos_lo = static_cast<uint32_t>(pos);
+        if (long_at < P.long_capacity) P.long_list[long_at] = slow_base + i;  // K2L's work list
+        long_at++;
+      } else {
+        const int e = k + skip < n_ends ? static_cast<int>(sm.seg_e[k + skip]) : limit;
+        const uint32_t len = static_cast<uint32_t>(e - wpos);
+        out.off = arena_base + run;
+        out.meta = len | ((sv >> 14) << 16);
+        out.pos_lo = 0;
+        uint32_t *dst = P.arena + out.off + len;
+        const uint32_t nw = (len + 3u) >> 2;
+        const uint8_t *src = buf + (wpos & ~3);
         const uint32_t sh = (wpos & 3) * 8;
-        uint32_t x[9];
-#pragma unroll
-        for (int q = 0; q < 9; q++) x[q] = ld_u32(buf + a + 4 * q);
-        uint32_t y[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) y[q] = __funnelshift_r(x[q], x[q + 1], sh);
-        uint4 *dst = P.slow_text + 2 * static_cast<size_t>(slow_base + i);
-        dst[0] = make_uint4(y[0], y[1], y[2], y[3]);
-        dst[1] = make_uint4(y[4], y[5], y[6], y[7]);
+        uint32_t x0 = ld_u32(src);
+#pragma unroll 1
+        for (uint32_t q = 0; q < nw; q++) {
+          const uint32_t x1 = ld_u32(src + 4 * q + 4);
+          uint32_t w = __funnelshift_r(x0, x1, sh);
+          if (q == nw - 1 && (len & 3u)) w &= (1u << (8 * (len & 3u))) - 1u;
+          dst[q] = w;
+          x0 = x1;
+        }
+        run += len + nw;
       }
       *reinterpret_cast<uint4 *>(&P.slow[slow_base + i]) = *reinterpret_cast<const uint4 *>(&out);
       P.seg_result[seg_base + k] = SEG_RESULT_SLOW | (slow_base + i);
@@ -1278,70 +987,39 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
 // ================================================================ K2: match
 
 constexpr uint32_t SEG_HAN_FIRST = 1u;   // about to match the first piece of a Han-led segment
-constexpr uint32_t SEG_KNOWN_MISS = 2u;  // the whole-window probe of the first piece is known to miss (K1 did it)
 
-// The exact byte-wise lane for one entry: the segment left its tile's window or holds invalid UTF-8.
-__device__ __noinline__ void match_walk(const EncodeParams &P, uint32_t i, size_t seg_pos, uint32_t spill_base) {
-  const TextView tv{P.text, P.n_bytes};
-  int32_t unk_at, tmp;
-  const uint32_t cnt = walk_segment(P.vocab, tv, seg_pos, nullptr, 0, -1, &unk_at);
-  const uint32_t off = spill_base + atomicAdd(&P.counters->tok_spill, cnt);
-  uint32_t written = 0;
-  if (static_cast<unsigned long long>(off) + cnt <= P.tok_capacity) {
-    walk_segment(P.vocab, tv, seg_pos, P.tok + off, cnt, unk_at, &tmp);
-    written = cnt;
-  } else {
-    P.call->overflow = 1u;
-  }
-  const uint32_t seg = P.slow[i].seg;
-  *reinterpret_cast<uint4 *>(&P.slow[i]) = make_uint4(written, off, 0u, 0u);  // result form, not inline
-  P.seg_result[seg] = SEG_RESULT_SLOW | (min(written, SEG_SLOW_COUNT_MAX) << SEG_SLOW_INDEX_BITS) | i;
-}
-
-// Every lane owns a long run of slow-list entries (its warp's share / 32), so
-// chains of very different length average out.  The loop is aligned on PIECES:
-//   round:  lanes without a segment take the next entry
-//           every lane loads the 24-byte window of its next piece
-//           inner loop: one table probe per iteration until every lane's piece
-//                       is settled (whole-window probe, then binary search for
-//                       the deepest trie node; a collision is one more turn)
-//           every lane reads its longest match off the deepest node and applies
-//           the piece (fast.cpp:66-91)
-// so the refill / window / apply code runs once per piece and warp, fully
-// converged, and only the short probe body repeats.
-constexpr int LANE_TEXT_WORDS = 17;  // 68 bytes per lane: 32 + 28 readable past any piece start, odd stride (banks)
-
-__global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams P) {
-  __shared__ uint4 key_mask[KEY_MASK_ROW * (WP_KEY_BYTES + 1)];
-  __shared__ uint32_t lane_text[MATCH_THREADS * LANE_TEXT_WORDS];
+// Every lane owns a long run of slow-list entries (its warp's share / 32), so chains of very different
+// length average out.  One loop iteration = one trie step for every lane that holds a segment, whatever the
+// lane is doing: a step that succeeds moves one byte down the trie and remembers the last terminal seen; a
+// step that fails, reaches a leaf or the end of the segment closes the piece (fast.cpp:66-91: emit the
+// longest match, continue behind it in the "##" map, or roll the whole word back to UNK).  Lanes without a
+// segment take the next entries of their warp's share at the top of the loop.
+__global__ void __launch_bounds__(MATCH_THREADS, 4) wp_match_kernel(EncodeParams P) {
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const DeviceVocab &V = P.vocab;
-  init_key_mask(key_mask, tid);
-  __syncthreads();
 
   if (P.call->overflow) return;  // a K1 tile gave up (scratch too small): its entries are unwritten, the host retries
   const uint32_t n_slow = min(P.counters->n_slow, P.slow_capacity);
-  const uint32_t spill_base = min(P.counters->tok_reserved, P.tok_capacity);
   const uint32_t n_warps = gridDim.x * (MATCH_THREADS / 32);
   const uint32_t gw = blockIdx.x * (MATCH_THREADS / 32) + (tid >> 5);
   const uint32_t per = ((n_slow + n_warps - 1) / n_warps + 31u) & ~31u;
   uint32_t cursor = min(n_slow, gw * per);             // warp-uniform: next unassigned entry of this warp
   const uint32_t cursor_end = min(n_slow, cursor + per);
-  const uint4 *tab = reinterpret_cast<const uint4 *>(V.slots);
 
-  bool have = false;       // this lane holds an unfinished segment
-  // K1 of this range is done, so the counters are final: every lane reads the same verdict, and one thread
-  // records it for the K1 tiles of the next range (in a cache line of its own: the counters' line is hot)
+  // K1 of this range is done, so the counters are final: every lane reads the same verdict
   const bool worth = memo_worthwhile(P.call->memo_lookups, P.call->memo_hits, P.range_index <= 1);
   if (blockIdx.x == 0 && tid == 0 && !worth) P.call->memo_off = 1u;
-  bool memo_on = P.memo != nullptr && (P.range_index < 2 || worth);
-  bool in_smem = false;    // ... whose bytes sit in this lane's shared-memory buffer
-  uint32_t *const my_text = lane_text + tid * LANE_TEXT_WORDS;
-  size_t seg_pos = 0;
-  uint32_t ent_index = 0, seg_len = 0, p = 0, tok_off = 0;
-  uint32_t nid = 0, word_first = 0, kind = WP_KIND_PREFIX, flags = 0, first_len = 0;
-  int32_t t0 = 0, t1 = 0, t2 = 0;  // the first three ids of the segment stay in registers (see the result form)
+  bool record = P.record_words != 0 && (P.range_index < 2 || worth);
+
+  bool have = false;       // this lane holds an unfinished segment
+  bool ext = false;        // the current node has children
+  const uint8_t *txt = nullptr;  // the segment's clean bytes (arena)
+  int32_t *out = nullptr;        // the segment's id scratch (arena)
+  uint32_t ent_index = 0, area = 0, seg = 0, seg_len = 0, first_len = 0;
+  uint32_t p = 0, d = 0, node = 0, last_d = 0;          // piece start, depth, trie node, depth of the last terminal
+  uint32_t nid = 0, word_first = 0, kind = WP_KIND_PREFIX, flags = 0;
+  int32_t last_id = WP_NO_ID, t0 = 0, t1 = 0, t2 = 0;   // the first three ids of the segment stay in registers
 
   for (;;) {
     // -- refill: lanes without a segment take the next entries of this warp's share
@@ -1349,38 +1027,28 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams
     if (needm && cursor < cursor_end) {
       const uint32_t i = cursor + __popc(needm & ((1u << lane) - 1u));
       cursor += __popc(needm);  // may pass cursor_end; entries beyond it are simply not taken
-      if (cursor + lane < cursor_end) {
-        // the next 32 entries of this warp's share: by the time a lane takes one, it sits in L1
-        prefetch_l1(&P.slow[cursor + lane]);
-        prefetch_l1(P.slow_text + 2 * static_cast<size_t>(cursor + lane));
-      }
+      if (cursor + lane < cursor_end) prefetch_l1(&P.slow[cursor + lane]);  // the next 32 entries of this share
       if (!have && i < cursor_end) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(&P.slow[i]));
         const uint32_t meta = raw.y;
-        seg_pos = static_cast<size_t>(raw.x) | (static_cast<size_t>(meta & 0xFFu) << 32);
-        if (meta & SLOW_META_WALK) {
-          match_walk(P, i, seg_pos, spill_base);
-        } else {
+        if (!(meta & SLOW_META_LONG)) {  // LONG entries are matched by K2L
           ent_index = i;
-          seg_len = (meta >> 8) & 0xFFFFu;
-          tok_off = raw.z;
-          my_text[LANE_TEXT_WORDS - 1] = raw.w;  // the segment's number (a spare word of the lane buffer)
-          in_smem = (meta & SLOW_META_TEXT) != 0;
-          if (in_smem) {
-            const uint4 ta = __ldg(P.slow_text + 2 * static_cast<size_t>(i));
-            const uint4 tb = __ldg(P.slow_text + 2 * static_cast<size_t>(i) + 1);
-            my_text[0] = ta.x; my_text[1] = ta.y; my_text[2] = ta.z; my_text[3] = ta.w;
-            my_text[4] = tb.x; my_text[5] = tb.y; my_text[6] = tb.z; my_text[7] = tb.w;
-            first_len = utf8_lead_len(ta.x & 0xFFu);
-          } else {
-            first_len = utf8_lead_len(P.text[seg_pos]);
-          }
+          area = raw.x;
+          seg = raw.w;
+          seg_len = meta & 0xFFFFu;
+          out = reinterpret_cast<int32_t *>(P.arena + area);
+          txt = reinterpret_cast<const uint8_t *>(P.arena + area + seg_len);
+          first_len = utf8_lead_len(txt[0]);
           have = true;
+          ext = true;
           p = 0;
+          d = 0;
+          last_d = 0;
           nid = 0;
           word_first = 0;
           kind = WP_KIND_PREFIX;
-          flags = (((meta >> 24) & 3u) == CLS_HAN ? SEG_HAN_FIRST : 0u) | ((meta & SLOW_META_MISSED) ? SEG_KNOWN_MISS : 0u);
+          node = WP_KIND_PREFIX;
+          flags = ((meta >> 16) & 3u) == CLS_HAN ? SEG_HAN_FIRST : 0u;
         }
       }
     }
@@ -1388,193 +1056,322 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) wp_match_kernel(EncodeParams
       if (cursor >= cursor_end) break;
       continue;
     }
+    if (!have) continue;
 
-    // -- piece start: window bytes and search bounds
-    uint32_t r[6] = {0, 0, 0, 0, 0, 0};
-    uint32_t k = 0, lo = 0, hi = 0, poff = 0;
-    uint32_t node_w5 = 0, node_slot = 0;
-    int32_t node_term = WP_NO_ID, node_best = WP_NO_ID;
-    bool searching = have;
-    if (have) {
-      if (in_smem) {
-        // p < 32, so the 28 bytes read stay inside the 68-byte lane buffer; bytes past the segment are
-        // stale but never enter a key (k <= remaining length)
-        const uint32_t a = p >> 2, sh = (p & 3u) * 8u;
-        uint32_t x[7];
-#pragma unroll
-        for (int q = 0; q < 7; q++) x[q] = my_text[a + q];
-#pragma unroll
-        for (int q = 0; q < 6; q++) r[q] = __funnelshift_r(x[q], x[q + 1], sh);
-      } else {
-        load_window_global(P.text, P.n_bytes, seg_pos + p, r);
-      }
-      const uint32_t wlen = seg_len - p;
-      const uint32_t k0 = wlen < WP_KEY_BYTES ? wlen : WP_KEY_BYTES;
-      if (flags & SEG_KNOWN_MISS) {  // k0 >= 2 here
-        hi = k0;
-        k = k0 >> 1;
-        flags &= ~SEG_KNOWN_MISS;
-      } else {
-        hi = k0 + 1;
-        k = k0;
+    // -- one trie step
+    bool closed = true;
+    if (ext && p + d < seg_len) {
+      uint4 e;
+      if (trie_step(V, node, txt[p + d], &e)) {
+        node = e.y;
+        d++;
+        if (static_cast<int32_t>(e.z) != WP_NO_ID) {
+          last_d = d;
+          last_id = static_cast<int32_t>(e.z);
+        }
+        ext = (e.w & EDGE_HAS_CHILDREN) != 0;
+        closed = !ext || p + d >= seg_len;
       }
     }
+    if (!closed) continue;
 
-    // -- probes: deepest trie node along the window (existence is monotone in the depth)
-    while (__any_sync(FULL, searching)) {
-      if (searching) {
-        uint32_t kw[6];
-        make_key_tab(key_mask, r, k, kind, kw);
-        const uint32_t idx = (key_hash(kw[0], kw[1], kw[2], kw[3], kw[4], kw[5]) + poff) & V.slot_mask;
-        uint4 sa, sb, sc, sd;
-        ld_slot(tab, idx, &sa, &sb);
-        uint32_t oc;
-        if (V.probe_pairs) {  // uniform
-          ld_slot(tab, (idx + 1) & V.slot_mask, &sc, &sd);
-          oc = pair_outcome(sa, sb, sc, sd, kw);
+    // -- the piece is closed: its longest match is the last terminal seen (fast.cpp:66-77)
+    const uint32_t mlen = last_d;
+    bool done = false;
+    // ids 0..2 go to registers, later ones straight to the id scratch
+    auto put = [&](uint32_t index, int32_t v) {
+      if (index == 0) t0 = v;
+      else if (index == 1) t1 = v;
+      else if (index == 2) t2 = v;
+      else out[index] = v;
+    };
+    if (flags & SEG_HAN_FIRST) {
+      flags = 0;
+      nid = 1;
+      if (mlen == 0) {
+        t0 = V.unk_id;
+        if (V.han_swallow) {
+          done = true;  // fast.cpp:85-88: begin += word_len swallows the run
         } else {
-          sc = sa;
-          sd = sb;
-          oc = slot_len(sb.y) == 0 ? PAIR_MISS : (slot_matches(sa, sb, kw) ? PAIR_HIT0 : PAIR_BOTH_OTHER);
+          word_first = 1;
+          p += first_len;
         }
-        if (oc == PAIR_BOTH_OTHER) {
-          poff += V.probe_pairs ? 2u : 1u;  // the slot(s) hold other keys: walk on, same key
-        } else {
-          poff = 0;
-          if (oc != PAIR_MISS) {
-            const bool second = oc == PAIR_HIT1;
-            lo = k;
-            node_w5 = second ? sd.y : sb.y;
-            node_term = static_cast<int32_t>(second ? sd.z : sb.z);
-            node_best = static_cast<int32_t>(second ? sd.w : sb.w);
-            node_slot = (idx + (second ? 1u : 0u)) & V.slot_mask;
-          } else {
-            hi = k;
-          }
-          k = (lo + hi) >> 1;
-          searching = hi - lo > 1;
-        }
-      }
-    }
-
-    // -- the deepest node is at depth lo: read the longest match off it and apply the piece
-    if (have) {
-      uint32_t mlen = 0;
-      int32_t mid = WP_NO_ID;
-      if (lo != 0) {
-        if (node_term != WP_NO_ID) {
-          mlen = lo;
-          mid = node_term;
-        } else if (slot_best_len(node_w5) != 0) {
-          mlen = slot_best_len(node_w5);
-          mid = node_best;
-        }
-        if (lo == WP_KEY_BYTES && slot_has_long(node_w5) && seg_len - p > WP_KEY_BYTES) {
-          // tokens longer than the inline key hang off this node, longest first
-          const uint32_t ref = V.long_ref[node_slot];
-          const uint32_t cnt = V.long_entries[ref];
-          const uint8_t *txt = P.text + seg_pos + p;
-          for (uint32_t li = 0; li < cnt; li++) {
-            const uint32_t len = V.long_entries[ref + 1 + 3 * li];
-            if (len > seg_len - p) continue;
-            const uint8_t *tok = V.long_bytes + V.long_entries[ref + 3 + 3 * li];
-            uint32_t o = WP_KEY_BYTES;
-            while (o < len && txt[o] == tok[o]) o++;
-            if (o == len) {
-              mlen = len;
-              mid = static_cast<int32_t>(V.long_entries[ref + 2 + 3 * li]);
-              break;
-            }
-          }
-        }
-      }
-      bool done = false;
-      int32_t *out = P.tok + tok_off;
-      // ids 0..2 go to registers, later ones straight to the id scratch
-      auto put = [&](uint32_t index, int32_t v) {
-        if (index == 0) t0 = v;
-        else if (index == 1) t1 = v;
-        else if (index == 2) t2 = v;
-        else out[index] = v;
-      };
-      if (flags & SEG_HAN_FIRST) {
-        flags = 0;
-        nid = 1;
-        if (mlen == 0) {
-          t0 = V.unk_id;
-          if (V.han_swallow) {
-            done = true;  // fast.cpp:85-88: begin += word_len swallows the run
-          } else {
-            word_first = 1;
-            p += first_len;
-          }
-        } else {
-          t0 = mid;
-          p += mlen;
-          if (mlen == first_len) {
-            word_first = 1;  // fast.cpp:89-91: the next position follows a spacing char => new word
-          } else {
-            kind = WP_KIND_SUFFIX;
-          }
-        }
-      } else if (mlen == 0) {  // fast.cpp:79-88: whole-word UNK, earlier pieces rolled back
-        put(word_first, V.unk_id);
-        nid = word_first + 1;
-        done = true;
       } else {
-        put(nid, mid);
-        nid++;
+        t0 = last_id;
         p += mlen;
-        kind = WP_KIND_SUFFIX;
-      }
-      if (done || p >= seg_len) {
-        // result form of the entry (read by K3): up to three ids inline — one 16-byte store and nothing
-        // else for most segments — else the count and where the ids sit in the id scratch
-        uint4 res;
-        if (nid <= 3) {
-          res = make_uint4(nid | SLOW_RESULT_INLINE, static_cast<uint32_t>(t0), static_cast<uint32_t>(t1),
-                           static_cast<uint32_t>(t2));
+        if (mlen == first_len) {
+          word_first = 1;  // fast.cpp:89-91: the next position follows a spacing char => new word
         } else {
-          out[0] = t0;
-          out[1] = t1;
-          out[2] = t2;
-          res = make_uint4(nid, tok_off, 0u, 0u);
-        }
-        *reinterpret_cast<uint4 *>(&P.slow[ent_index]) = res;
-        P.seg_result[my_text[LANE_TEXT_WORDS - 1]] =
-            SEG_RESULT_SLOW | (min(nid, SEG_SLOW_COUNT_MAX) << SEG_SLOW_INDEX_BITS) | ent_index;
-        have = false;
-        if (memo_on && in_smem && seg_len <= MEMO_KEY_BYTES && nid <= 3) {
-          // record bytes -> ids in the word memo so that K1 settles every later occurrence itself
-          const uint4 ma = key_mask[KEY_MASK_ROW * seg_len];
-          const uint32_t k0 = my_text[0] & ma.x, k1 = my_text[1] & ma.y, k2 = my_text[2] & ma.z, k3 = my_text[3] & ma.w;
-          uint32_t idx = key_hash(k0, k1, k2, k3, seg_len, MEMO_SALT) & P.memo_mask;
-          bool placed = false;
-          for (int t = 0; t < 4 && !placed; t++) {
-            uint4 *slot = P.memo + 2 * static_cast<size_t>(idx);
-            unsigned int *state = reinterpret_cast<unsigned int *>(slot + 1);
-            const unsigned int old = atomicCAS(state, 0u, 1u);
-            if (old == 0u) {
-              // claimed.  No fence between the payload and READY: the readers that need a complete slot (K1
-              // and K3) run in later kernels; a concurrent K2 lane that sees READY early can at worst fail to
-              // recognise its own word here and store a harmless duplicate one slot further.
-              slot[0] = make_uint4(k0, k1, k2, k3);
-              state[1] = static_cast<unsigned int>(t0);
-              state[2] = static_cast<unsigned int>(t1);
-              state[3] = static_cast<unsigned int>(t2);
-              *reinterpret_cast<volatile unsigned int *>(state) = MEMO_READY | (nid << 8) | seg_len;
-              placed = true;
-            } else if (old == 1u) {
-              placed = true;  // another lane is writing this slot right now (most likely the same word)
-            } else if ((old & 0xFFu) == seg_len) {
-              const uint4 a = __ldcg(slot);
-              if (a.x == k0 && a.y == k1 && a.z == k2 && a.w == k3) placed = true;  // already there
-            }
-            idx = (idx + 1) & P.memo_mask;
-          }
-          if (!placed) memo_on = false;  // crowded neighbourhood: this lane stops feeding the memo
+          kind = WP_KIND_SUFFIX;
         }
       }
+    } else if (mlen == 0) {  // fast.cpp:79-88: whole-word UNK, earlier pieces rolled back
+      put(word_first, V.unk_id);
+      nid = word_first + 1;
+      done = true;
+    } else {
+      put(nid, last_id);
+      nid++;
+      p += mlen;
+      kind = WP_KIND_SUFFIX;
+    }
+    if (!done && p < seg_len) {
+      d = 0;
+      last_d = 0;
+      node = kind;
+      ext = true;
+      continue;
+    }
+
+    // -- the segment is finished.  Result form of the entry (read by K3): up to three ids inline — one 16-byte
+    // store and nothing else for most segments — else the count and where the ids sit in the arena
+    uint4 res;
+    if (nid <= 3) {
+      res = make_uint4(nid | SLOW_RESULT_INLINE, static_cast<uint32_t>(t0), static_cast<uint32_t>(t1),
+                       static_cast<uint32_t>(t2));
+    } else {
+      out[0] = t0;
+      out[1] = t1;
+      out[2] = t2;
+      res = make_uint4(nid, area, 0u, 0u);
+    }
+    *reinterpret_cast<uint4 *>(&P.slow[ent_index]) = res;
+    P.seg_result[seg] = SEG_RESULT_SLOW | (min(nid, SEG_SLOW_COUNT_MAX) << SEG_SLOW_INDEX_BITS) | ent_index;
+    have = false;
+    if (record && seg_len <= WORD_KEY_BYTES && nid <= WORD_MAX_IDS) {
+      // record bytes -> ids in the word table so that K1 settles every later occurrence itself
+      const uint32_t *tw = P.arena + area + seg_len;
+      const uint32_t k0 = tw[0], k1 = seg_len > 4 ? tw[1] : 0u, k2 = seg_len > 8 ? tw[2] : 0u, k3 = seg_len > 12 ? tw[3] : 0u;
+      uint32_t idx = word_hash(k0, k1, k2, k3, seg_len, P.word_shift);
+      bool placed = false;
+      for (uint32_t t = 0; t < WORD_PROBES && !placed; t++) {
+        WordSlot *slot = P.words + idx;
+        const unsigned int old = atomicCAS(&slot->meta, 0u, WORD_CLAIMED);
+        if (old == 0u) {
+          // claimed.  The readers that need a complete slot (K1 and K3) run in later kernels; a concurrent K2
+          // lane that meets the slot half written can at worst fail to recognise its own word and store a
+          // harmless duplicate one slot further.
+          *reinterpret_cast<uint4 *>(slot->key) = make_uint4(k0, k1, k2, k3);
+          slot->ids[0] = t0;
+          slot->ids[1] = t1;
+          slot->ids[2] = t2;
+          for (uint32_t q = 3; q < nid; q++) slot->ids[q] = __ldcg(out + q);
+          __threadfence();
+          *reinterpret_cast<volatile unsigned int *>(&slot->meta) = word_meta(seg_len, nid, true);
+          placed = true;
+        } else if (old == WORD_CLAIMED) {
+          placed = true;  // another lane is writing this slot right now (most likely the same word)
+        } else if (word_meta_len(old) == seg_len) {
+          const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(slot->key));
+          if (a.x == k0 && a.y == k1 && a.z == k2 && a.w == k3) placed = true;  // already there
+        }
+        idx = (idx + 1) & P.word_mask;
+      }
+      if (!placed) record = false;  // crowded neighbourhood: this lane stops feeding the table
+    }
+  }
+}
+
+// ========================================================= K2L: long segments
+//
+// A segment that leaves its tile's window (or is longer than LONG_SEGMENT_BYTES) may be arbitrarily long — a
+// URL, a base64 blob, a whole text without a space (the reference's own stress shape, tests/tests.cpp:259-272,
+// is ONE word of 10 MB) — so it is not walked by one lane.  One CTA per segment:
+//   end    : the segment ends at the first spacing char after its start; found by a parallel scan;
+//   head   : the first piece (word-initial map; Han-led segments: fast.cpp:85-91) by one thread;
+//   rounds of LONG_BLOCK raw bytes:
+//     A  every thread takes positions of the block: is it a valid ordinary-char lead, and if so the longest
+//        "##" match that starts there (all positions in parallel — only those on the greedy chain are used);
+//     B  one thread follows the chain through the block (position -> position behind its match), staging
+//        the ids; a position without a match turns the whole word into UNK (fast.cpp:79-88);
+//     C  the staged ids go to the arena, coalesced.
+constexpr int LONG_THREADS = 128;
+constexpr int LONG_BLOCK = 1024;
+
+struct LongSmem {
+  uint32_t delta[LONG_BLOCK];  // raw bytes from a piece start to the position behind its longest match (0 = none)
+  int32_t id[LONG_BLOCK];
+  int32_t stage[LONG_BLOCK];
+  uint8_t code[LONG_BLOCK];    // 0 = dropped / continuation byte, 1 = lead of an ordinary char
+  unsigned long long seg_end;  // raw position of the spacing char that ends the segment (or the text size)
+  unsigned long long cur;      // raw position of the next piece
+  uint32_t entry;              // index into the long list
+  uint32_t n_stage, n_out, word_first, off, finished, failed;
+};
+
+__global__ void __launch_bounds__(LONG_THREADS) wp_long_kernel(EncodeParams P) {
+  __shared__ LongSmem sm;
+  const int tid = threadIdx.x;
+  const DeviceVocab &V = P.vocab;
+  const TextView tv{P.text, P.n_bytes};
+  if (P.call->overflow) return;
+  const uint32_t n_long = min(P.counters->n_long, P.long_capacity);
+  const uint32_t spill_base = min(P.counters->arena_reserved, P.arena_capacity);
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sm.entry = atomicAdd(&P.counters->long_ticket, 1u);
+    __syncthreads();
+    if (sm.entry >= n_long) break;
+    const uint32_t si = P.long_list[sm.entry];
+    const SlowEntry ent = P.slow[si];
+    const size_t start = static_cast<size_t>(ent.pos_lo) | (static_cast<size_t>(ent.meta >> 24) << 32);
+    uint32_t len0, cls0;
+    gnext(tv, start, &len0, &cls0);  // the start is a valid lead of a non-space class
+    if (tid == 0) {
+      sm.seg_end = tv.n;
+      sm.n_stage = 0;
+      sm.n_out = 0;
+      sm.word_first = 0;
+      sm.finished = 0;
+      sm.failed = 0;
+    }
+    __syncthreads();
+
+    // ---- end: the first valid spacing char behind the first char
+    for (size_t base = start + len0; base < tv.n; base += 8 * LONG_THREADS) {
+      unsigned long long found = ~0ull;
+#pragma unroll 1
+      for (int j = 0; j < 8; j++) {
+        const size_t q = base + static_cast<size_t>(j) * LONG_THREADS + tid;
+        if (q >= tv.n) break;
+        const uint32_t b0 = tv.t[q];
+        if (is_cont_byte(b0) || (b0 < 0x80u && cp_class(b0) == CLS_OTHER)) continue;
+        uint32_t cls;
+        if (gdecode(tv, q, &cls) && cls != CLS_OTHER) {
+          found = q;
+          break;
+        }
+      }
+      if (found != ~0ull) atomicMin(&sm.seg_end, found);
+      __syncthreads();
+      const bool stop = sm.seg_end < base + 8 * LONG_THREADS;
+      __syncthreads();
+      if (stop) break;
+    }
+    const size_t seg_end = static_cast<size_t>(sm.seg_end);
+
+    // ---- head (one thread): reserve the id area, match the first piece (and the one behind a lone Han char)
+    if (tid == 0) {
+      const unsigned long long want = seg_end - start;  // ids <= chars <= bytes
+      const unsigned long long off = static_cast<unsigned long long>(spill_base) +
+                                     atomicAdd(&P.counters->arena_spill, static_cast<unsigned int>(min(want, 0xFFFFFFFFull)));
+      if (off + want > P.arena_capacity) {
+        P.call->overflow = 1u;
+        sm.finished = 1;
+        sm.off = 0;
+      } else {
+        sm.off = static_cast<uint32_t>(off);
+        int32_t *out = reinterpret_cast<int32_t *>(P.arena + off);
+        const TextView seg{P.text, seg_end};  // windows never reach past the segment
+        int32_t id = 0;
+        size_t cur = longest_match_global(V, seg, start, WP_KIND_PREFIX, &id);
+        bool need_prefix = false;  // the next piece starts a fresh word (behind a lone Han char)
+        if (cls0 == CLS_HAN) {
+          if (cur == start) {
+            out[0] = V.unk_id;
+            if (V.han_swallow) {
+              sm.finished = 1;  // fast.cpp:85-88: begin += word_len swallows the run
+            } else {
+              cur = start + len0;
+              need_prefix = true;
+            }
+          } else {
+            out[0] = id;
+            need_prefix = cur == start + len0;  // fast.cpp:89-91: the next position follows a spacing char
+          }
+          sm.n_out = 1;
+          if (need_prefix) sm.word_first = 1;
+        } else if (cur == start) {  // fast.cpp:79-88
+          out[0] = V.unk_id;
+          sm.n_out = 1;
+          sm.finished = 1;
+        } else {
+          out[0] = id;
+          sm.n_out = 1;
+        }
+        if (!sm.finished && need_prefix) {
+          uint32_t l, c;
+          const size_t q = gnext(seg, cur, &l, &c);
+          if (q >= seg_end) {
+            sm.finished = 1;
+          } else {
+            cur = longest_match_global(V, seg, q, WP_KIND_PREFIX, &id);
+            if (cur == q) {
+              out[1] = V.unk_id;
+              sm.finished = 1;
+            } else {
+              out[1] = id;
+            }
+            sm.n_out = 2;
+          }
+        }
+        sm.cur = cur;
+      }
+    }
+    __syncthreads();
+
+    // ---- rounds
+    const TextView seg{P.text, seg_end};
+    while (!sm.finished) {
+      const size_t b0 = static_cast<size_t>(sm.cur);
+      if (b0 >= seg_end) break;
+      const size_t b1 = min(seg_end, b0 + LONG_BLOCK);
+      // A: every position of the block
+#pragma unroll 1
+      for (size_t q = b0 + tid; q < b1; q += LONG_THREADS) {
+        uint32_t cls, code = 0, delta = 0;
+        int32_t id = 0;
+        const uint32_t b = tv.t[q];
+        if (!is_cont_byte(b) && gdecode(seg, q, &cls)) {  // (no spacing char before seg_end)
+          code = 1;
+          delta = static_cast<uint32_t>(longest_match_global(V, seg, q, WP_KIND_SUFFIX, &id) - q);
+        }
+        sm.code[q - b0] = static_cast<uint8_t>(code);
+        sm.delta[q - b0] = delta;
+        sm.id[q - b0] = id;
+      }
+      __syncthreads();
+      // B: the greedy chain through the block
+      if (tid == 0) {
+        size_t cur = b0;
+        uint32_t n = 0;
+        while (cur < b1) {
+          const uint32_t i = static_cast<uint32_t>(cur - b0);
+          if (sm.code[i] == 0) {
+            cur++;
+            continue;
+          }
+          const uint32_t dl = sm.delta[i];
+          if (dl == 0) {
+            sm.failed = 1;
+            break;
+          }
+          sm.stage[n++] = sm.id[i];
+          cur += dl;
+        }
+        sm.n_stage = n;
+        sm.cur = cur;
+        if (sm.failed || cur >= seg_end) sm.finished = 1;
+      }
+      __syncthreads();
+      // C: staged ids -> arena
+      if (!sm.failed) {
+        int32_t *out = reinterpret_cast<int32_t *>(P.arena + sm.off) + sm.n_out;
+        for (uint32_t i = tid; i < sm.n_stage; i += LONG_THREADS) out[i] = sm.stage[i];
+      }
+      __syncthreads();
+      if (tid == 0) sm.n_out += sm.n_stage;
+      __syncthreads();
+    }
+    if (tid == 0) {
+      uint32_t cnt = sm.n_out;
+      if (sm.failed) {  // fast.cpp:79-88: the word's pieces are rolled back, one UNK stands for it
+        cnt = sm.word_first + 1;
+        P.arena[sm.off + sm.word_first] = static_cast<uint32_t>(V.unk_id);
+      }
+      if (P.call->overflow) cnt = 0;
+      *reinterpret_cast<uint4 *>(&P.slow[si]) = make_uint4(cnt, sm.off, 0u, 0u);  // result form, not inline
+      P.seg_result[ent.seg] = SEG_RESULT_SLOW | (min(cnt, SEG_SLOW_COUNT_MAX) << SEG_SLOW_INDEX_BITS) | si;
     }
   }
 }
@@ -1591,8 +1388,8 @@ struct ScatterSmem {
   unsigned long long base;
 };
 
-// ids of one segment that K1 did not settle -> dst[0..cnt): from the memo slot, inline in the slow entry, or
-// from the id scratch
+// ids of one segment that K1 did not settle with a single id -> dst[0..cnt): inline in the slow entry, from
+// the arena, or from the word-table slot
 __device__ __forceinline__ void scatter_fetch(const EncodeParams &P, uint32_t res, uint32_t cnt, int32_t *dst) {
   if (res & SEG_RESULT_SLOW) {
     const uint32_t si = res & SEG_SLOW_INDEX_MASK;
@@ -1602,15 +1399,17 @@ __device__ __forceinline__ void scatter_fetch(const EncodeParams &P, uint32_t re
       dst[0] = static_cast<int32_t>(e.y);
       if (cnt > 1) dst[1] = static_cast<int32_t>(e.z);
       if (cnt > 2) dst[2] = static_cast<int32_t>(e.w);
-    } else if (static_cast<unsigned long long>(e.y) + cnt <= P.tok_capacity) {
-      const int32_t *src = P.tok + e.y;
+    } else if (static_cast<unsigned long long>(e.y) + cnt <= P.arena_capacity) {
+      const int32_t *src = reinterpret_cast<const int32_t *>(P.arena + e.y);
       for (uint32_t t = 0; t < cnt; t++) dst[t] = src[t];
     }
   } else {
-    const uint4 e = *reinterpret_cast<const uint4 *>(P.memo + 2 * static_cast<size_t>(res & SEG_MEMO_SLOT_MASK) + 1);
+    const WordSlot *slot = P.words + (res & SEG_WORD_SLOT_MASK);
+    const uint4 e = *reinterpret_cast<const uint4 *>(&slot->meta);  // {meta, id0, id1, id2}
     dst[0] = static_cast<int32_t>(e.y);
     if (cnt > 1) dst[1] = static_cast<int32_t>(e.z);
     if (cnt > 2) dst[2] = static_cast<int32_t>(e.w);
+    for (uint32_t t = 3; t < cnt; t++) dst[t] = slot->ids[t];
   }
 }
 
@@ -1661,12 +1460,12 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
 #pragma unroll
     for (int j = 0; j < SCATTER_ITEMS; j++) {
       const uint32_t slow_cnt = (res[j] >> SEG_SLOW_INDEX_BITS) & SEG_SLOW_COUNT_MAX;
-      const uint32_t memo_cnt = (res[j] >> SEG_MEMO_SLOT_BITS) & 3u;
-      uint32_t c = (res[j] & SEG_RESULT_SLOW) ? slow_cnt : ((res[j] & SEG_RESULT_MEMO) ? memo_cnt : 1u);
+      const uint32_t word_cnt = (res[j] >> SEG_WORD_SLOT_BITS) & 0xFu;
+      uint32_t c = (res[j] & SEG_RESULT_SLOW) ? slow_cnt : ((res[j] & SEG_RESULT_WORD) ? word_cnt : 1u);
       if (first + j >= n_segs) c = 0;
       if ((res[j] & SEG_RESULT_SLOW) && slow_cnt == SEG_SLOW_COUNT_MAX && c != 0) {  // rare: 31 ids or more
         const uint32_t si = res[j] & SEG_SLOW_INDEX_MASK;
-        c = si < P.slow_capacity ? (P.slow[si].pos_lo & ~SLOW_RESULT_INLINE) : 0u;  // word 0 of the result form
+        c = si < P.slow_capacity ? (P.slow[si].off & ~SLOW_RESULT_INLINE) : 0u;  // word 0 of the result form
       }
       cnt[j] = c;
       mine += c;
@@ -1682,7 +1481,7 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
       // lanes of a warp idle behind the few that have one).
 #pragma unroll
       for (int j = 0; j < SCATTER_ITEMS; j++) {
-        const bool other = (res[j] & (SEG_RESULT_SLOW | SEG_RESULT_MEMO)) != 0 && cnt[j] != 0;
+        const bool other = (res[j] & (SEG_RESULT_SLOW | SEG_RESULT_WORD)) != 0 && cnt[j] != 0;
         if (cnt[j] != 0 && !other) sm.stage[at] = static_cast<int32_t>(res[j]) - 1;
         const uint32_t om = __ballot_sync(FULL, other);
         if (om) {
@@ -1731,25 +1530,25 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
       for (int j = 0; j < SCATTER_ITEMS; j++) {
         if (cnt[j] == 0) continue;
         const unsigned long long o = out0 + at;
-        if (!(res[j] & (SEG_RESULT_SLOW | SEG_RESULT_MEMO))) {
+        if (!(res[j] & (SEG_RESULT_SLOW | SEG_RESULT_WORD))) {
           if (o < P.capacity) P.ids[o] = static_cast<int32_t>(res[j]) - 1;
         } else if (o + cnt[j] <= P.capacity) {
           scatter_fetch(P, res[j], cnt[j], P.ids + o);
         } else {
           // the caller's buffer ends inside this segment (the call reports WP_ERR_CAPACITY): id by id
-          int32_t tmp[3];
-          if (cnt[j] <= 3) {
+          int32_t tmp[WORD_MAX_IDS];
+          if (cnt[j] <= WORD_MAX_IDS) {
             scatter_fetch(P, res[j], cnt[j], tmp);
             for (uint32_t t = 0; t < cnt[j]; t++) {
               if (o + t < P.capacity) P.ids[o + t] = tmp[t];
             }
-          } else {
+          } else {  // more ids than a word slot holds: a slow entry with its ids in the arena
             const uint32_t si = res[j] & SEG_SLOW_INDEX_MASK;
             if (si < P.slow_capacity) {
               const uint4 e = *reinterpret_cast<const uint4 *>(&P.slow[si]);
-              if (static_cast<unsigned long long>(e.y) + cnt[j] <= P.tok_capacity) {
+              if (static_cast<unsigned long long>(e.y) + cnt[j] <= P.arena_capacity) {
                 for (uint32_t t = 0; t < cnt[j]; t++) {
-                  if (o + t < P.capacity) P.ids[o + t] = P.tok[e.y + t];
+                  if (o + t < P.capacity) P.ids[o + t] = static_cast<int32_t>(P.arena[e.y + t]);
                 }
               }
             }
@@ -1880,6 +1679,34 @@ cudaError_t launch_format(const int32_t *ids, size_t n, char *out, unsigned long
 
 uint32_t format_block_ids() { return FORMAT_IDS; }
 
+// ------------------------------------------------------------ word-table seed
+// Every encode call that records words starts from a working table that holds exactly the static words.
+__global__ void wp_seed_words_kernel(const WordSlot *__restrict__ image, uint32_t image_slots, WordSlot *work,
+                                     uint32_t mask, uint32_t shift) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= image_slots) return;
+  const uint4 *src = reinterpret_cast<const uint4 *>(image + i);
+  const uint4 key = src[0], lo = src[1];
+  if (lo.x == 0) return;
+  uint32_t idx = word_hash(key.x, key.y, key.z, key.w, word_meta_len(lo.x), shift);
+  while (atomicCAS(&work[idx].meta, 0u, WORD_CLAIMED) != 0u) idx = (idx + 1) & mask;
+  uint4 *dst = reinterpret_cast<uint4 *>(work + idx);
+  dst[0] = key;
+  dst[2] = src[2];
+  dst[3] = src[3];
+  dst[1] = lo;  // meta last (no reader runs concurrently; the order only keeps CLAIMED until the slot is whole)
+}
+
+cudaError_t launch_seed_words(const WordSlot *image, uint32_t image_slots, WordSlot *work, uint32_t work_slots_log2,
+                              cudaStream_t stream, uint64_t *launches) {
+  cudaError_t e = cudaMemsetAsync(work, 0, (size_t(1) << work_slots_log2) * sizeof(WordSlot), stream);
+  if (e != cudaSuccess) return e;
+  wp_seed_words_kernel<<<(image_slots + 255) / 256, 256, 0, stream>>>(image, image_slots, work,
+                                                                      (1u << work_slots_log2) - 1u, 32 - work_slots_log2);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
 // -------------------------------------------------------------------- launch
 
 uint32_t encode_tile_bytes() { return TILE; }
@@ -1899,46 +1726,52 @@ cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   if (sm_count <= 0) sm_count = 148;
-  // K1 and K2 probe the vocabulary table at random: ask L2 to keep it resident while text, ids and the
-  // intermediates stream through (access policy window = the slot array, everything else streaming).
+  // K1 and K3 read the word table at random, K2 the edge table: ask L2 to keep the one a kernel uses resident
+  // while text, ids and the intermediates stream through (access policy window, everything else streaming).
   cudaLaunchAttribute attr[1];
-  unsigned n_attr = 0;
-  if (P.persist_bytes > 0) {
+  auto window = [&](const void *base, size_t bytes, float ratio) -> unsigned {
+    if (bytes == 0) return 0;
     attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-    attr[0].val.accessPolicyWindow.base_ptr = const_cast<Slot *>(P.vocab.slots);
-    attr[0].val.accessPolicyWindow.num_bytes = P.persist_bytes;
-    attr[0].val.accessPolicyWindow.hitRatio = P.persist_ratio;
+    attr[0].val.accessPolicyWindow.base_ptr = const_cast<void *>(base);
+    attr[0].val.accessPolicyWindow.num_bytes = bytes;
+    attr[0].val.accessPolicyWindow.hitRatio = ratio;
     attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    n_attr = 1;
-  }
+    return 1;
+  };
   cudaLaunchConfig_t cfg{};
   cfg.stream = stream;
   cfg.attrs = attr;
-  cfg.numAttrs = n_attr;
 
   if (timing) cudaEventRecord(timing[0], stream);
   cfg.gridDim = dim3(P.n_tiles);
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = sizeof(TileSmem);
+  cfg.numAttrs = window(P.words, P.persist_words_bytes, P.persist_words_ratio);
   e = cudaLaunchKernelEx(&cfg, wp_split_kernel, P);
   if (e != cudaSuccess) return e;
 
   if (timing) cudaEventRecord(timing[1], stream);
-  cfg.gridDim = dim3(sm_count * 3);  // = resident capacity (__launch_bounds__(256, 3)): one wave, large shares
+  cfg.gridDim = dim3(sm_count * 4);  // = resident capacity (__launch_bounds__(256, 4)): one wave, large shares
   cfg.blockDim = dim3(MATCH_THREADS);
   cfg.dynamicSmemBytes = 0;
+  cfg.numAttrs = window(P.vocab.edges, P.persist_edges_bytes, P.persist_edges_ratio);
   e = cudaLaunchKernelEx(&cfg, wp_match_kernel, P);
+  if (e != cudaSuccess) return e;
+
+  cfg.gridDim = dim3(sm_count * 8);
+  cfg.blockDim = dim3(LONG_THREADS);
+  e = cudaLaunchKernelEx(&cfg, wp_long_kernel, P);
   if (e != cudaSuccess) return e;
 
   if (timing) cudaEventRecord(timing[2], stream);
   cfg.gridDim = dim3(sm_count * 4);
   cfg.blockDim = dim3(SCATTER_THREADS);
-  cfg.numAttrs = 0;
+  cfg.numAttrs = window(P.words, P.persist_words_bytes, P.persist_words_ratio);
   e = cudaLaunchKernelEx(&cfg, wp_scatter_kernel, P);
   if (e != cudaSuccess) return e;
   if (timing) cudaEventRecord(timing[3], stream);
-  if (launches) *launches += 3;
+  if (launches) *launches += 4;
   return cudaSuccess;
 }
 

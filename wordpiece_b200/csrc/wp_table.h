@@ -1,25 +1,31 @@
-// Device vocabulary table layout, shared by the host builder (wp_vocab.cpp) and
-// the kernels (wp_encode.cu).
+// Device vocabulary tables, shared by the host builder (wp_vocab.cpp) and the
+// kernels (wp_encode.cu).
 //
 // The reference keeps two unordered_map<VectorSegment,int> (word-initial and
 // "##" continuation, fast.cpp:21-35) and finds the longest match by probing the
 // window longest -> shortest (fast.cpp:66-77), O(window) probes per piece.  The
 // dictionary semantics are exact (utf8.hpp:60-70), so any exact structure that
-// returns the same longest match yields the same ids.  Ours is a HASHED TRIE
-// over canonical UTF-8 bytes:
+// returns the same longest match yields the same ids.  Two structures here,
+// both over canonical UTF-8 BYTES:
 //
-//   * one open-addressed table of 32-byte slots (one L2 sector each); a slot is
-//     a NODE = one byte-prefix (length 1..WP_KEY_BYTES) of some kept token, of
-//     one kind (0 word-initial, 1 continuation), with its bytes stored INLINE so
-//     that a probe is verified exactly by the same load that found it;
-//   * node existence is monotone in the prefix length, so the deepest node along
-//     a window is found by binary search (O(log) probes, first probe = the whole
-//     window, which settles the common whole-word hit in one probe);
-//   * each node carries the id of the token ending exactly there (term_id) and
-//     the longest token that is a proper prefix of it (best_len/best_id), so the
-//     longest match is read off the deepest node;
-//   * tokens longer than WP_KEY_BYTES hang off their depth-WP_KEY_BYTES node as a
-//     list sorted by length (longest first) and are compared byte by byte.
+//   E  the EDGE TRIE (K2, the walker): every byte-prefix of a kept token is a
+//      node; an edge (parent node, byte) -> child node lives in one open-
+//      addressed table of 16-byte slots, hashed on the 32-bit word
+//      parent << 8 | byte.  The edge carries the id of the token that ends at
+//      the child (term_id), so a longest match is a descent that remembers the
+//      last terminal seen: one dependent 16-byte load per text byte, ~15
+//      instructions a step, no key material, no length limit (tokens of any
+//      length are just deeper paths).  Node 0 is the root of the word-initial
+//      map, node 1 the root of the "##" map.
+//
+//   W  the WORD TABLE (K1): whole segment bytes (<= 16) -> the segment's ids.
+//      Its STATIC part is built from the vocabulary: a segment whose bytes are
+//      exactly a word-initial token is that token (the longest candidate of
+//      fast.cpp:66-72 is the whole window) — ~80 % of English running words,
+//      one 32-byte load.  Its DYNAMIC part is filled per encode call by K2 with
+//      the words it had to match piece by piece (exact bytes -> exact ids, so a
+//      hit is the same ids the matcher would produce): text repeats its words,
+//      and every later occurrence is settled by K1's single lookup.
 #pragma once
 #include <stdint.h>
 
@@ -27,65 +33,60 @@
 
 namespace wp {
 
-constexpr uint32_t WP_KEY_BYTES = 22;        // inline key bytes per node
 constexpr int32_t WP_NO_ID = -2;             // "no token ends here" (ids are >= 0, UNK may be -1)
-constexpr uint32_t WP_KIND_PREFIX = 0;       // word-initial map (prefix_to_id)
-constexpr uint32_t WP_KIND_SUFFIX = 1;       // "##" map (suffix_to_id)
+constexpr uint32_t WP_KIND_PREFIX = 0;       // word-initial map (prefix_to_id); also the root node of that map
+constexpr uint32_t WP_KIND_SUFFIX = 1;       // "##" map (suffix_to_id); also its root node
 
-// Slot = 8 x u32:
-//   w[0..4]            key bytes 0..19 (little endian, zero padded)
-//   w[5] bits  0..15   key bytes 20..21
-//        bits 16..23   len (1..22; 0 = empty slot)
-//        bit  24       kind
-//        bit  25       has_long (len == 22 and longer tokens share this prefix)
-//        bits 26..30   best_len (0 = none; < len)
-//   w[6]               term_id  (WP_NO_ID if no token ends at this node)
-//   w[7]               best_id  (valid if best_len != 0)
-struct Slot {
-  uint32_t w[8];
+// ------------------------------------------------------------------ edge trie
+struct Edge {
+  uint32_t key;      // parent << 8 | byte; EDGE_EMPTY = free slot
+  uint32_t child;    // node reached
+  int32_t term_id;   // token that ends at the child (WP_NO_ID if none); duplicates: last index wins (fast.cpp:34)
+  uint32_t flags;    // bit 0: the child has children (a descent that reaches a leaf stops without another probe)
 };
-static_assert(sizeof(Slot) == 32, "slot must be one 32-byte sector");
+static_assert(sizeof(Edge) == 16, "an edge is one 16-byte load");
+constexpr uint32_t EDGE_EMPTY = 0xFFFFFFFFu;
+constexpr uint32_t EDGE_HAS_CHILDREN = 1u;
+constexpr uint32_t EDGE_MAX_NODES = 1u << 24;
 
-constexpr uint32_t WP_W5_KEYMASK = 0x01FFFFFFu;  // key bytes 20..21, len, kind
+WP_HD uint32_t edge_key(uint32_t parent, uint32_t byte) { return (parent << 8) | byte; }
+// Multiplicative hash, index from the HIGH bits (shift = 32 - log2(slots)).
+WP_HD uint32_t edge_hash(uint32_t key, uint32_t shift) { return (key * 0x9E3779B1u) >> shift; }
 
-WP_HD uint32_t slot_len(uint32_t w5) { return (w5 >> 16) & 0xFFu; }
-WP_HD uint32_t slot_has_long(uint32_t w5) { return (w5 >> 25) & 1u; }
-WP_HD uint32_t slot_best_len(uint32_t w5) { return (w5 >> 26) & 0x1Fu; }
-WP_HD uint32_t make_w5(uint32_t bytes2021, uint32_t len, uint32_t kind) {
-  return (bytes2021 & 0xFFFFu) | (len << 16) | (kind << 24);
+// ----------------------------------------------------------------- word table
+constexpr uint32_t WORD_KEY_BYTES = 16;
+constexpr uint32_t WORD_MAX_IDS = 11;
+struct WordSlot {
+  uint32_t key[4];   // the segment's bytes, zero padded
+  uint32_t meta;     // 0 = empty, WORD_CLAIMED = being written, else WORD_READY | flags | count << 8 | byte length
+  int32_t ids[WORD_MAX_IDS];
+};
+static_assert(sizeof(WordSlot) == 64, "a word slot is two 32-byte sectors; K1 reads only the first");
+constexpr uint32_t WORD_CLAIMED = 1u;
+constexpr uint32_t WORD_READY = 0x80000000u;
+constexpr uint32_t WORD_DYNAMIC = 0x40000000u;   // recorded by K2 during this call (statistics only)
+WP_HD uint32_t word_meta_len(uint32_t meta) { return meta & 0x1Fu; }
+WP_HD uint32_t word_meta_count(uint32_t meta) { return (meta >> 8) & 0xFu; }
+WP_HD uint32_t word_meta(uint32_t len, uint32_t count, bool dynamic) {
+  return WORD_READY | (dynamic ? WORD_DYNAMIC : 0u) | (count << 8) | len;
 }
-
-// Hash of the six key words (w[5] already reduced to WP_W5_KEYMASK bits).  Multiply-xor: the six products
-// are independent (they issue back to back on the GPU), then one xor-shift-multiply finaliser; the table
-// index is taken from the low bits, so the finaliser folds the high halves down.
-WP_HD uint32_t key_hash(uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3, uint32_t k4, uint32_t k5) {
-  uint32_t h = (k0 * 0x9E3779B1u) ^ (k1 * 0x85EBCA77u) ^ (k2 * 0xC2B2AE3Du) ^ (k3 * 0x27D4EB2Fu) ^ (k4 * 0x165667B1u) ^
-               ((k5 + 0x7F4A7C15u) * 0xD6E8FEB9u);
+// Multiply-add over the four key words and the length (five IMADs), one fold, index from the high bits.
+WP_HD uint32_t word_hash(uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3, uint32_t len, uint32_t shift) {
+  uint32_t h = k0 * 0x9E3779B1u + k1 * 0x85EBCA77u + k2 * 0xC2B2AE3Du + k3 * 0x27D4EB2Fu + len * 0x165667B1u;
   h ^= h >> 15;
-  h *= 0x2C1B3C6Du;
-  h ^= h >> 13;
-  h *= 0x297A2D39u;
-  h ^= h >> 16;
-  return h;
+  return (h * 0x2C1B3C6Du) >> shift;
 }
-
-// One entry of a long-token list (tokens with more than WP_KEY_BYTES bytes).
-struct LongEntry {
-  uint32_t len;       // byte length of the token
-  int32_t id;         // token id
-  uint32_t byte_off;  // offset of the token's canonical bytes in the byte pool
-};
+// A K1 lookup looks at this many consecutive slots before it gives up and leaves the segment to K2 (a
+// single-char segment, which K2 never sees, follows the probe sequence to its end instead — rare).
+constexpr uint32_t WORD_PROBES = 4;
 
 // Everything a kernel needs to know about a vocabulary (device pointers).
 struct DeviceVocab {
-  const Slot *slots;            // n_slots entries, n_slots a power of two
-  uint32_t slot_mask;           // n_slots - 1
-  const uint32_t *long_ref;     // per slot: index into long_entries of {count, entries...}; only for has_long slots
-  const uint32_t *long_entries; // [count, (len,id,byte_off) x count] groups
-  const uint8_t *long_bytes;    // byte pool of long tokens
+  const Edge *edges;            // n_edge_slots entries, a power of two
+  uint32_t edge_mask;           // n_edge_slots - 1
+  uint32_t edge_shift;          // 32 - log2(n_edge_slots)
   int32_t unk_id;               // utils.hpp:30 / utils.cpp:112-114
   uint32_t han_swallow;         // 1 iff max_len >= 2 (an OOV Han char swallows the following run)
-  uint32_t probe_pairs;         // K2 looks at two slots per probe (pays while the table is L2-resident: <= 16 MiB)
 };
 
 }  // namespace wp

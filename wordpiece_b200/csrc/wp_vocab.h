@@ -1,5 +1,5 @@
 // Host-side vocabulary: token classification with the reference's rules and
-// the hashed-trie table the kernels probe (layout in wp_table.h).
+// the two device tables the kernels use (layout in wp_table.h).
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -24,24 +24,26 @@ struct HostVocab {
   int32_t unk_id = -1;  // utils.hpp:30
   size_t max_len = 0;   // code points, over non-special non-malformed tokens (fast.cpp:31)
 
-  // device table image
-  std::vector<Slot> slots;  // power-of-two size
-  std::vector<uint32_t> long_ref;
-  std::vector<uint32_t> long_entries;
-  std::vector<uint8_t> long_bytes;
-  size_t n_nodes = 0;
-  size_t n_long = 0;
+  // device table images
+  std::vector<Edge> edges;      // power-of-two size
+  std::vector<WordSlot> words;  // power-of-two size >= 4 x static words: the static word table
+  size_t n_nodes = 0;           // trie nodes (both roots included)
+  size_t n_static_words = 0;    // word-initial tokens of at most WORD_KEY_BYTES bytes
+  size_t n_long = 0;            // kept tokens longer than WORD_KEY_BYTES bytes (statistics)
 };
 
 // Returns false (and sets *err) where the reference throws "Vocab word is empty".
 bool build_host_vocab(const char *const *tokens, const size_t *lens, size_t n, HostVocab *out, std::string *err);
 
-// Host mirror of the device longest-match query, used by unit tests of the table
-// (wp_selftest) — NOT a fallback: nothing on the encode path calls it.
+// Host mirrors of the device queries, used by unit tests of the table images — NOT a fallback: nothing on
+// the encode path calls them.
 struct MatchResult {
   uint32_t len;  // bytes matched, 0 = miss
   int32_t id;
 };
+// longest token of `kind` that is a prefix of text[0, window_bytes)
 MatchResult host_longest_match(const HostVocab &v, const uint8_t *text, size_t window_bytes, uint32_t kind);
+// whole-segment lookup in the static word table: id count (0 = absent), ids[0..count)
+uint32_t host_word_lookup(const HostVocab &v, const uint8_t *text, size_t len, int32_t *ids, uint32_t *slot_out);
 
 }  // namespace wp

@@ -1,62 +1,54 @@
-"""Byte-range sharding of a text across GPUs (BASELINE.json configs[3]).
+"""Byte-range sharding of a text across GPUs (BASELINE.json configs[3]) — thin ctypes layer.
 
-The encode path shards with no exchange step: the reference's serial state is
-reset at every ``is_space`` code point (fast.cpp:89-91, and its own chunking cuts
-there, fast.cpp:113-115), so contiguous byte ranges whose cuts sit right after a
-space byte sequence are encoded independently and the id arrays concatenated.
-Global id offsets are an exclusive scan over the per-shard id counts.
+The logic lives in the C ABI (``wp_plan_shards``, ``wp_encode_sharded[_gather]``,
+csrc/wp_capi.cu): the encode path shards with no exchange step — the reference's
+serial state is reset at every ``is_space`` code point (fast.cpp:89-91, and its own
+chunking cuts there, fast.cpp:113-115) — so contiguous byte ranges cut at safe
+starts are encoded independently and the id arrays concatenated.  Global id offsets
+are an exclusive scan over the per-shard id counts.
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-_ASCII_SPACES = (0x09, 0x0A, 0x0B, 0x0C, 0x0D, 0x20)
+from ._capi import Vocab, _buffer_address, _check, load_library
 
 
-def _is_space_at(text: np.ndarray, i: int) -> int:
-    """Length of the reference ``is_space`` byte sequence starting at i (0 if none): utf8.cpp:10-12."""
-    b = int(text[i])
-    if b in _ASCII_SPACES:
-        return 1
-    if b == 0xE2 and i + 2 < text.size and int(text[i + 1]) == 0x96 and int(text[i + 2]) == 0x81:
-        return 3  # U+2581
-    return 0
+class _ShardStruct(C.Structure):
+    _fields_ = [("begin", C.c_size_t), ("end", C.c_size_t), ("n_ids", C.c_uint64), ("id_offset", C.c_uint64),
+                ("device", C.c_int), ("encode_ms", C.c_float)]
 
 
-def plan_shards(text: np.ndarray, n_shards: int, search_limit: int = 1 << 26) -> List[Tuple[int, int]]:
-    """Split ``text`` (uint8 array) into ``n_shards`` contiguous ranges of near-equal size.
+@dataclass
+class Shard:
+    begin: int
+    end: int
+    n_ids: int
+    id_offset: int
+    device: int
+    encode_ms: float
 
-    Each cut is moved forward to just after the next space byte sequence.  If no
-    space occurs within ``search_limit`` bytes (space-free CJK corpora) the cut is
-    moved to the start of the next ASCII punctuation byte instead, which is also a
-    safe start.  Ranges may be empty when the text is tiny.
-    """
-    n = int(text.size)
-    cuts = [0]
-    for k in range(1, n_shards):
-        pos = max(cuts[-1], (n * k) // n_shards)
-        end = min(n, pos + search_limit)
-        cut = None
-        i = pos
-        while i < end:
-            ln = _is_space_at(text, i)
-            if ln:
-                cut = i + ln
-                break
-            i += 1
-        if cut is None:
-            i = pos
-            while i < end:
-                b = int(text[i])
-                if b < 0x80 and (0x21 <= b <= 0x2F or 0x3A <= b <= 0x40 or 0x5B <= b <= 0x60 or 0x7B <= b <= 0x7E):
-                    cut = i
-                    break
-                i += 1
-        cuts.append(n if cut is None else cut)
-    cuts.append(n)
-    return [(cuts[i], cuts[i + 1]) for i in range(n_shards)]
+
+def plan_shards(text, n_shards: int) -> List[int]:
+    """``wp_plan_shards``: the ``n_shards + 1`` cut offsets (first 0, last len) of near-equal shards, each cut
+    moved forward to the next safe cut (after a space; for space-free CJK text at punctuation / Han chars)."""
+    L = load_library()
+    addr, n, keep = _buffer_address(text)
+    cuts = (C.c_size_t * (n_shards + 1))()
+    got = int(L.wp_plan_shards(addr, n, n_shards, cuts))
+    del keep
+    if got != n_shards + 1:
+        raise ValueError("wp_plan_shards: bad arguments")
+    return [int(c) for c in cuts]
+
+
+def shard_ranges(text, n_shards: int) -> List[Tuple[int, int]]:
+    cuts = plan_shards(text, n_shards)
+    return list(zip(cuts[:-1], cuts[1:]))
 
 
 def global_offsets(counts: Sequence[int]) -> List[int]:
@@ -66,3 +58,34 @@ def global_offsets(counts: Sequence[int]) -> List[int]:
         out.append(run)
         run += int(c)
     return out
+
+
+def _handles(vocabs: Sequence[Vocab]):
+    return (C.c_void_p * len(vocabs))(*[v._h for v in vocabs])
+
+
+def encode_sharded(vocabs: Sequence[Vocab], text, out: np.ndarray) -> Tuple[int, List[Shard]]:
+    """``wp_encode_sharded``: host text -> host ids over ``len(vocabs)`` GPUs (one handle per device)."""
+    assert out.dtype == np.int32 and out.flags.c_contiguous
+    L = load_library()
+    addr, n, keep = _buffer_address(text)
+    cnt = C.c_size_t()
+    sh = (_ShardStruct * len(vocabs))()
+    _check(L.wp_encode_sharded(_handles(vocabs), len(vocabs), addr, n, out.ctypes.data, out.size, C.byref(cnt), sh))
+    del keep
+    return int(cnt.value), [Shard(s.begin, s.end, s.n_ids, s.id_offset, s.device, s.encode_ms) for s in sh]
+
+
+def encode_sharded_gather(vocabs: Sequence[Vocab], text, d_ids, gather_index: int = 0):
+    """``wp_encode_sharded_gather``: ids gathered peer-to-peer into the int32 CUDA tensor ``d_ids`` on the device
+    of ``vocabs[gather_index]``.  Returns (count, shards, gather_ms)."""
+    L = load_library()
+    addr, n, keep = _buffer_address(text)
+    cnt = C.c_size_t()
+    ms = C.c_float()
+    sh = (_ShardStruct * len(vocabs))()
+    _check(L.wp_encode_sharded_gather(_handles(vocabs), len(vocabs), addr, n, gather_index, d_ids.data_ptr(),
+                                      d_ids.numel(), C.byref(cnt), sh, C.byref(ms)))
+    del keep
+    return (int(cnt.value), [Shard(s.begin, s.end, s.n_ids, s.id_offset, s.device, s.encode_ms) for s in sh],
+            float(ms.value))

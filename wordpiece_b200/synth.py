@@ -406,3 +406,70 @@ def write_vocab_file(path: str, vocab: Sequence[bytes]) -> None:
     with open(path, "wb") as f:
         for t in vocab:
             f.write(t + b"\n")
+
+
+# --------------------------------------------------------------- derived shapes
+
+_B64 = np.frombuffer(b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789", dtype=np.uint8)
+_INVALID_BYTES = np.array([0xFF, 0xC0, 0x80, 0xFE, 0xF8, 0xBF, 0xC1, 0xE2], dtype=np.uint8)
+
+
+def dirty_web(clean: np.ndarray, seed: int, invalid_rate: float = 0.01, long_token_rate: float = 0.005,
+              long_min: int = 300, long_max: int = 4000) -> np.ndarray:
+    """"Ordinary dirty web text" of the same size as ``clean`` (an ASCII corpus): ``long_token_rate`` of the
+    tokens are space-free strings of ``long_min``..``long_max`` bytes (base64 blobs; a third of them URL-like,
+    with a '/' every 20-60 bytes), and ``invalid_rate`` of the bytes are overwritten with bytes that are
+    invalid UTF-8 where they stand (at 1 % every 4 KiB tile holds some)."""
+    rng = np.random.default_rng(seed)
+    n = clean.size
+    mean_tokens = 1.0 / max(long_token_rate, 1e-9)
+    parts, size, pos = [], 0, 0
+    while size < n:
+        take = int(rng.exponential(mean_tokens * 5.7)) + 1           # ~5.7 bytes per running token
+        end = min(n, pos + take)
+        while end < n and clean[end - 1] != 0x20:
+            end += 1
+        if end <= pos:
+            pos = 0
+            continue
+        parts.append(clean[pos:end])
+        size += end - pos
+        pos = end if end < n else 0
+        ln = int(rng.integers(long_min, long_max + 1))
+        blob = _B64[rng.integers(0, _B64.size, ln)]
+        if rng.random() < 0.33:
+            k = 0
+            while True:
+                k += int(rng.integers(20, 61))
+                if k >= ln:
+                    break
+                blob[k] = 0x2F
+        parts.append(blob)
+        parts.append(np.array([0x20], np.uint8))
+        size += ln + 1
+    out = np.concatenate(parts)[:n].copy()
+    k = int(n * invalid_rate)
+    if k:
+        at = rng.integers(0, n, k)
+        out[at] = _INVALID_BYTES[rng.integers(0, _INVALID_BYTES.size, k)]
+    return out
+
+
+def open_vocabulary(clean: np.ndarray, seed: int, hapax_rate: float = 0.03) -> np.ndarray:
+    """An ASCII corpus with an OPEN vocabulary: ``hapax_rate`` of the running words are replaced by strings
+    that occur only once (random alphanumerics of 3-14 chars: numbers, names, ids, typos), so that a cache
+    of matched words cannot have seen them.  Same size as ``clean``."""
+    rng = np.random.default_rng(seed)
+    n = clean.size
+    spaces = np.flatnonzero(clean == 0x20)
+    pick = spaces[rng.random(spaces.size) < hapax_rate]
+    out = clean.copy()
+    lens = rng.integers(3, 15, pick.size)
+    alnum = _B64
+    for p, ln in zip(pick.tolist(), lens.tolist()):
+        a = p + 1
+        b = min(n, a + ln)
+        if b < n:
+            out[a:b] = alnum[rng.integers(0, alnum.size, b - a)]
+            out[b] = 0x20
+    return out
