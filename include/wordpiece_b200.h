@@ -15,7 +15,9 @@
  * encode call runs the CUDA kernels or fails with WP_ERR_CUDA / WP_ERR_NO_DEVICE.
  *
  * Threading: a wp_vocab handle owns one CUDA stream and scratch buffers on one
- * device; use a handle from one host thread at a time (the reference is not
+ * device; use a handle from one host thread at a time, and let every encode call on
+ * it finish being ENQUEUED before the next (the device work of consecutive calls is
+ * serialised by the library, whatever streams they use) (the reference is not
  * re-entrant either: one process-global pool, utils.cpp:25-28).  Several handles
  * (e.g. one per GPU) may be used concurrently.
  */
@@ -119,7 +121,11 @@ wp_status wp_encode_device(wp_vocab *v, const void *d_text, size_t n_bytes, int3
                            size_t *n_ids, void *stream);
 
 /* As above but fully asynchronous: the id count is written to the device
- * word *d_n_ids (uint64) and nothing is synchronised. */
+ * word *d_n_ids (uint64) and nothing is synchronised.  The internal scratch is sized for every text whose
+ * segments longer than 256 bytes add up to at most the text size of one 64 MiB range; if a call outgrows it
+ * *d_n_ids is UINT64_MAX and d_ids is incomplete — repeat the call through wp_encode_device, which retries
+ * with a larger scratch.  Calls on one handle share its scratch: the library orders them with an event, so
+ * they may be enqueued on different streams, but they never overlap. */
 wp_status wp_encode_device_async(wp_vocab *v, const void *d_text, size_t n_bytes, int32_t *d_ids, size_t capacity,
                                  uint64_t *d_n_ids, void *stream);
 
@@ -133,6 +139,9 @@ wp_status wp_encode_device_async(wp_vocab *v, const void *d_text, size_t n_bytes
  * number).  Safe cuts: right after an is_space char (fast.cpp:113-115), and — for space-free CJK text — at a
  * punctuation char, right after one, or at a Han char.  Pure host code. */
 size_t wp_plan_shards(const char *text, size_t n_bytes, size_t n_shards, size_t *cuts);
+/* The first safe cut at or after pos (n_bytes if there is none): what wp_plan_shards applies to every
+ * nominal boundary.  Lets a rank that holds only its part of a corpus find its own shard borders. */
+size_t wp_next_safe_cut(const char *text, size_t n_bytes, size_t pos);
 
 typedef struct wp_shard {
   size_t begin, end;    /* byte range of the text */

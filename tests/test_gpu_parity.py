@@ -309,6 +309,40 @@ def test_host_buffer_pipeline(gpu_device, monkeypatch):
     v.close()
 
 
+def test_hostile_bytes_at_chunk_borders(gpu_device):
+    """K1 classifies 32-byte chunks; a UTF-8 sequence that breaks just before a chunk border leaves stray
+    continuation bytes just behind it (E2 's' | 80).  Random hostile byte runs are laid over every 32-byte
+    border of a text (and over 4 KiB tile borders), in words that need several pieces, so that a single kept
+    stray byte changes the ids."""
+    rng = random.Random(77)
+    vocab = ["[UNK]"] + [c for c in "abcdefghijklmnopqrstuvwxyz"] + ["##" + c for c in "abcdefghijklmnopqrstuvwxyz"] + \
+            ["re", "##tc", "##s", "ab", "##cd", "é", "##é", "中", "文", "か", "##か", ",", "."]
+    hostile = [b"\xe2", b"\x80", b"\xbf", b"\xc3", b"\xe4\xb8", b"\xf0\x9f", b"\xf0\x9f\x98", b"\xed\xa0", b"\xc0", b"\xff",
+               "é".encode(), "中".encode(), "か".encode(), b"s", b"tc", b" ", b"a", b"", b"", b"\xe2\x96\x81", b"\xe2\x80\x94"]
+    for trial in range(4):
+        buf = bytearray()
+        while len(buf) < 150_000:
+            # fill up to a few bytes before the next 32-byte border with letters and spaces, then hostile bytes
+            border = (len(buf) // 32 + 1) * 32
+            lead_in = border - len(buf) - rng.randint(0, 5)
+            while lead_in > 0:
+                w = "".join(rng.choice("abcdrestc") for _ in range(rng.randint(1, 7))).encode()[:lead_in]
+                buf += w
+                lead_in -= len(w)
+                if lead_in > 0 and rng.random() < 0.6:
+                    buf += b" "
+                    lead_in -= 1
+            for _ in range(rng.randint(1, 5)):
+                buf += rng.choice(hostile)
+        text = bytes(buf)
+        _check(text, vocab, gpu_device, f"chunk-border fuzz #{trial}")
+        _check(b"xy " * trial + text, vocab, gpu_device, f"chunk-border fuzz #{trial} shifted")
+    # the case that was found in the dirty-web text: the stray byte is the first byte of a chunk
+    for shift in range(0, 40):
+        t = b"a" * shift + b" re\xbftc\xe2s\x80 brarbad ci teas"
+        _check(t * 300, vocab, gpu_device, f"E2 s | 80 at shift {shift}")
+
+
 def test_cpp_drop_in_runner(gpu_device, tmp_path):
     """The C++ entry points (include/word_piece.hpp) through the runner CLI with the reference's argv
     contract (tests/runner.cpp:13-65): `fast` prints "Total ids N" and writes "id id id "; `fast-external`

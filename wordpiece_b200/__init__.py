@@ -40,6 +40,7 @@ from .sharding import (  # noqa: F401
     encode_sharded,
     encode_sharded_gather,
     global_offsets,
+    next_safe_cut,
     plan_shards,
     shard_ranges,
 )
@@ -60,6 +61,7 @@ __all__ = [
     "encode_sharded",
     "encode_sharded_gather",
     "global_offsets",
+    "next_safe_cut",
     "plan_shards",
     "shard_ranges",
 ]

@@ -10,7 +10,8 @@ from typing import Iterable, List, Optional, Sequence, Union
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libwordpiece_b200.so")
+# (WORDPIECE_B200_LIB: another build of the same library, e.g. a tuning variant from `make variant`)
+LIB_PATH = os.environ.get("WORDPIECE_B200_LIB") or os.path.join(_HERE, "lib", "libwordpiece_b200.so")
 
 WP_OK = 0
 WP_ERR_INVALID_ARG = 1
@@ -75,6 +76,7 @@ EXPORTED_SYMBOLS = [
     "wp_encode_device",
     "wp_encode_device_async",
     "wp_plan_shards",
+    "wp_next_safe_cut",
     "wp_encode_sharded",
     "wp_encode_sharded_gather",
     "wp_last_stats",
@@ -140,6 +142,8 @@ def load_library() -> C.CDLL:
     L.wp_encode_device_async.restype = C.c_int
     L.wp_plan_shards.argtypes = [vp, sz, sz, C.POINTER(sz)]
     L.wp_plan_shards.restype = sz
+    L.wp_next_safe_cut.argtypes = [vp, sz, sz]
+    L.wp_next_safe_cut.restype = sz
     L.wp_encode_sharded.argtypes = [vp, sz, vp, sz, vp, sz, C.POINTER(sz), vp]
     L.wp_encode_sharded.restype = C.c_int
     L.wp_encode_sharded_gather.argtypes = [vp, sz, vp, sz, sz, vp, sz, C.POINTER(sz), vp, C.POINTER(C.c_float)]

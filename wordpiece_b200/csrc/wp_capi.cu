@@ -91,6 +91,9 @@ struct wp_vocab {
   } slot[3];
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   bool pipe_ready = false;
+  // every call on a handle shares its scratch, counters and word table: the kernels of one call must have
+  // finished before those of the next begin, on whatever streams the caller enqueues them
+  cudaEvent_t last_done = nullptr;
   // optional per-kernel timing (wp_set_kernel_timing): events around K1/K2/K3 of every range
   bool timing = false;
   std::vector<cudaEvent_t> timing_events;  // 4 per range of the last call
@@ -238,6 +241,8 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   const Workspace w = plan_workspace(range_bytes, spill_ids ? spill_ids : range_bytes + tile);
   wp_status st = ensure_work(v, w.total);
   if (st != WP_OK) return st;
+  if (!v->last_done) WP_CUDA(cudaEventCreateWithFlags(&v->last_done, cudaEventDisableTiming));
+  WP_CUDA(cudaStreamWaitEvent(stream, v->last_done, 0));  // (a never-recorded event does not block)
   WP_CUDA(cudaMemsetAsync(v->d_call, 0, sizeof(wp::CallCounters), stream));
   v->timing_used = 0;
   bool use_memo = (call_bytes ? call_bytes : n_bytes) >= kMemoMinBytes;  // judged on the whole user call
@@ -326,6 +331,7 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
     // 2 MiB, then 8 MiB (enough lookups to judge whether the memo pays on this text), then full ranges
     next_tiles = (use_memo && !warm && range == 0 && ((size_t(8) << 20) / tile) < w.n_tiles) ? (size_t(8) << 20) / tile : w.n_tiles;
   }
+  WP_CUDA(cudaEventRecord(v->last_done, stream));
   g_launches.fetch_add(launches, std::memory_order_relaxed);
   info->n_tiles = static_cast<uint32_t>(n_tiles);
   info->n_ranges = range;
@@ -637,6 +643,7 @@ void wp_vocab_destroy(wp_vocab *v) {
       if (sl.d2h_done) cudaEventDestroy(sl.d2h_done);
     }
     for (cudaEvent_t e : v->timing_events) cudaEventDestroy(e);
+    if (v->last_done) cudaEventDestroy(v->last_done);
     if (v->s_h2d) cudaStreamDestroy(v->s_h2d);
     if (v->s_d2h) cudaStreamDestroy(v->s_d2h);
     cudaFree(v->d_call);
@@ -673,8 +680,11 @@ wp_status wp_encode_device_async(wp_vocab *v, const void *d_text, size_t n_bytes
   wp_status st = enqueue_encode(v, d_text, n_bytes, d_ids, capacity, s, 0, &info);
   if (st != WP_OK) return st;
   if (d_n_ids) {
-    WP_CUDA(cudaMemcpyAsync(d_n_ids, &v->d_call->ids_total[info.n_ranges & 1u], sizeof(uint64_t),
-                            cudaMemcpyDeviceToDevice, s));
+    uint64_t launches = 0;
+    WP_CUDA(wp::launch_publish_count(v->d_call, info.n_ranges & 1u, reinterpret_cast<unsigned long long *>(d_n_ids), s,
+                                     &launches));
+    WP_CUDA(cudaEventRecord(v->last_done, s));  // the count reads the counters the next call clears
+    g_launches.fetch_add(launches, std::memory_order_relaxed);
   }
   return WP_OK;
 }
@@ -803,6 +813,13 @@ wp_status wp_encode(wp_vocab *v, const char *text, size_t n_bytes, int32_t **ids
   *ids_out = host;
   *n_ids = cnt;
   return WP_OK;
+}
+
+size_t wp_next_safe_cut(const char *text, size_t n_bytes, size_t pos) {
+  if (!text) return n_bytes;
+  const unsigned char *t = reinterpret_cast<const unsigned char *>(text);
+  while (pos < n_bytes && !safe_cut(t, n_bytes, pos)) pos++;
+  return pos < n_bytes ? pos : n_bytes;
 }
 
 size_t wp_plan_shards(const char *text, size_t n_bytes, size_t n_shards, size_t *cuts) {

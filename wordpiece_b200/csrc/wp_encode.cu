@@ -62,7 +62,20 @@ constexpr uint32_t FULL = 0xFFFFFFFFu;
 constexpr uint32_t POS_MASK = 0x3FFFu;           // window positions fit 14 bits
 constexpr uint32_t SLOW_LONG = 0x8000u;          // tile slow-list flag: matched from the raw text (leaves the window / very long)
 
-constexpr int MATCH_THREADS = 256;               // K2
+// tuning knobs (make variant DEFS=...)
+#ifndef WP_K2_BLOCKS
+#define WP_K2_BLOCKS 4                           // K2 CTAs per SM (launch bound and grid)
+#endif
+#ifndef WP_K2_THREADS
+#define WP_K2_THREADS 256
+#endif
+#ifndef WP_K1_PER_TURN
+#define WP_K1_PER_TURN 2                         // word-table lookups in flight per lane
+#endif
+#ifndef WP_K3_BLOCKS
+#define WP_K3_BLOCKS 4
+#endif
+constexpr int MATCH_THREADS = WP_K2_THREADS;     // K2
 constexpr int SCATTER_THREADS = 256;             // K3
 constexpr int SCATTER_ITEMS = 8;                 // segments per thread and block iteration
 constexpr int SCATTER_SEGS = SCATTER_THREADS * SCATTER_ITEMS;  // 2048
@@ -322,7 +335,11 @@ __device__ __forceinline__ void classify_chunk(TileSmem &sm, const uint8_t *buf,
   if (any_high & 0x80808080u) {
     // ---- structural validation in the byte-lane domain
     WordFlags prev = word_flags(ld_u32(cb - 4));
-    uint32_t bad = prev.suspect, contm = 0, cand = 0;
+    // (a lead in the four bytes before the chunk that already misses a continuation byte THERE is invalid, and
+    // the continuation bytes it would have owned at the start of this chunk are strays: the per-position
+    // expectation below cannot see that, e.g. E2 's' | 80)
+    uint32_t bad = prev.suspect | (((prev.m1 << 8) | (prev.m2 << 16) | (prev.m3 << 24)) & ~prev.cont & 0x80808080u);
+    uint32_t contm = 0, cand = 0;
 #pragma unroll 1
     for (int i = 0; i < 8; i++) {
       const uint32_t wi = ld_u32(cb + 4 * i);
@@ -729,7 +746,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   // settles the segment — with the token it is (static part, fast.cpp:66-72: the longest candidate is the
   // whole window) or with the ids K2 recorded for these bytes earlier in this call.  A single-char segment
   // that is absent is UNK.  The rest go to the slow list.
-  constexpr int PER_TURN = 2;
+  constexpr int PER_TURN = WP_K1_PER_TURN;
   uint32_t my_dyn = 0, my_elig = 0;
   for (uint32_t base = 0; base < n_segs; base += PER_TURN * THREADS) {
     uint32_t kk[PER_TURN], state[PER_TURN], wlen[PER_TURN], idx[PER_TURN], key[PER_TURN][4];
@@ -994,7 +1011,7 @@ constexpr uint32_t SEG_HAN_FIRST = 1u;   // about to match the first piece of a 
 // step that fails, reaches a leaf or the end of the segment closes the piece (fast.cpp:66-91: emit the
 // longest match, continue behind it in the "##" map, or roll the whole word back to UNK).  Lanes without a
 // segment take the next entries of their warp's share at the top of the loop.
-__global__ void __launch_bounds__(MATCH_THREADS, 4) wp_match_kernel(EncodeParams P) {
+__global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(EncodeParams P) {
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const DeviceVocab &V = P.vocab;
@@ -1707,6 +1724,21 @@ cudaError_t launch_seed_words(const WordSlot *image, uint32_t image_slots, WordS
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------ async id count
+// The count of an asynchronous call for its caller: UINT64_MAX if a scratch capacity was exceeded (the ids
+// are incomplete then and the caller must repeat the call through a synchronous entry, which retries with
+// more scratch), else the number of ids.
+__global__ void wp_publish_count_kernel(const CallCounters *call, uint32_t parity, unsigned long long *out) {
+  *out = call->overflow ? ~0ull : call->ids_total[parity];
+}
+
+cudaError_t launch_publish_count(const CallCounters *call, uint32_t parity, unsigned long long *d_out, cudaStream_t stream,
+                                 uint64_t *launches) {
+  wp_publish_count_kernel<<<1, 1, 0, stream>>>(call, parity, d_out);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
 // -------------------------------------------------------------------- launch
 
 uint32_t encode_tile_bytes() { return TILE; }
@@ -1752,7 +1784,7 @@ cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_
   if (e != cudaSuccess) return e;
 
   if (timing) cudaEventRecord(timing[1], stream);
-  cfg.gridDim = dim3(sm_count * 4);  // = resident capacity (__launch_bounds__(256, 4)): one wave, large shares
+  cfg.gridDim = dim3(sm_count * WP_K2_BLOCKS);  // = resident capacity (see the launch bound): one wave, large shares
   cfg.blockDim = dim3(MATCH_THREADS);
   cfg.dynamicSmemBytes = 0;
   cfg.numAttrs = window(P.vocab.edges, P.persist_edges_bytes, P.persist_edges_ratio);
@@ -1765,7 +1797,7 @@ cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_
   if (e != cudaSuccess) return e;
 
   if (timing) cudaEventRecord(timing[2], stream);
-  cfg.gridDim = dim3(sm_count * 4);
+  cfg.gridDim = dim3(sm_count * WP_K3_BLOCKS);
   cfg.blockDim = dim3(SCATTER_THREADS);
   cfg.numAttrs = window(P.words, P.persist_words_bytes, P.persist_words_ratio);
   e = cudaLaunchKernelEx(&cfg, wp_scatter_kernel, P);

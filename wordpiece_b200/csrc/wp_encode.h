@@ -130,6 +130,10 @@ struct EncodeParams {
 cudaError_t launch_seed_words(const WordSlot *image, uint32_t image_slots, WordSlot *work, uint32_t work_slots_log2,
                               cudaStream_t stream, uint64_t *launches);
 
+// *d_out <- the id count of the call whose counters are `call` (UINT64_MAX if its scratch overflowed).
+cudaError_t launch_publish_count(const CallCounters *call, uint32_t parity, unsigned long long *d_out, cudaStream_t stream,
+                                 uint64_t *launches);
+
 uint32_t encode_tile_bytes();
 uint32_t scatter_block_segments();
 // Enqueue K1, K2, K2L, K3 for one range.  *launches is incremented per kernel launched.

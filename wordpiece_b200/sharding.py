@@ -46,6 +46,15 @@ def plan_shards(text, n_shards: int) -> List[int]:
     return [int(c) for c in cuts]
 
 
+def next_safe_cut(text, pos: int) -> int:
+    """``wp_next_safe_cut``: the first safe cut at or after ``pos`` (len(text) if none)."""
+    L = load_library()
+    addr, n, keep = _buffer_address(text)
+    cut = int(L.wp_next_safe_cut(addr, n, pos))
+    del keep
+    return cut
+
+
 def shard_ranges(text, n_shards: int) -> List[Tuple[int, int]]:
     cuts = plan_shards(text, n_shards)
     return list(zip(cuts[:-1], cuts[1:]))
