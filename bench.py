@@ -286,7 +286,9 @@ def other_configs(dev_index: int, peak: float):
         vocab_tokens = g.spec.vocab
         v = wordpiece_b200.Vocab(vocab_tokens, device=dev_index)
         d_text = torch.from_numpy(text).cuda(dev_index)
-        d_ids = torch.empty(text.size // 2 + 4096, dtype=torch.int32, device=d_text.device)
+        # one id per byte is the worst case (ids <= chars <= bytes); the high-UNK and random-alphanumeric shapes
+        # pass 0.5 ids per byte
+        d_ids = torch.empty(text.size, dtype=torch.int32, device=d_text.device)
         d_cnt = torch.zeros(1, dtype=torch.int64, device=d_text.device)
         _, n_ids = v.encode_device(d_text, d_ids)
         st = v.stats()

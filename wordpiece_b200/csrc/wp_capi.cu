@@ -94,6 +94,11 @@ struct wp_vocab {
   // every call on a handle shares its scratch, counters and word table: the kernels of one call must have
   // finished before those of the next begin, on whatever streams the caller enqueues them
   cudaEvent_t last_done = nullptr;
+  // overlap of consecutive ranges (see enqueue_encode): K2/K2L/K3 run on a second, high-priority stream
+  cudaStream_t s_aux = nullptr;
+  cudaEvent_t ev_split[2] = {nullptr, nullptr};    // K1 of the range in scratch half b is done
+  cudaEvent_t ev_scatter[2] = {nullptr, nullptr};  // K3 of the range in scratch half b is done (the half is free)
+  cudaEvent_t ev_match = nullptr;                  // K2 of a warm-up range is done (its words are all recorded)
   // optional per-kernel timing (wp_set_kernel_timing): events around K1/K2/K3 of every range
   bool timing = false;
   std::vector<cudaEvent_t> timing_events;  // 4 per range of the last call
@@ -239,8 +244,7 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   }
   const size_t range_bytes = n_bytes < range_max ? n_bytes : range_max;
   const Workspace w = plan_workspace(range_bytes, spill_ids ? spill_ids : range_bytes + tile);
-  wp_status st = ensure_work(v, w.total);
-  if (st != WP_OK) return st;
+  wp_status st = WP_OK;
   if (!v->last_done) WP_CUDA(cudaEventCreateWithFlags(&v->last_done, cudaEventDisableTiming));
   WP_CUDA(cudaStreamWaitEvent(stream, v->last_done, 0));  // (a never-recorded event does not block)
   WP_CUDA(cudaMemsetAsync(v->d_call, 0, sizeof(wp::CallCounters), stream));
@@ -279,16 +283,9 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   P.ids = d_ids;
   P.capacity = capacity;
   P.call = v->d_call;
-  P.counters = reinterpret_cast<wp::RangeCounters *>(v->d_work);
-  P.tile_state = reinterpret_cast<unsigned long long *>(v->d_work + w.off_tile_state);
-  P.block_state = reinterpret_cast<unsigned long long *>(v->d_work + w.off_block_state);
-  P.seg_result = reinterpret_cast<uint32_t *>(v->d_work + w.off_seg);
   P.seg_capacity = w.seg_cap;
-  P.slow = reinterpret_cast<wp::SlowEntry *>(v->d_work + w.off_slow);
   P.slow_capacity = w.slow_cap;
-  P.long_list = reinterpret_cast<uint32_t *>(v->d_work + w.off_long);
   P.long_capacity = w.long_cap;
-  P.arena = reinterpret_cast<uint32_t *>(v->d_work + w.off_arena);
   P.arena_capacity = w.arena_cap;
   P.n_scatter_blocks = w.n_scatter_blocks;
   P.words = use_memo ? v->d_words_work : v->d_words_static;
@@ -300,37 +297,107 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   P.persist_words_ratio = use_memo ? v->persist_work_ratio : v->persist_words_ratio;
   P.persist_edges_bytes = v->persist_edges_bytes;
   P.persist_edges_ratio = v->persist_edges_ratio;
-  uint32_t range = 0;
   // Two small ranges first (2 MiB, 8 MiB): the first fills the word memo — its own unsettled words all go
   // through K2 — the second shows whether the text repeats its words (memo_worthwhile), so that the bulk of
   // the text, in full ranges, either finds the frequent repeats in the memo or does not pay for it.
-  size_t next_tiles = w.n_tiles;
-  if (use_memo && !warm) {
-    const size_t first_tiles = (size_t(2) << 20) / tile;
-    if (first_tiles < next_tiles) next_tiles = first_tiles;
+  std::vector<std::pair<size_t, size_t>> ranges;  // first tile, tile count
+  {
+    size_t next_tiles = w.n_tiles;
+    if (use_memo && !warm) {
+      const size_t first_tiles = (size_t(2) << 20) / tile;
+      if (first_tiles < next_tiles) next_tiles = first_tiles;
+    }
+    for (size_t first = 0; first < n_tiles;) {
+      const size_t count = n_tiles - first < next_tiles ? n_tiles - first : next_tiles;
+      ranges.emplace_back(first, count);
+      first += count;
+      // 2 MiB, then 8 MiB (enough lookups to judge whether the memo pays on this text), then full ranges
+      next_tiles = (use_memo && !warm && ranges.size() == 1 && ((size_t(8) << 20) / tile) < w.n_tiles) ? (size_t(8) << 20) / tile
+                                                                                                       : w.n_tiles;
+    }
   }
-  for (size_t first = 0; first < n_tiles; range++) {
-    size_t count = n_tiles - first < next_tiles ? n_tiles - first : next_tiles;
-    WP_CUDA(cudaMemsetAsync(v->d_work, 0, w.zero_bytes, stream));
-    P.first_tile = static_cast<uint32_t>(first);
-    P.n_tiles = static_cast<uint32_t>(count);
+  const uint32_t n_ranges = static_cast<uint32_t>(ranges.size());
+
+  // OVERLAP of consecutive ranges.  K1 is bound by instruction issue, K2 and K3 by the latency of dependent
+  // loads, and none of them keeps more than half of an SM's warp slots busy, so the kernels of range r+1 and
+  // range r run side by side: every K1 goes to the caller's stream, K2/K2L/K3 to a second, higher-priority
+  // stream, and the scratch is doubled (range r uses half r & 1).  Order kept by events: K2(r) after K1(r);
+  // K1(r+2) after K3(r) (the scratch half is free); K3(r) after K3(r-1) (stream order: the id offset chain).
+  // The words K2 records while the next K1 is already running are tagged with their epoch and that K1 does
+  // not use them (wp_table.h), so no slot is read while it is written; during the warm-up ranges K1 waits
+  // for the K2 before it instead, because there the freshly recorded words are the point.  Ids do not depend
+  // on any of this: the word table is a cache of exact results.
+  bool overlap = n_ranges >= 3 && !v->timing;
+  if (const char *e = std::getenv("WORDPIECE_B200_OVERLAP")) overlap = overlap && std::atoi(e) != 0;
+  const size_t half = align_up(w.total, 256);
+  st = ensure_work(v, overlap ? 2 * half : w.total);
+  if (st != WP_OK) return st;
+  if (overlap && !v->s_aux) {
+    int lo = 0, hi = 0;
+    WP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = greatest priority (numerically lowest)
+    WP_CUDA(cudaStreamCreateWithPriority(&v->s_aux, cudaStreamNonBlocking, hi));
+    for (int b = 0; b < 2; b++) {
+      WP_CUDA(cudaEventCreateWithFlags(&v->ev_split[b], cudaEventDisableTiming));
+      WP_CUDA(cudaEventCreateWithFlags(&v->ev_scatter[b], cudaEventDisableTiming));
+    }
+    WP_CUDA(cudaEventCreateWithFlags(&v->ev_match, cudaEventDisableTiming));
+  }
+  auto bind_scratch = [&](uint8_t *base) {
+    P.counters = reinterpret_cast<wp::RangeCounters *>(base);
+    P.tile_state = reinterpret_cast<unsigned long long *>(base + w.off_tile_state);
+    P.block_state = reinterpret_cast<unsigned long long *>(base + w.off_block_state);
+    P.seg_result = reinterpret_cast<uint32_t *>(base + w.off_seg);
+    P.slow = reinterpret_cast<wp::SlowEntry *>(base + w.off_slow);
+    P.long_list = reinterpret_cast<uint32_t *>(base + w.off_long);
+    P.arena = reinterpret_cast<uint32_t *>(base + w.off_arena);
+  };
+  const uint32_t n_warmup = (use_memo && !warm) ? 2u : 0u;  // ranges 0 and 1 warm the memo up
+  for (uint32_t range = 0; range < n_ranges; range++) {
+    const uint32_t b = overlap ? (range & 1u) : 0u;
+    uint8_t *scratch = v->d_work + (overlap ? b * half : 0);
+    bind_scratch(scratch);
+    P.first_tile = static_cast<uint32_t>(ranges[range].first);
+    P.n_tiles = static_cast<uint32_t>(ranges[range].second);
     P.range_parity = range & 1u;
     P.range_index = warm ? range + 2 : range;
-    cudaEvent_t *tev = nullptr;
-    if (v->timing) {
-      while (v->timing_events.size() < v->timing_used + 4) {
-        cudaEvent_t e;
-        WP_CUDA(cudaEventCreate(&e));
-        v->timing_events.push_back(e);
+    P.record_epoch = P.range_index + 1u < wp::WORD_EPOCH_MAX ? P.range_index + 1u : wp::WORD_EPOCH_MAX;
+    P.accept_epoch = wp::WORD_EPOCH_MAX;
+    if (!overlap) {
+      WP_CUDA(cudaMemsetAsync(scratch, 0, w.zero_bytes, stream));
+      cudaEvent_t *tev = nullptr;
+      if (v->timing) {
+        while (v->timing_events.size() < v->timing_used + 4) {
+          cudaEvent_t e;
+          WP_CUDA(cudaEventCreate(&e));
+          v->timing_events.push_back(e);
+        }
+        tev = v->timing_events.data() + v->timing_used;
+        v->timing_used += 4;
       }
-      tev = v->timing_events.data() + v->timing_used;
-      v->timing_used += 4;
+      WP_CUDA(wp::launch_encode_range(P, v->sm_count, stream, &launches, tev));
+      continue;
     }
-    WP_CUDA(wp::launch_encode_range(P, v->sm_count, stream, &launches, tev));
-    first += count;
-    // 2 MiB, then 8 MiB (enough lookups to judge whether the memo pays on this text), then full ranges
-    next_tiles = (use_memo && !warm && range == 0 && ((size_t(8) << 20) / tile) < w.n_tiles) ? (size_t(8) << 20) / tile : w.n_tiles;
+    // the K2 that ran (or runs) right before this K1: finished for the ranges after the warm-up ones (K1
+    // waits for it), possibly still recording otherwise — then its epoch (range index) is not accepted
+    const bool wait_match = range >= 1 && range <= n_warmup;
+    P.accept_epoch = wait_match || range == 0 ? wp::WORD_EPOCH_MAX : (P.range_index >= 1 ? P.range_index - 1u : 0u);
+    if (P.accept_epoch >= wp::WORD_EPOCH_MAX && !(wait_match || range == 0)) P.accept_epoch = wp::WORD_EPOCH_MAX - 1u;
+    if (range >= 2) WP_CUDA(cudaStreamWaitEvent(stream, v->ev_scatter[b], 0));
+    if (wait_match) WP_CUDA(cudaStreamWaitEvent(stream, v->ev_match, 0));
+    WP_CUDA(cudaMemsetAsync(scratch, 0, w.zero_bytes, stream));
+    WP_CUDA(wp::launch_encode_range(P, v->sm_count, stream, &launches, nullptr, wp::PHASE_SPLIT));
+    WP_CUDA(cudaEventRecord(v->ev_split[b], stream));
+    WP_CUDA(cudaStreamWaitEvent(v->s_aux, v->ev_split[b], 0));
+    WP_CUDA(wp::launch_encode_range(P, v->sm_count, v->s_aux, &launches, nullptr, wp::PHASE_MATCH));
+    if (range < n_warmup) WP_CUDA(cudaEventRecord(v->ev_match, v->s_aux));
+    WP_CUDA(wp::launch_encode_range(P, v->sm_count, v->s_aux, &launches, nullptr, wp::PHASE_SCATTER));
+    WP_CUDA(cudaEventRecord(v->ev_scatter[b], v->s_aux));
   }
+  if (overlap) {
+    // the caller's stream continues only when the last K3 (which is after every other kernel of the call) is done
+    WP_CUDA(cudaStreamWaitEvent(stream, v->ev_scatter[(n_ranges - 1) & 1u], 0));
+  }
+  const uint32_t range = n_ranges;
   WP_CUDA(cudaEventRecord(v->last_done, stream));
   g_launches.fetch_add(launches, std::memory_order_relaxed);
   info->n_tiles = static_cast<uint32_t>(n_tiles);
@@ -644,6 +711,12 @@ void wp_vocab_destroy(wp_vocab *v) {
     }
     for (cudaEvent_t e : v->timing_events) cudaEventDestroy(e);
     if (v->last_done) cudaEventDestroy(v->last_done);
+    for (int b = 0; b < 2; b++) {
+      if (v->ev_split[b]) cudaEventDestroy(v->ev_split[b]);
+      if (v->ev_scatter[b]) cudaEventDestroy(v->ev_scatter[b]);
+    }
+    if (v->ev_match) cudaEventDestroy(v->ev_match);
+    if (v->s_aux) cudaStreamDestroy(v->s_aux);
     if (v->s_h2d) cudaStreamDestroy(v->s_h2d);
     if (v->s_d2h) cudaStreamDestroy(v->s_d2h);
     cudaFree(v->d_call);

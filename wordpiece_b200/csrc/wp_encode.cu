@@ -87,13 +87,13 @@ static_assert(LONG_SEGMENT_BYTES <= HALO, "a segment that starts in the tile and
 static_assert(NCHUNK + 1 <= THREADS, "one thread per chunk in the classification and compaction passes");
 static_assert(WINDOW <= static_cast<int>(POS_MASK), "positions must fit the packed list entries");
 static_assert(TILE <= 4096, "segment ordinals must fit 12 bits of the tile slow list");
+static_assert(NCHUNK < 256, "chunk indices are kept in bytes (hi_list)");
 
 struct __align__(16) TileSmem {
   uint8_t raw[RAW_BYTES];              // [0,LEFT) left halo, then the window, then look-ahead
   uint16_t seg_s[TILE];                // owned segment k (text order): start position | class << 14
   uint16_t seg_e[WINDOW + 64];         // j-th segment end in the window
   uint16_t slow[MAX_TILE_SLOW];        // segments the whole-window probe did not settle: ordinal | flags
-  uint32_t settled[TILE / 32];         // bit k: segment k was settled by S2a (its result is parked in seg_s/seg_e)
   uint32_t dyn_hits;                   // segments settled by a word K2 recorded during this call
   uint32_t n_eligible;                 // slow segments short enough for the word table (recording statistics)
   uint32_t any_single;                 // some single-char segment is still to be settled (see S2)
@@ -105,6 +105,8 @@ struct __align__(16) TileSmem {
   uint32_t m_kept[NCHUNK + 1];         // bytes of the RAW window that survive the strict decoder (dirty tiles)
   uint32_t kept_scan[NCHUNK + 2];      // exclusive scan of kept bytes per chunk (dirty tiles)
   uint8_t spill[NCHUNK + 1];           // bytes by which the chunk's last sequence runs into the next chunk
+  uint8_t hi_list[NCHUNK + 8];         // chunks that hold a byte >= 0x80 (classification pass 2)
+  uint32_t n_hi;
   uint4 key_mask[WORD_KEY_BYTES + 1];  // row k: byte masks of the four key words for a k-byte key
   uint32_t warp_sums[WARPS];
   uint32_t prev_class;                 // class of the last valid char before the tile
@@ -116,6 +118,8 @@ struct __align__(16) TileSmem {
   uint32_t arena_base;                 // first arena word reserved for this tile
   unsigned long long seg_base;         // segments of all earlier tiles of the range
 };
+
+static_assert(sizeof(TileSmem) + 1024 <= 233472 / 7, "seven K1 tiles must fit one SM's shared memory");
 
 // ------------------------------------------------------------------- helpers
 
@@ -304,22 +308,27 @@ __device__ __forceinline__ WordFlags word_flags(uint32_t w) {
   return f;
 }
 
-// Classify chunk c of `buf` (window coordinates) into the mask arrays.  `limit`
-// is the number of meaningful bytes in buf (positions >= limit are ignored).
+// Classification of the window into the mask arrays, in two passes.  `limit` is the number of meaningful
+// bytes in buf (positions >= limit are ignored).
 //
-// Fast lane (no per-byte loop): ASCII classes by SWAR range tests; multi-byte
-// text is validated STRUCTURALLY (every lead followed by exactly its
-// continuation bytes) with byte-lane shifts; only leads that can be space /
-// punctuation / Han (C2, E2..E9, EF) are decoded.  Chunks holding a lead whose
-// validity depends on its value (overlong / surrogate / 4-byte forms) or any
-// structural error take the exact per-byte lane below.
-__device__ __forceinline__ void classify_chunk(TileSmem &sm, const uint8_t *buf, int c, int limit) {
+// Pass 1, every chunk: the ASCII classes by SWAR range tests, and whether the chunk holds any byte >= 0x80.
+// Pass 2, only the chunks that do, COMPACTED into a list so that all lanes of a warp are busy (in
+// English-like text one chunk in eight holds a non-ASCII byte; run in place, those few lanes made their
+// whole warp execute the pass): multi-byte text is validated STRUCTURALLY (every lead followed by exactly its
+// continuation bytes) with byte-lane shifts; only leads that can be space / punctuation / Han (C2, E2..E9,
+// EF) are decoded.  Chunks holding a lead whose validity depends on its value (overlong / surrogate /
+// 4-byte forms) or any structural error take the exact per-byte lane.
+__device__ __forceinline__ uint32_t limit_mask(int c, int limit) {
+  const int left = limit - c * CHUNK;
+  return left >= CHUNK ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+}
+
+__device__ __forceinline__ bool classify_ascii(TileSmem &sm, const uint8_t *buf, int c, int limit) {
   const uint8_t *cb = buf + c * CHUNK;
-  uint32_t lead = 0xFFFFFFFFu, sp = 0, pu = 0, ha = 0, cover = 0xFFFFFFFFu, spill = 0;
-  uint32_t any_high = 0;
+  uint32_t sp = 0, pu = 0, any_high = 0;
   // (the loops over the chunk's eight words are deliberately NOT fully unrolled: K1's executed code must fit
-  // the SM's 32 KB instruction cache — six tiles in different phases share it — and these two loops alone
-  // were a sixth of it; the words are re-read from shared memory where they are needed)
+  // the SM's 32 KB instruction cache — the tiles resident on an SM are in different phases — and these loops
+  // alone were a sixth of it; the words are re-read from shared memory where they are needed)
 #pragma unroll 2
   for (int i = 0; i < 8; i++) {
     const uint32_t wi = ld_u32(cb + 4 * i);
@@ -332,80 +341,112 @@ __device__ __forceinline__ void classify_chunk(TileSmem &sm, const uint8_t *buf,
     pu |= swar_nibble(q) << (4 * i);
     any_high |= wi;
   }
-  if (any_high & 0x80808080u) {
-    // ---- structural validation in the byte-lane domain
-    WordFlags prev = word_flags(ld_u32(cb - 4));
-    // (a lead in the four bytes before the chunk that already misses a continuation byte THERE is invalid, and
-    // the continuation bytes it would have owned at the start of this chunk are strays: the per-position
-    // expectation below cannot see that, e.g. E2 's' | 80)
-    uint32_t bad = prev.suspect | (((prev.m1 << 8) | (prev.m2 << 16) | (prev.m3 << 24)) & ~prev.cont & 0x80808080u);
-    uint32_t contm = 0, cand = 0;
+  const uint32_t in = limit_mask(c, limit);
+  sm.m_space[c] = sp & in;
+  sm.m_punct[c] = pu & in;
+  const bool high = (any_high & 0x80808080u) != 0;
+  if (!high) {
+    sm.m_lead[c] = in;
+    sm.m_han[c] = 0;
+    sm.m_cover[c] = 0xFFFFFFFFu;
+    sm.spill[c] = 0;
+  }
+  return high;
+}
+
+__device__ __forceinline__ void classify_multibyte(TileSmem &sm, const uint8_t *buf, int c, int limit) {
+  const uint8_t *cb = buf + c * CHUNK;
+  uint32_t lead = 0xFFFFFFFFu, sp = sm.m_space[c], pu = sm.m_punct[c], ha = 0, cover = 0xFFFFFFFFu, spill = 0;
+  // ---- structural validation in the byte-lane domain
+  WordFlags prev = word_flags(ld_u32(cb - 4));
+  // (a lead in the four bytes before the chunk that already misses a continuation byte THERE is invalid, and
+  // the continuation bytes it would have owned at the start of this chunk are strays: the per-position
+  // expectation below cannot see that, e.g. E2 's' | 80)
+  uint32_t bad = prev.suspect | (((prev.m1 << 8) | (prev.m2 << 16) | (prev.m3 << 24)) & ~prev.cont & 0x80808080u);
+  uint32_t contm = 0, cand = 0;
 #pragma unroll 1
-    for (int i = 0; i < 8; i++) {
-      const uint32_t wi = ld_u32(cb + 4 * i);
-      const WordFlags f = word_flags(wi);
-      const uint32_t expect = lanes_back(prev.m1, f.m1, 1) | lanes_back(prev.m2, f.m2, 2) | lanes_back(prev.m3, f.m3, 3);
-      bad |= (expect ^ f.cont) | f.suspect;
-      contm |= swar_nibble(f.cont) << (4 * i);
-      // leads that may be a spacing char: C2 (Latin-1 punctuation), E2 (U+2010.., U+2581), E3..E9, EF (Han)
-      const uint32_t low = wi & 0x0F0F0F0Fu;
-      const uint32_t lead3 = f.m2 & ~(wi << 3);
-      const uint32_t cf = swar_zero(wi ^ 0xC2C2C2C2u) | (lead3 & (swar_range(low, 2, 9) | swar_zero(low ^ 0x0F0F0F0Fu)));
-      cand |= swar_nibble(cf) << (4 * i);
-      prev = f;
+  for (int i = 0; i < 8; i++) {
+    const uint32_t wi = ld_u32(cb + 4 * i);
+    const WordFlags f = word_flags(wi);
+    const uint32_t expect = lanes_back(prev.m1, f.m1, 1) | lanes_back(prev.m2, f.m2, 2) | lanes_back(prev.m3, f.m3, 3);
+    bad |= (expect ^ f.cont) | f.suspect;
+    contm |= swar_nibble(f.cont) << (4 * i);
+    // leads that may be a spacing char: C2 (Latin-1 punctuation), E2 (U+2010.., U+2581), E3..E9, EF (Han)
+    const uint32_t low = wi & 0x0F0F0F0Fu;
+    const uint32_t lead3 = f.m2 & ~(wi << 3);
+    const uint32_t cf = swar_zero(wi ^ 0xC2C2C2C2u) | (lead3 & (swar_range(low, 2, 9) | swar_zero(low ^ 0x0F0F0F0Fu)));
+    cand |= swar_nibble(cf) << (4 * i);
+    prev = f;
+  }
+  {
+    // sequences that run past the chunk must find their continuation bytes in the next word
+    const WordFlags nx = word_flags(ld_u32(cb + CHUNK));
+    const uint32_t expect = lanes_back(prev.m1, 0u, 1) | lanes_back(prev.m2, 0u, 2) | lanes_back(prev.m3, 0u, 3);
+    bad |= expect & ~nx.cont;
+    spill = __popc(expect);
+  }
+  if (bad == 0) {
+    lead = ~contm;
+    while (cand) {
+      const int j = __ffs(cand) - 1;
+      cand &= cand - 1;
+      const uint32_t b0 = cb[j], b1 = cb[j + 1], b2 = cb[j + 2];
+      const uint32_t cp = b0 < 0xE0u ? (((b0 & 0x1Fu) << 6) | (b1 & 0x3Fu))
+                                     : (((b0 & 0x0Fu) << 12) | ((b1 & 0x3Fu) << 6) | (b2 & 0x3Fu));
+      const uint32_t cls = cp_class(cp);
+      sp |= (cls == CLS_SPACE ? 1u : 0u) << j;
+      pu |= (cls == CLS_PUNCT ? 1u : 0u) << j;
+      ha |= (cls == CLS_HAN ? 1u : 0u) << j;
     }
-    {
-      // sequences that run past the chunk must find their continuation bytes in the next word
-      const WordFlags nx = word_flags(ld_u32(cb + CHUNK));
-      const uint32_t expect = lanes_back(prev.m1, 0u, 1) | lanes_back(prev.m2, 0u, 2) | lanes_back(prev.m3, 0u, 3);
-      bad |= expect & ~nx.cont;
-      spill = __popc(expect);
-    }
-    if (bad == 0) {
-      lead = ~contm;
-      while (cand) {
-        const int j = __ffs(cand) - 1;
-        cand &= cand - 1;
-        const uint32_t b0 = cb[j], b1 = cb[j + 1], b2 = cb[j + 2];
-        const uint32_t cp = b0 < 0xE0u ? (((b0 & 0x1Fu) << 6) | (b1 & 0x3Fu))
-                                       : (((b0 & 0x0Fu) << 12) | ((b1 & 0x3Fu) << 6) | (b2 & 0x3Fu));
-        const uint32_t cls = cp_class(cp);
-        sp |= (cls == CLS_SPACE ? 1u : 0u) << j;
-        pu |= (cls == CLS_PUNCT ? 1u : 0u) << j;
-        ha |= (cls == CLS_HAN ? 1u : 0u) << j;
-      }
-    } else {
-      // ---- exact per-byte lane (utf8.cpp:54-90): overlongs, surrogates, 4-byte forms, stray bytes
-      lead = 0;
-      cover = 0;
-      spill = 0;
-      sp = 0;
-      pu = 0;
-      for (int j = 0; j < CHUNK; j++) {
-        const uint32_t b0 = cb[j];
-        if (is_cont_byte(b0)) continue;
-        uint32_t cp = 0;
-        const uint32_t len = b0 < 0x80u ? (cp = b0, 1u) : utf8_decode(b0, cb[j + 1], cb[j + 2], cb[j + 3], 4u, &cp);
-        if (len == 0) continue;
-        lead |= 1u << j;
-        cover |= ((1u << len) - 1u) << j;
-        if (j + static_cast<int>(len) > CHUNK) spill = j + len - CHUNK;
-        const uint32_t cls = cp_class(cp);
-        sp |= (cls == CLS_SPACE ? 1u : 0u) << j;
-        pu |= (cls == CLS_PUNCT ? 1u : 0u) << j;
-        ha |= (cls == CLS_HAN ? 1u : 0u) << j;
-      }
+  } else {
+    // ---- exact per-byte lane (utf8.cpp:54-90): overlongs, surrogates, 4-byte forms, stray bytes
+    lead = 0;
+    cover = 0;
+    spill = 0;
+    sp = 0;
+    pu = 0;
+    for (int j = 0; j < CHUNK; j++) {
+      const uint32_t b0 = cb[j];
+      if (is_cont_byte(b0)) continue;
+      uint32_t cp = 0;
+      const uint32_t len = b0 < 0x80u ? (cp = b0, 1u) : utf8_decode(b0, cb[j + 1], cb[j + 2], cb[j + 3], 4u, &cp);
+      if (len == 0) continue;
+      lead |= 1u << j;
+      cover |= ((1u << len) - 1u) << j;
+      if (j + static_cast<int>(len) > CHUNK) spill = j + len - CHUNK;
+      const uint32_t cls = cp_class(cp);
+      sp |= (cls == CLS_SPACE ? 1u : 0u) << j;
+      pu |= (cls == CLS_PUNCT ? 1u : 0u) << j;
+      ha |= (cls == CLS_HAN ? 1u : 0u) << j;
     }
   }
   // ignore everything at or past `limit`
-  const int left = limit - c * CHUNK;
-  const uint32_t in = left >= CHUNK ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+  const uint32_t in = limit_mask(c, limit);
   sm.m_lead[c] = lead & in;
   sm.m_space[c] = sp & in;
   sm.m_punct[c] = pu & in;
   sm.m_han[c] = ha & in;
   sm.m_cover[c] = cover;
   sm.spill[c] = static_cast<uint8_t>(spill);
+}
+
+// Both passes over the whole window (block-wide; sm.n_hi must be zero on entry; the caller synchronises
+// before it reads the masks).  Out of line: K1 calls it from two places.
+__device__ __noinline__ void classify_window(TileSmem &sm, const uint8_t *buf, int limit) {
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const bool high = tid < NCHUNK && classify_ascii(sm, buf, tid, limit);
+  const uint32_t hm = __ballot_sync(FULL, high);
+  if (hm) {
+    uint32_t at = 0;
+    const int leader = __ffs(hm) - 1;
+    if (lane == leader) at = smem_add(&sm.n_hi, static_cast<uint32_t>(__popc(hm)));
+    at = __shfl_sync(FULL, at, leader);
+    if (high) sm.hi_list[at + __popc(hm & ((1u << lane) - 1u))] = static_cast<uint8_t>(tid);
+  }
+  __syncthreads();
+  const uint32_t n_hi = sm.n_hi;
+  for (uint32_t i = tid; i < n_hi; i += THREADS) classify_multibyte(sm, buf, sm.hi_list[i], limit);
 }
 
 // block-wide exclusive scan of one value per thread; returns the exclusive prefix, *total = sum
@@ -433,7 +474,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t *warp_sums, ui
 }
 
 // K1 calls the scan from three places; one out-of-line copy keeps its executed code inside the instruction
-// cache (see classify_chunk).  Returns the exclusive prefix in the low and the total in the high 32 bits.
+// cache (see classify_ascii).  Returns the exclusive prefix in the low and the total in the high 32 bits.
 __device__ __noinline__ unsigned long long tile_exclusive_scan(uint32_t *warp_sums, uint32_t v) {
   uint32_t total;
   const uint32_t at = block_exclusive_scan<WARPS>(warp_sums, v, &total);
@@ -541,6 +582,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     sm.dyn_hits = 0;
     sm.n_eligible = 0;
     sm.any_single = 0;
+    sm.n_hi = 0;
   }
   init_key_mask(sm.key_mask, tid);
   __syncthreads();
@@ -606,7 +648,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   // ---- S1b: classify the window; find bytes that the strict decoder drops
   uint8_t *const buf = sm.raw + LEFT;
   int limit = WINDOW;
-  if (tid < NCHUNK) classify_chunk(sm, buf, tid, WINDOW);
+  classify_window(sm, buf, WINDOW);
   if (tid == THREADS - 2) {
     // a sequence that starts in the last 3 bytes before the tile may own its first bytes
     uint32_t ls = 0;
@@ -633,6 +675,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     // utf8.cpp:130-147.
     uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t my_cnt = 0;
+    if (tid == 0) sm.n_hi = 0;  // for the second classification below (barriers lie on both sides)
     if (tid <= NCHUNK) {
       const uint4 a = *reinterpret_cast<const uint4 *>(buf + tid * CHUNK);
       const uint4 b = *reinterpret_cast<const uint4 *>(buf + tid * CHUNK + 16);
@@ -659,7 +702,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     for (int i = static_cast<int>(packed_len) + tid; i < WINDOW + LOOKAHEAD; i += THREADS) buf[i] = 0x20;
     __syncthreads();
     limit = static_cast<int>(packed_len) < WINDOW ? static_cast<int>(packed_len) : WINDOW;
-    if (tid < NCHUNK) classify_chunk(sm, buf, tid, limit);
+    classify_window(sm, buf, limit);
     __syncthreads();
   }
   // owned range in buffer coordinates: segments that start in [0, own_end)
@@ -746,117 +789,103 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   // settles the segment — with the token it is (static part, fast.cpp:66-72: the longest candidate is the
   // whole window) or with the ids K2 recorded for these bytes earlier in this call.  A single-char segment
   // that is absent is UNK.  The rest go to the slow list.
+  //
+  // Straight-line on purpose: every lane — also one past the last segment, or with a segment too long for the
+  // table — loads a window, hashes it and loads a slot (clamped to something harmless), and the outcome is
+  // applied with predicates; only the further probes behind an occupied slot are a loop.
   constexpr int PER_TURN = WP_K1_PER_TURN;
   uint32_t my_dyn = 0, my_elig = 0;
+  const uint32_t accept_epoch = P.accept_epoch;
+  const uint32_t word_mask = P.word_mask;
+#pragma unroll 1
   for (uint32_t base = 0; base < n_segs; base += PER_TURN * THREADS) {
-    uint32_t kk[PER_TURN], state[PER_TURN], wlen[PER_TURN], idx[PER_TURN], key[PER_TURN][4];
+    uint32_t state[PER_TURN], wlen[PER_TURN], idx[PER_TURN], key[PER_TURN][4];
     uint4 sa[PER_TURN], sb[PER_TURN];
 #pragma unroll
     for (int u = 0; u < PER_TURN; u++) {
       const uint32_t k = base + u * THREADS + tid;
-      kk[u] = k;
-      state[u] = 0;  // 0 = no segment, 1 = looked up, 2 = slow, 3 = slow and LONG
-      wlen[u] = 0;
-      idx[u] = 0;
-      sa[u] = make_uint4(0, 0, 0, 0);
-      sb[u] = make_uint4(0, 0, 0, 0);
-      if (k < n_segs) {
-        const int s = static_cast<int>(sm.seg_s[k] & POS_MASK);
-        const uint32_t j = k + skip;
-        int e = limit;
-        bool leaves = false;
-        if (j < n_ends) {
-          e = sm.seg_e[j];
-        } else {
-          leaves = more_text;  // no end inside the window
-        }
-        const uint32_t len = static_cast<uint32_t>(e - s);
-        wlen[u] = len;
-        if (leaves || len > LONG_SEGMENT_BYTES) {
-          state[u] = 3;
-        } else if (len > WORD_KEY_BYTES) {
-          state[u] = 2;
-        } else {
-          state[u] = 1;
-          uint32_t r[4];
-          load_window(buf, s, r);
-          const uint4 km = sm.key_mask[len];
-          key[u][0] = r[0] & km.x;
-          key[u][1] = r[1] & km.y;
-          key[u][2] = r[2] & km.z;
-          key[u][3] = r[3] & km.w;
-          idx[u] = word_hash(key[u][0], key[u][1], key[u][2], key[u][3], len, P.word_shift);
-          ld_word_slot(wtab, idx[u], &sa[u], &sb[u]);
-        }
-      }
+      const uint32_t kc = min(k, n_segs - 1u);
+      const int s = static_cast<int>(sm.seg_s[kc] & POS_MASK);
+      const uint32_t j = kc + skip;
+      const bool has_end = j < n_ends;
+      const int e0 = sm.seg_e[j];  // (in bounds either way: j <= TILE)
+      const int e = has_end ? e0 : limit;
+      const uint32_t len = static_cast<uint32_t>(e - s);
+      const bool is_long = (!has_end && more_text) || len > LONG_SEGMENT_BYTES;  // no end inside the window / very long
+      // 0 = no segment, 1 = looked up, 2 = slow, 3 = slow and LONG
+      state[u] = k >= n_segs ? 0u : (is_long ? 3u : (len > WORD_KEY_BYTES ? 2u : 1u));
+      wlen[u] = len;
+      const uint32_t lc = min(len, WORD_KEY_BYTES);
+      uint32_t r[4];
+      load_window(buf, s, r);
+      const uint4 km = sm.key_mask[lc];
+      key[u][0] = r[0] & km.x;
+      key[u][1] = r[1] & km.y;
+      key[u][2] = r[2] & km.z;
+      key[u][3] = r[3] & km.w;
+      idx[u] = word_hash(key[u][0], key[u][1], key[u][2], key[u][3], lc, P.word_shift);
+      ld_word_slot(wtab, idx[u], &sa[u], &sb[u]);
     }
 #pragma unroll
     for (int u = 0; u < PER_TURN; u++) {
-      bool settled = false;
-      if (state[u] == 1) {
-        uint32_t outcome = 2;  // 0 = absent, 1 = hit, 2 = not decided within WORD_PROBES slots
-        for (uint32_t t = 0;; t++) {
-          const uint32_t meta = sb[u].x;
-          if (meta == 0) {
-            outcome = 0;
-            break;
+      const bool look = state[u] == 1u;
+      auto slot_hit = [&](const uint4 &a, const uint4 &m) {
+        return (m.x & WORD_READY) && word_meta_len(m.x) == wlen[u] && a.x == key[u][0] && a.y == key[u][1] &&
+               a.z == key[u][2] && a.w == key[u][3] && word_meta_epoch(m.x) <= accept_epoch;
+      };
+      bool hit = slot_hit(sa[u], sb[u]);
+      bool absent = sb[u].x == 0u;         // an empty slot ends the probe sequence: no such word
+      bool more = look && !hit && !absent;  // the slot holds another word: look at the next ones
+      if (__any_sync(FULL, more)) {
+#pragma unroll 1
+        for (uint32_t t = 1; t < WORD_PROBES; t++) {
+          if (more) {
+            idx[u] = (idx[u] + 1u) & word_mask;
+            ld_word_slot(wtab, idx[u], &sa[u], &sb[u]);
+            hit = slot_hit(sa[u], sb[u]);
+            absent = sb[u].x == 0u;
+            more = !hit && !absent;
           }
-          if ((meta & WORD_READY) && word_meta_len(meta) == wlen[u] && sa[u].x == key[u][0] && sa[u].y == key[u][1] &&
-              sa[u].z == key[u][2] && sa[u].w == key[u][3]) {
-            outcome = 1;
-            break;
-          }
-          if (t == WORD_PROBES - 1) break;
-          idx[u] = (idx[u] + 1) & P.word_mask;
-          ld_word_slot(wtab, idx[u], &sa[u], &sb[u]);
-        }
-        const bool single = wlen[u] == utf8_lead_len(key[u][0] & 0xFFu);
-        if (outcome == 1 || single) {
-          // settled: park the result in the two list entries of the segment, which are no longer needed, until
-          // the tile knows its first global segment number
-          uint32_t res;
-          if (outcome == 1) {
-            const uint32_t cnt = word_meta_count(sb[u].x);
-            res = cnt == 1 ? sb[u].y + 1u : (SEG_RESULT_WORD | (cnt << SEG_WORD_SLOT_BITS) | idx[u]);
-            my_dyn += (sb[u].x & WORD_DYNAMIC) ? 1u : 0u;
-          } else {
-            res = static_cast<uint32_t>(V.unk_id + 1);
-          }
-          if (outcome == 2) {
-            sm.seg_e[kk[u] + skip] = PARK_PENDING;  // seg_s keeps the position for the pass below
-            sm.any_single = 1u;
-          } else {
-            sm.seg_s[kk[u]] = static_cast<uint16_t>(res);
-            sm.seg_e[kk[u] + skip] = static_cast<uint16_t>(res >> 16);
-          }
-          settled = true;
-        } else {
-          state[u] = 2;
-          my_elig++;
+          if (!__any_sync(FULL, more)) break;
         }
       }
-      const uint32_t settledm = __ballot_sync(FULL, settled);
-      if (lane == 0 && base + u * THREADS + (tid & ~31) < n_segs) sm.settled[(base + u * THREADS + tid) >> 5] = settledm;
-      const uint32_t slowm = __ballot_sync(FULL, state[u] >= 2);
+      // hit / absent / (neither:) not decided within WORD_PROBES slots
+      const bool single = wlen[u] == utf8_lead_len(key[u][0] & 0xFFu);
+      const bool settled = look && (hit || single);
+      if (settled) {
+        // park the result in the two list entries of the segment, which are no longer needed, until the tile
+        // knows its first global segment number
+        const uint32_t cnt = word_meta_count(sb[u].x);
+        uint32_t res = cnt == 1u ? sb[u].y + 1u : (SEG_RESULT_WORD | (cnt << SEG_WORD_SLOT_BITS) | idx[u]);
+        if (!hit) res = absent ? static_cast<uint32_t>(V.unk_id + 1) : (static_cast<uint32_t>(PARK_PENDING) << 16);
+        if (!hit && !absent) sm.any_single = 1u;  // (seg_s keeps the position for the pass below)
+        else sm.seg_s[base + u * THREADS + tid] = static_cast<uint16_t>(res);
+        sm.seg_e[base + u * THREADS + tid + skip] = static_cast<uint16_t>(res >> 16);
+        my_dyn += (hit && (sb[u].x & WORD_DYNAMIC)) ? 1u : 0u;
+      } else if (look) {
+        state[u] = 2u;
+        my_elig++;
+      }
+      const uint32_t slowm = __ballot_sync(FULL, state[u] >= 2u);
       if (slowm) {
         uint32_t at = 0;
         const int leader = __ffs(slowm) - 1;
         if (lane == leader) at = smem_add(&sm.n_slow, static_cast<uint32_t>(__popc(slowm)));
         at = __shfl_sync(FULL, at, leader);
-        if (state[u] >= 2)
-          sm.slow[at + __popc(slowm & ((1u << lane) - 1u))] = static_cast<uint16_t>(kk[u] | (state[u] == 3 ? SLOW_LONG : 0u));
+        if (state[u] >= 2u)
+          sm.slow[at + __popc(slowm & ((1u << lane) - 1u))] =
+              static_cast<uint16_t>((base + u * THREADS + tid) | (state[u] == 3u ? SLOW_LONG : 0u));
       }
     }
   }
   if (P.record_words) {
     // statistics for K2's decision whether recording words still pays (memo_worthwhile)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      my_dyn += __shfl_xor_sync(FULL, my_dyn, o);
-      my_elig += __shfl_xor_sync(FULL, my_elig, o);
+    my_dyn = __reduce_add_sync(FULL, my_dyn);
+    my_elig = __reduce_add_sync(FULL, my_elig);
+    if (lane == 0 && (my_dyn | my_elig)) {
+      smem_add_noret(&sm.dyn_hits, my_dyn);
+      smem_add_noret(&sm.n_eligible, my_elig);
     }
-    if (lane == 0 && my_dyn) smem_add_noret(&sm.dyn_hits, my_dyn);
-    if (lane == 0 && my_elig) smem_add_noret(&sm.n_eligible, my_elig);
   }
   __syncthreads();
 
@@ -864,7 +893,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   if (sm.any_single) {  // uniform
 #pragma unroll 1
     for (uint32_t k = tid; k < n_segs; k += THREADS) {
-      if (!((sm.settled[k >> 5] >> (k & 31)) & 1u) || sm.seg_e[k + skip] != PARK_PENDING) continue;
+      if (sm.seg_e[k + skip] != PARK_PENDING) continue;  // (an end position and a parked high half are smaller)
       uint32_t r[4];
       load_window(buf, static_cast<int>(sm.seg_s[k] & POS_MASK), r);
       const uint32_t len = utf8_lead_len(r[0] & 0xFFu);
@@ -890,11 +919,11 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     if (tid == 0) P.call->overflow = 1u;
     return;  // uniform
   }
+  // (every segment is written: the words of the unsettled ones are garbage here and are overwritten below,
+  // behind a barrier, when their slow entries exist)
 #pragma unroll 1
-  for (uint32_t k = tid; k < n_segs; k += THREADS) {
-    if ((sm.settled[k >> 5] >> (k & 31)) & 1u)
-      P.seg_result[seg_base + k] = static_cast<uint32_t>(sm.seg_s[k]) | (static_cast<uint32_t>(sm.seg_e[k + skip]) << 16);
-  }
+  for (uint32_t k = tid; k < n_segs; k += THREADS)
+    P.seg_result[seg_base + k] = static_cast<uint32_t>(sm.seg_s[k]) | (static_cast<uint32_t>(sm.seg_e[k + skip]) << 16);
   if (tid == 0 && P.record_words && P.range_index >= 1) {
     const uint32_t h = sm.dyn_hits, l = sm.dyn_hits + sm.n_eligible;
     if (h) atomicAdd(&P.call->memo_hits, static_cast<unsigned long long>(h));
@@ -1027,7 +1056,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
   // K1 of this range is done, so the counters are final: every lane reads the same verdict
   const bool worth = memo_worthwhile(P.call->memo_lookups, P.call->memo_hits, P.range_index <= 1);
   if (blockIdx.x == 0 && tid == 0 && !worth) P.call->memo_off = 1u;
-  bool record = P.record_words != 0 && (P.range_index < 2 || worth);
+  bool record = P.record_words != 0 && (P.range_index < 2 || worth) && P.record_epoch < WORD_EPOCH_MAX;
 
   bool have = false;       // this lane holds an unfinished segment
   bool ext = false;        // the current node has children
@@ -1174,7 +1203,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
           slot->ids[2] = t2;
           for (uint32_t q = 3; q < nid; q++) slot->ids[q] = __ldcg(out + q);
           __threadfence();
-          *reinterpret_cast<volatile unsigned int *>(&slot->meta) = word_meta(seg_len, nid, true);
+          *reinterpret_cast<volatile unsigned int *>(&slot->meta) = word_meta(seg_len, nid, true, P.record_epoch);
           placed = true;
         } else if (old == WORD_CLAIMED) {
           placed = true;  // another lane is writing this slot right now (most likely the same word)
@@ -1430,6 +1459,52 @@ __device__ __forceinline__ void scatter_fetch(const EncodeParams &P, uint32_t re
   }
 }
 
+// The rare block whose ids do not fit the staging buffer: every thread writes the ids of its own segments
+// straight to the output, starting at `o`.  Rolled (it re-reads its seg_result words instead of indexing registers): it
+// must not bloat the kernel's hot loop.
+__device__ __forceinline__ void scatter_direct(const EncodeParams &P, unsigned long long first, unsigned long long n_segs,
+                                            unsigned long long o) {
+#pragma unroll 1
+  for (int j = 0; j < SCATTER_ITEMS; j++) {
+    if (first + j >= n_segs) break;
+    const uint32_t res = P.seg_result[first + j];
+    uint32_t cnt = 1u;
+    if (res >= SEG_RESULT_WORD) {
+      cnt = (res >> SEG_SLOW_INDEX_BITS) & ((res & SEG_RESULT_SLOW) ? SEG_SLOW_COUNT_MAX : 0xFu);
+      if (cnt == SEG_SLOW_COUNT_MAX && (res & SEG_RESULT_SLOW)) {
+        const uint32_t si = res & SEG_SLOW_INDEX_MASK;
+        cnt = si < P.slow_capacity ? (P.slow[si].off & ~SLOW_RESULT_INLINE) : 0u;
+      }
+    }
+    if (cnt == 0) continue;
+    if (res < SEG_RESULT_WORD) {
+      if (o < P.capacity) P.ids[o] = static_cast<int32_t>(res) - 1;
+    } else if (o + cnt <= P.capacity) {
+      scatter_fetch(P, res, cnt, P.ids + o);
+    } else {
+      // the caller's buffer ends inside this segment (the call reports WP_ERR_CAPACITY): id by id
+      int32_t tmp[WORD_MAX_IDS];
+      if (cnt <= WORD_MAX_IDS) {
+        scatter_fetch(P, res, cnt, tmp);
+        for (uint32_t t = 0; t < cnt; t++) {
+          if (o + t < P.capacity) P.ids[o + t] = tmp[t];
+        }
+      } else {  // more ids than a word slot holds: a slow entry with its ids in the arena
+        const uint32_t si = res & SEG_SLOW_INDEX_MASK;
+        if (si < P.slow_capacity) {
+          const uint4 e = *reinterpret_cast<const uint4 *>(&P.slow[si]);
+          if (static_cast<unsigned long long>(e.y) + cnt <= P.arena_capacity) {
+            for (uint32_t t = 0; t < cnt; t++) {
+              if (o + t < P.capacity) P.ids[o + t] = static_cast<int32_t>(P.arena[e.y + t]);
+            }
+          }
+        }
+      }
+    }
+    o += cnt;
+  }
+}
+
 __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParams P) {
   __shared__ ScatterSmem sm;
   const int tid = threadIdx.x;
@@ -1462,7 +1537,8 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
       if (tid < SCATTER_SEGS / 32 && pf < n_segs) prefetch_l2(P.seg_result + pf);
     }
 
-    // per-segment id counts, straight from the seg_result words (K1: 1; memo and slow: count bits)
+    // per-segment id counts, straight from the seg_result words (K1: 1; word table and slow: count bits).
+    // Items past the last segment get a word that counts zero ids (SEG_RESULT_WORD with count 0).
     uint32_t res[SCATTER_ITEMS], cnt[SCATTER_ITEMS];
     if (first + SCATTER_ITEMS <= n_segs) {
       const uint4 a = *reinterpret_cast<const uint4 *>(P.seg_result + first);
@@ -1471,18 +1547,19 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
       res[4] = c.x; res[5] = c.y; res[6] = c.z; res[7] = c.w;
     } else {
 #pragma unroll
-      for (int j = 0; j < SCATTER_ITEMS; j++) res[j] = first + j < n_segs ? P.seg_result[first + j] : 0u;
+      for (int j = 0; j < SCATTER_ITEMS; j++) res[j] = first + j < n_segs ? P.seg_result[first + j] : SEG_RESULT_WORD;
     }
-    uint32_t mine = 0;
+    uint32_t mine = 0, n_other = 0;
 #pragma unroll
     for (int j = 0; j < SCATTER_ITEMS; j++) {
-      const uint32_t slow_cnt = (res[j] >> SEG_SLOW_INDEX_BITS) & SEG_SLOW_COUNT_MAX;
-      const uint32_t word_cnt = (res[j] >> SEG_WORD_SLOT_BITS) & 0xFu;
-      uint32_t c = (res[j] & SEG_RESULT_SLOW) ? slow_cnt : ((res[j] & SEG_RESULT_WORD) ? word_cnt : 1u);
-      if (first + j >= n_segs) c = 0;
-      if ((res[j] & SEG_RESULT_SLOW) && slow_cnt == SEG_SLOW_COUNT_MAX && c != 0) {  // rare: 31 ids or more
-        const uint32_t si = res[j] & SEG_SLOW_INDEX_MASK;
-        c = si < P.slow_capacity ? (P.slow[si].off & ~SLOW_RESULT_INLINE) : 0u;  // word 0 of the result form
+      uint32_t c = 1u;
+      if (res[j] >= SEG_RESULT_WORD) {
+        c = (res[j] >> SEG_SLOW_INDEX_BITS) & ((res[j] & SEG_RESULT_SLOW) ? SEG_SLOW_COUNT_MAX : 0xFu);
+        if (c == SEG_SLOW_COUNT_MAX && (res[j] & SEG_RESULT_SLOW)) {  // rare: 31 ids or more
+          const uint32_t si = res[j] & SEG_SLOW_INDEX_MASK;
+          c = si < P.slow_capacity ? (P.slow[si].off & ~SLOW_RESULT_INLINE) : 0u;  // word 0 of the result form
+        }
+        n_other += c != 0u;
       }
       cnt[j] = c;
       mine += c;
@@ -1494,30 +1571,33 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
 
     if (total <= SCATTER_STAGE) {
       // stage in shared memory, then write out coalesced.  Ids settled by K1 are placed at once; the other
-      // segments are listed and fetched one per thread, all lanes busy (inline they would leave most
-      // lanes of a warp idle behind the few that have one).
+      // segments are listed (one reservation per warp) and fetched one per thread, all lanes busy (inline
+      // they would leave most lanes of a warp idle behind the few that have one).
+      uint32_t d = n_other;  // exclusive prefix within the warp, then + the warp's place in the list
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL, d, o);
+        if (lane >= o) d += y;
+      }
+      uint32_t wbase = 0;
+      if (lane == 31 && d) wbase = smem_add(&sm.n_desc, d);
+      d = d - n_other + __shfl_sync(FULL, wbase, 31);
 #pragma unroll
       for (int j = 0; j < SCATTER_ITEMS; j++) {
-        const bool other = (res[j] & (SEG_RESULT_SLOW | SEG_RESULT_WORD)) != 0 && cnt[j] != 0;
-        if (cnt[j] != 0 && !other) sm.stage[at] = static_cast<int32_t>(res[j]) - 1;
-        const uint32_t om = __ballot_sync(FULL, other);
-        if (om) {
-          uint32_t d = 0;
-          const int leader = __ffs(om) - 1;
-          if (lane == leader) d = smem_add(&sm.n_desc, static_cast<uint32_t>(__popc(om)));
-          d = __shfl_sync(FULL, d, leader) + __popc(om & ((1u << lane) - 1u));
-          if (other) {
-            sm.desc_pos[d] = (at << 16) | cnt[j];
-            sm.desc_src[d] = res[j];
-          }
+        if (res[j] < SEG_RESULT_WORD) {
+          sm.stage[at] = static_cast<int32_t>(res[j]) - 1;
+        } else if (cnt[j] != 0) {
+          sm.desc_pos[d] = (at << 16) | cnt[j];
+          sm.desc_src[d] = res[j];
+          d++;
         }
         at += cnt[j];
       }
       __syncthreads();
       const uint32_t n_desc = sm.n_desc;
-      for (uint32_t d = tid; d < n_desc; d += SCATTER_THREADS) {
-        const uint32_t dp = sm.desc_pos[d];
-        scatter_fetch(P, sm.desc_src[d], dp & 0xFFFFu, sm.stage + (dp >> 16));
+      for (uint32_t i = tid; i < n_desc; i += SCATTER_THREADS) {
+        const uint32_t dp = sm.desc_pos[i];
+        scatter_fetch(P, sm.desc_src[i], dp & 0xFFFFu, sm.stage + (dp >> 16));
       }
       // the ids are staged; only now the block needs its place in the output
       if (warp == 0) {
@@ -1529,8 +1609,22 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
       }
       __syncthreads();
       const unsigned long long out0 = ids_in + sm.base;
-      for (uint32_t i = tid; i < total; i += SCATTER_THREADS) {
-        if (out0 + i < P.capacity) P.ids[out0 + i] = sm.stage[i];
+      if (out0 + total <= P.capacity) {
+        // 16-byte stores: a scalar head up to the first 16-byte boundary of the output, vectors, a scalar tail
+        int32_t *dst = P.ids + out0;
+        const uint32_t head = min(total, static_cast<uint32_t>((4u - ((reinterpret_cast<uintptr_t>(dst) >> 2) & 3u)) & 3u));
+        const uint32_t n_vec = (total - head) >> 2;
+        if (tid < head) dst[tid] = sm.stage[tid];
+        for (uint32_t q = tid; q < n_vec; q += SCATTER_THREADS) {
+          const uint32_t i = head + 4u * q;
+          *reinterpret_cast<int4 *>(dst + i) = make_int4(sm.stage[i], sm.stage[i + 1], sm.stage[i + 2], sm.stage[i + 3]);
+        }
+        const uint32_t done = head + 4u * n_vec;
+        if (tid < total - done) dst[done + tid] = sm.stage[done + tid];
+      } else {
+        for (uint32_t i = tid; i < total; i += SCATTER_THREADS) {
+          if (out0 + i < P.capacity) P.ids[out0 + i] = sm.stage[i];
+        }
       }
     } else {
       // a block with unusually many ids (long words cut into many pieces): write directly
@@ -1542,37 +1636,7 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
         }
       }
       __syncthreads();
-      const unsigned long long out0 = ids_in + sm.base;
-#pragma unroll
-      for (int j = 0; j < SCATTER_ITEMS; j++) {
-        if (cnt[j] == 0) continue;
-        const unsigned long long o = out0 + at;
-        if (!(res[j] & (SEG_RESULT_SLOW | SEG_RESULT_WORD))) {
-          if (o < P.capacity) P.ids[o] = static_cast<int32_t>(res[j]) - 1;
-        } else if (o + cnt[j] <= P.capacity) {
-          scatter_fetch(P, res[j], cnt[j], P.ids + o);
-        } else {
-          // the caller's buffer ends inside this segment (the call reports WP_ERR_CAPACITY): id by id
-          int32_t tmp[WORD_MAX_IDS];
-          if (cnt[j] <= WORD_MAX_IDS) {
-            scatter_fetch(P, res[j], cnt[j], tmp);
-            for (uint32_t t = 0; t < cnt[j]; t++) {
-              if (o + t < P.capacity) P.ids[o + t] = tmp[t];
-            }
-          } else {  // more ids than a word slot holds: a slow entry with its ids in the arena
-            const uint32_t si = res[j] & SEG_SLOW_INDEX_MASK;
-            if (si < P.slow_capacity) {
-              const uint4 e = *reinterpret_cast<const uint4 *>(&P.slow[si]);
-              if (static_cast<unsigned long long>(e.y) + cnt[j] <= P.arena_capacity) {
-                for (uint32_t t = 0; t < cnt[j]; t++) {
-                  if (o + t < P.capacity) P.ids[o + t] = static_cast<int32_t>(P.arena[e.y + t]);
-                }
-              }
-            }
-          }
-        }
-        at += cnt[j];
-      }
+      scatter_direct(P, first, n_segs, ids_in + sm.base + at);
     }
   }
 }
@@ -1745,7 +1809,7 @@ uint32_t encode_tile_bytes() { return TILE; }
 uint32_t scatter_block_segments() { return SCATTER_SEGS; }
 
 cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_t stream, uint64_t *launches,
-                                cudaEvent_t *timing) {
+                                cudaEvent_t *timing, unsigned phases) {
   // the opt-in to > 48 KB of dynamic shared memory is per device (K1 stays below it, but keep it explicit)
   static bool configured[64] = {false};
   int dev = 0;
@@ -1775,35 +1839,43 @@ cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_
   cfg.stream = stream;
   cfg.attrs = attr;
 
+  if (phases != PHASE_ALL) timing = nullptr;
   if (timing) cudaEventRecord(timing[0], stream);
-  cfg.gridDim = dim3(P.n_tiles);
-  cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = sizeof(TileSmem);
-  cfg.numAttrs = window(P.words, P.persist_words_bytes, P.persist_words_ratio);
-  e = cudaLaunchKernelEx(&cfg, wp_split_kernel, P);
-  if (e != cudaSuccess) return e;
-
+  if (phases & PHASE_SPLIT) {
+    cfg.gridDim = dim3(P.n_tiles);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = sizeof(TileSmem);
+    cfg.numAttrs = window(P.words, P.persist_words_bytes, P.persist_words_ratio);
+    e = cudaLaunchKernelEx(&cfg, wp_split_kernel, P);
+    if (e != cudaSuccess) return e;
+    if (launches) *launches += 1;
+  }
   if (timing) cudaEventRecord(timing[1], stream);
-  cfg.gridDim = dim3(sm_count * WP_K2_BLOCKS);  // = resident capacity (see the launch bound): one wave, large shares
-  cfg.blockDim = dim3(MATCH_THREADS);
-  cfg.dynamicSmemBytes = 0;
-  cfg.numAttrs = window(P.vocab.edges, P.persist_edges_bytes, P.persist_edges_ratio);
-  e = cudaLaunchKernelEx(&cfg, wp_match_kernel, P);
-  if (e != cudaSuccess) return e;
+  if (phases & PHASE_MATCH) {
+    cfg.gridDim = dim3(sm_count * WP_K2_BLOCKS);  // = resident capacity (see the launch bound): one wave, large shares
+    cfg.blockDim = dim3(MATCH_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.numAttrs = window(P.vocab.edges, P.persist_edges_bytes, P.persist_edges_ratio);
+    e = cudaLaunchKernelEx(&cfg, wp_match_kernel, P);
+    if (e != cudaSuccess) return e;
 
-  cfg.gridDim = dim3(sm_count * 8);
-  cfg.blockDim = dim3(LONG_THREADS);
-  e = cudaLaunchKernelEx(&cfg, wp_long_kernel, P);
-  if (e != cudaSuccess) return e;
-
+    cfg.gridDim = dim3(sm_count * 8);
+    cfg.blockDim = dim3(LONG_THREADS);
+    e = cudaLaunchKernelEx(&cfg, wp_long_kernel, P);
+    if (e != cudaSuccess) return e;
+    if (launches) *launches += 2;
+  }
   if (timing) cudaEventRecord(timing[2], stream);
-  cfg.gridDim = dim3(sm_count * WP_K3_BLOCKS);
-  cfg.blockDim = dim3(SCATTER_THREADS);
-  cfg.numAttrs = window(P.words, P.persist_words_bytes, P.persist_words_ratio);
-  e = cudaLaunchKernelEx(&cfg, wp_scatter_kernel, P);
-  if (e != cudaSuccess) return e;
+  if (phases & PHASE_SCATTER) {
+    cfg.gridDim = dim3(sm_count * WP_K3_BLOCKS);
+    cfg.blockDim = dim3(SCATTER_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.numAttrs = window(P.words, P.persist_words_bytes, P.persist_words_ratio);
+    e = cudaLaunchKernelEx(&cfg, wp_scatter_kernel, P);
+    if (e != cudaSuccess) return e;
+    if (launches) *launches += 1;
+  }
   if (timing) cudaEventRecord(timing[3], stream);
-  if (launches) *launches += 4;
   return cudaSuccess;
 }
 

@@ -121,6 +121,8 @@ struct EncodeParams {
   uint32_t word_shift;              // 32 - log2(slots)
   uint32_t record_words;            // K2 records the words it matches (working table only)
   uint32_t range_index;             // 0, 1, 2, ... within the call
+  uint32_t accept_epoch;            // K1 uses word slots of an epoch <= this (wp_table.h); WORD_EPOCH_MAX = all
+  uint32_t record_epoch;            // epoch K2 tags its recordings with (range index + 1)
   // L2 residency hint (0 bytes = none): K1 and K3 keep the word table, K2 the edge table
   size_t persist_words_bytes, persist_edges_bytes;
   float persist_words_ratio, persist_edges_ratio;
@@ -136,10 +138,13 @@ cudaError_t launch_publish_count(const CallCounters *call, uint32_t parity, unsi
 
 uint32_t encode_tile_bytes();
 uint32_t scatter_block_segments();
-// Enqueue K1, K2, K2L, K3 for one range.  *launches is incremented per kernel launched.
-// `timing` (optional): 4 events recorded around the launches (before K1, K1|K2, K2+K2L|K3, after K3).
+// Enqueue the kernels of one range: PHASE_SPLIT = K1, PHASE_MATCH = K2 + K2L, PHASE_SCATTER = K3 (the host
+// may put the phases of a range on different streams to overlap consecutive ranges).  *launches is
+// incremented per kernel launched.  `timing` (optional, all phases only): 4 events recorded around the
+// launches (before K1, K1|K2, K2+K2L|K3, after K3).
+constexpr unsigned PHASE_SPLIT = 1u, PHASE_MATCH = 2u, PHASE_SCATTER = 4u, PHASE_ALL = 7u;
 cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_t stream, uint64_t *launches,
-                                cudaEvent_t *timing = nullptr);
+                                cudaEvent_t *timing = nullptr, unsigned phases = PHASE_ALL);
 
 // ids -> "id id id " (decimal, one space after every id).  launch_format_total adds the text length to *total
 // (zeroed by the caller); launch_format writes it to `out` (block_state: one zeroed word per
