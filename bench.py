@@ -355,6 +355,43 @@ def latency_4k(text: np.ndarray, vocab, n_slices: int = 2000):
             "call": "wp_encode_into / wp_encode_device, one 4 KiB text per call, handle reused"}
 
 
+def batch_throughput(text: np.ndarray, vocab, n_texts: int = 10000, size: int = 4096):
+    """many short texts in ONE call (wp_encode_batch): `n_texts` slices of about `size` bytes, host
+    pointers in, pinned id buffer out; every copy (packing, H2D, D2H) inside the timed call.  Checked against
+    one-call-per-text on a sample."""
+    import torch
+
+    rng = np.random.default_rng(1)
+    slices = []
+    for start in rng.integers(0, text.size - 2 * size, size=n_texts):
+        s = int(start)
+        while text[s - 1] != 0x20:
+            s += 1
+        e = s + size
+        while text[e - 1] != 0x20:
+            e -= 1
+        slices.append(text[s:e].tobytes())
+    total = sum(len(b) for b in slices)
+    prepared = vocab.batch_pointers(slices)
+    out = torch.empty(total, dtype=torch.int32, pin_memory=True).numpy()
+    offs = np.zeros(n_texts + 1, np.uint64)
+    ids, offsets = vocab.encode_batch(slices, out=out, offsets=offs, prepared=prepared)
+    ok = True
+    for i in range(0, n_texts, max(1, n_texts // 50)):
+        one = vocab.encode(slices[i])
+        ok = ok and bool(np.array_equal(one, ids[int(offsets[i]):int(offsets[i + 1])]))
+    times = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        vocab.encode_batch(slices, out=out, offsets=offs, prepared=prepared)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return {"texts": n_texts, "text_bytes": total, "ids": int(ids.size), "seconds_best_of_5": best,
+            "gb_per_s": total / best / 1e9, "texts_per_s": n_texts / best, "matches_single_calls": ok,
+            "call": "wp_encode_batch: host text pointers in (packed by the library into pinned memory), one H2D, "
+                    "one pass of the kernels, ids + per-text offsets back into a pinned buffer"}
+
+
 def dropin_and_process(text: np.ndarray, vocab_tokens, n_ids: int):
     """(1) e2e through the reference's own C++ signature: a small C++ helper (csrc/dropin_bench.cpp) reads the
     text and the vocabulary from files and times word_piece::fast::encode(std::string, std::vector<std::string>)
@@ -674,6 +711,8 @@ def main():
             try:
                 extra["configs"] = other_configs(local_rank, peak)
                 extra["configs"]["latency_4KiB"] = latency_4k(h_text.numpy(), vocab)
+                extra["configs"]["batch_10000x4KiB"] = batch_throughput(h_text.numpy(), vocab, 10000, 4096)
+                extra["configs"]["batch_100000x256B"] = batch_throughput(h_text.numpy(), vocab, 100000, 256)
                 extra.update(dropin_and_process(h_text.numpy(), vocab_tokens, n_ids))
             except Exception as e:  # the headline must survive a failing side leg
                 extra["configs_error"] = f"{type(e).__name__}: {e}"

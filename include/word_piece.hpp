@@ -36,5 +36,34 @@ void encodeExternal(const std::string &text_file,
                     const std::string &out_file,
                     size_t memory_limit);
 
+// ---- Extension, not in the reference: a vocabulary that stays on the GPU.
+// The reference's entry points are stateless — every call re-parses the vocabulary and rebuilds both hash maps
+// (fast.cpp:154-157, :21-35).  The functions above hide that behind a content-keyed cache; an Encoder makes
+// the lifetime explicit and adds the call the reference lacks: many short texts in one launch.
+class Encoder {
+ public:
+  explicit Encoder(const std::vector<std::string> &vocab, int device = 0);  // throws like encode(text, vocab)
+  static Encoder fromFile(const std::string &vocab_file, int device = 0);   // utils.cpp:123-137 line rules
+  ~Encoder();
+  Encoder(Encoder &&other) noexcept;
+  Encoder &operator=(Encoder &&other) noexcept;
+  Encoder(const Encoder &) = delete;
+  Encoder &operator=(const Encoder &) = delete;
+
+  // == fast::encode(text, vocab) for the vocabulary this object holds
+  std::vector<int> encode(const std::string &text) const;
+  // Every text encoded as encode(texts[i]) would; ids of text i are ids[offsets[i] .. offsets[i + 1]).
+  // One host->device copy, one pass of the kernels over the whole batch, one copy back.
+  void encodeBatch(const std::vector<std::string> &texts, std::vector<int> &ids, std::vector<size_t> &offsets) const;
+  std::vector<std::vector<int>> encodeBatch(const std::vector<std::string> &texts) const;
+  // == fast::decode for this vocabulary
+  std::vector<std::string> decode(const std::vector<int> &ids) const;
+  size_t vocabSize() const;
+
+ private:
+  explicit Encoder(void *handle) : handle_(handle) {}
+  void *handle_ = nullptr;  // wp_vocab* (wordpiece_b200.h)
+};
+
 }  // namespace fast
 }  // namespace word_piece

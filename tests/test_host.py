@@ -235,3 +235,34 @@ def test_pipeline_chunk_plan():
     # no space to cut at within half a chunk: no plan
     glued = text[:50_000] + b"x" * 9000 + text[50_000:]
     assert debug_plan_chunks(glued, 4096) == []
+
+
+def test_batch_packing_rule_is_exact():
+    """wp_encode_batch packs its texts into one buffer, each followed by one space, and encodes the buffer once.
+    The rule it rests on, checked here with the oracle alone (no device): the ids of the packed buffer are the
+    ids of the texts one after the other — also when a text ends inside a UTF-8 sequence, in an open word or in
+    a Han char (fast.cpp:89-91: a space resets the matcher; utf8.cpp:130-147: a cut sequence stays invalid)."""
+    import random
+
+    import textgen
+
+    hand = [b"ab", b"", b"a", b"b c", b"\xe4\xb8", b"\xad abc", b"ab\xc3", b"\xa9", b"\xe4\xb8\xad", b"a",
+            b"\xe6\x96\x87", b"", b"abc.", b".", b"   ", b"\xff", b"abc\xe2\x96", b"\x81x", "中a".encode(), b"xyz"]
+    hand_vocab = ["[UNK]", "a", "b", "ab", "##b", "##c", "abc", "中", "中a", "##a", "é", "##é", ".", "文"]
+    jobs = [(hand_vocab, hand)]
+    for seed in (1, 2, 3):
+        rng = random.Random(seed)
+        vocab = textgen.mixed_vocab(rng, 300, long_tokens=3)
+        texts = []
+        for _ in range(300):
+            n = rng.randint(0, 300)
+            t = textgen.mixed_text(rng, n, vocab, invalid_rate=0.02, long_run_rate=0.01) if n else b""
+            if t and rng.random() < 0.3:
+                t = t[: rng.randint(0, len(t))]
+            texts.append(t)
+        jobs.append((vocab, texts))
+    for vocab, texts in jobs:
+        o = Oracle(vocab)
+        whole = o.encode(b"".join(t + b" " for t in texts))
+        parts = np.concatenate([o.encode(t) for t in texts])
+        assert np.array_equal(whole, parts)

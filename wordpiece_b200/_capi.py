@@ -2,8 +2,10 @@
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
 import mmap
 import os
+import threading
 from dataclasses import dataclass
 from typing import Iterable, List, Optional, Sequence, Union
 
@@ -79,6 +81,7 @@ EXPORTED_SYMBOLS = [
     "wp_next_safe_cut",
     "wp_encode_sharded",
     "wp_encode_sharded_gather",
+    "wp_encode_batch",
     "wp_last_stats",
     "wp_set_kernel_timing",
     "wp_last_kernel_ms",
@@ -138,6 +141,8 @@ def load_library() -> C.CDLL:
     L.wp_encode_into.restype = C.c_int
     L.wp_encode_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), vp]
     L.wp_encode_device.restype = C.c_int
+    L.wp_encode_batch.argtypes = [vp, vp, vp, sz, vp, sz, vp, C.POINTER(sz)]
+    L.wp_encode_batch.restype = C.c_int
     L.wp_encode_device_async.argtypes = [vp, vp, sz, vp, sz, vp, vp]
     L.wp_encode_device_async.restype = C.c_int
     L.wp_plan_shards.argtypes = [vp, sz, sz, C.POINTER(sz)]
@@ -340,6 +345,42 @@ class Vocab:
         del keep
         return int(cnt.value)
 
+    @staticmethod
+    def batch_pointers(texts):
+        """The C arguments of a batch (pointer and length arrays), built once for repeated calls on the same
+        texts: (ptrs, lens, n, total_bytes, keepalive)."""
+        bufs = [t.encode("utf-8") if isinstance(t, str) else t for t in texts]
+        n = len(bufs)
+        keep = []
+        ptrs = (C.c_void_p * max(n, 1))()
+        lens = (C.c_size_t * max(n, 1))()
+        total = 0
+        for i, b in enumerate(bufs):
+            addr, ln, k = _buffer_address(b)
+            keep.append(k)
+            ptrs[i] = addr
+            lens[i] = ln
+            total += ln
+        return ptrs, lens, n, total, keep
+
+    def encode_batch(self, texts, out: Optional[np.ndarray] = None, offsets: Optional[np.ndarray] = None, prepared=None):
+        """Many host texts in one call -> (ids, offsets): ids of text i are ``ids[offsets[i]:offsets[i + 1]]``,
+        each text encoded exactly as ``encode`` would encode it alone.  ``wp_encode_batch``.  ``out`` may be a
+        preallocated int32 buffer (pinned memory is fastest); otherwise one id per byte is allocated.
+        ``prepared`` = the result of ``batch_pointers(texts)`` (skips the per-text Python work)."""
+        ptrs, lens, n, total, keep = prepared if prepared is not None else self.batch_pointers(texts)
+        if out is None:
+            out = np.empty(max(total, 1), np.int32)
+        if offsets is None:
+            offsets = np.zeros(n + 1, np.uint64)
+        assert out.dtype == np.int32 and out.flags.c_contiguous
+        assert offsets.dtype == np.uint64 and offsets.size >= n + 1 and offsets.flags.c_contiguous
+        cnt = C.c_size_t()
+        _check(self._L.wp_encode_batch(self._h, ptrs, lens, n, out.ctypes.data, out.size, offsets.ctypes.data,
+                                       C.byref(cnt)))
+        del keep
+        return out[: int(cnt.value)], offsets[: n + 1]
+
     def encode_device(self, d_text, d_ids=None, stream=None):
         """Device text (torch uint8 CUDA tensor) -> (torch int32 CUDA tensor of ids, count).
 
@@ -406,6 +447,7 @@ class Vocab:
 # ---- the reference's stateless entry points ---------------------------------
 
 _cache: dict = {}
+_cache_lock = threading.Lock()
 
 
 def _default_device() -> int:
@@ -432,13 +474,19 @@ def _cached_vocab(tokens: Sequence[Union[str, bytes]], device: Optional[int]) ->
             blob = "\n".join(tokens).encode("utf-8")  # all str
         except TypeError:
             blob = b"\n".join(_as_bytes(t) for t in tokens)
-    key = (dev, hash(blob), len(blob), len(tokens))
-    v = _cache.get(key)
-    if v is None:
-        if len(_cache) >= 4:
-            _cache.pop(next(iter(_cache))).close()
-        v = Vocab(tokens, device=dev)
-        _cache[key] = v
+    if blob.count(b"\n") == len(tokens) - 1 or not tokens:
+        # no token holds the separator, so the joined bytes determine the list; 128-bit digest of the content
+        key = (dev, hashlib.blake2b(blob, digest_size=16).digest(), len(blob), len(tokens))
+    else:
+        key = (dev, tuple(_as_bytes(t) for t in tokens))  # a token with a newline inside: the exact list is the key
+    with _cache_lock:
+        v = _cache.get(key)
+        if v is None:
+            if len(_cache) >= 4:
+                # (the evicted handle is closed when its last user drops it, not here: another thread may hold it)
+                _cache.pop(next(iter(_cache)))
+            v = Vocab(tokens, device=dev)
+            _cache[key] = v
     return v
 
 

@@ -54,6 +54,7 @@ struct CacheEntry {
   uint64_t key;
   size_t n_tokens;
   size_t n_bytes;
+  std::vector<std::string> tokens;  // the vocabulary itself: a hit is confirmed by comparing contents, not by the hash
   wp_vocab *handle;
 };
 
@@ -78,7 +79,7 @@ class VocabCache {
       bytes += t.size();
     }
     for (auto it = entries_.begin(); it != entries_.end(); ++it) {
-      if (it->key == h && it->n_tokens == vocab.size() && it->n_bytes == bytes) {
+      if (it->key == h && it->n_tokens == vocab.size() && it->n_bytes == bytes && it->tokens == vocab) {
         entries_.splice(entries_.begin(), entries_, it);
         return entries_.front().handle;
       }
@@ -96,7 +97,7 @@ class VocabCache {
       const int fl = wp_vocab_token_flags(handle, i);
       if (fl & 4) std::cerr << "Vocab word is malformed: " << vocab[i] << std::endl;  // utils.cpp:104
     }
-    entries_.push_front(CacheEntry{h, vocab.size(), bytes, handle});
+    entries_.push_front(CacheEntry{h, vocab.size(), bytes, vocab, handle});
     if (entries_.size() > kMaxEntries) {
       wp_vocab_destroy(entries_.back().handle);
       entries_.pop_back();
@@ -158,19 +159,53 @@ class MappedFile {
   size_t size_ = 0;
 };
 
+// A std::vector<int> of n elements whose storage has NOT been written: std::vector<int>(n) zero-fills, which
+// for the 1.1 GB of ids of a 1 GiB text means touching every page once with one thread (0.4 s, more than the
+// whole encode) before the real data overwrites it.  libstdc++ keeps three pointers; after reserve() the
+// library fills the storage (several threads, first touch included) and then moves the end pointer.  Other
+// standard libraries take the portable road: ids into a scratch buffer, then assign().
+#if defined(__GLIBCXX__)
+struct VectorTail : std::vector<int> {
+  void set_size(size_t n) { this->_M_impl._M_finish = this->_M_impl._M_start + n; }
+};
+constexpr bool kUninitializedVectors = true;
+#else
+constexpr bool kUninitializedVectors = false;
+#endif
+
 // fast.cpp:143-150
 std::vector<int> encode_buffer(wp_vocab *v, const char *text, size_t size) {
   if (size == 0) return {};
-  int32_t *ids = nullptr;
-  size_t n = 0;
-  const wp_status st = wp_encode(v, text, size, &ids, &n);
-  if (st != WP_OK) raise(st);
+  static_assert(sizeof(int) == sizeof(int32_t), "ids are 32-bit");
+  std::vector<int> out;
+  // first guess: half an id per byte (English-like text needs a quarter; small texts get the worst case, one
+  // id per byte, right away); the call reports the exact count if the guess was short
+  size_t cap = size <= (size_t(1) << 20) ? size : size / 2 + 1024;
+  for (int attempt = 0;; attempt++) {
+    size_t n = 0;
+    wp_status st;
+    if (kUninitializedVectors) {
+      out.reserve(cap);
+      st = wp_encode_into(v, text, size, reinterpret_cast<int32_t *>(out.data()), cap, &n);
+#if defined(__GLIBCXX__)
+      if (st == WP_OK) static_cast<VectorTail &>(out).set_size(n);
+#endif
+    } else {
+      std::vector<int32_t> tmp(cap);
+      st = wp_encode_into(v, text, size, tmp.data(), cap, &n);
+      if (st == WP_OK) out.assign(tmp.begin(), tmp.begin() + static_cast<std::ptrdiff_t>(n));
+    }
+    if (st == WP_ERR_CAPACITY && attempt == 0) {
+      cap = n;
+      continue;
+    }
+    if (st != WP_OK) raise(st);
+    break;
+  }
   wp_stats stats{};
   wp_last_stats(v, &stats);
   if (stats.dirty_tiles > 0)  // utf8.cpp:143-145
     std::cerr << "WARNING Input contains invalid unicode characters." << std::endl;
-  std::vector<int> out(ids, ids + n);
-  wp_free(ids);
   return out;
 }
 
@@ -181,6 +216,45 @@ bool starts_with_space(const char *p, size_t size) {
   if (c < 0x80) return (c >= 0x09 && c <= 0x0D) || c == 0x20;
   return size >= 3 && c == 0xE2 && static_cast<unsigned char>(p[1]) == 0x96 &&
          static_cast<unsigned char>(p[2]) == 0x81;  // U+2581
+}
+
+wp_vocab *create_handle(const std::vector<std::string> &vocab, int device) {
+  std::vector<const char *> ptrs(vocab.size());
+  std::vector<size_t> lens(vocab.size());
+  for (size_t i = 0; i < vocab.size(); i++) {
+    ptrs[i] = vocab[i].data();
+    lens[i] = vocab[i].size();
+  }
+  wp_vocab *handle = nullptr;
+  const wp_status st = wp_vocab_create(ptrs.data(), lens.data(), vocab.size(), device, &handle);
+  if (st != WP_OK) raise(st);
+  for (size_t i = 0; i < vocab.size(); i++) {
+    if (wp_vocab_token_flags(handle, i) & 4) std::cerr << "Vocab word is malformed: " << vocab[i] << std::endl;  // utils.cpp:104
+  }
+  return handle;
+}
+
+std::vector<std::string> decode_with(wp_vocab *v, const std::vector<int> &ids) {
+  const size_t size = wp_vocab_size(v);
+  for (int id : ids) {  // fast.cpp:171-178 diagnostics
+    if (id < 0 || static_cast<size_t>(id) > size) {
+      std::cerr << "no token " << id << std::endl;
+    } else if (static_cast<size_t>(id) < size && (wp_vocab_token_flags(v, static_cast<size_t>(id)) & 4)) {
+      std::cerr << "trying to access malformed token" << std::endl;
+    }
+  }
+  char *buf = nullptr;
+  size_t *offs = nullptr;
+  size_t n = 0;
+  static_assert(sizeof(int) == sizeof(int32_t), "ids are 32-bit");
+  const wp_status st = wp_decode(v, reinterpret_cast<const int32_t *>(ids.data()), ids.size(), &buf, &offs, &n, nullptr);
+  if (st != WP_OK) raise(st);
+  std::vector<std::string> result;
+  result.reserve(n);
+  for (size_t i = 0; i < n; i++) result.emplace_back(buf + offs[i], offs[i + 1] - offs[i]);
+  wp_free(buf);
+  wp_free(offs);
+  return result;
 }
 
 }  // namespace
@@ -203,27 +277,7 @@ std::vector<int> encode(const std::string &text_file, const std::string &vocab_f
 
 std::vector<std::string> decode(const std::string vocab_file, const std::vector<int> &ids) {
   std::lock_guard<std::mutex> lock(cache().mu);
-  wp_vocab *v = cache().get(read_vocab_lines(vocab_file));
-  const size_t size = wp_vocab_size(v);
-  for (int id : ids) {  // fast.cpp:171-178 diagnostics
-    if (id < 0 || static_cast<size_t>(id) > size) {
-      std::cerr << "no token " << id << std::endl;
-    } else if (static_cast<size_t>(id) < size && (wp_vocab_token_flags(v, static_cast<size_t>(id)) & 4)) {
-      std::cerr << "trying to access malformed token" << std::endl;
-    }
-  }
-  char *buf = nullptr;
-  size_t *offs = nullptr;
-  size_t n = 0;
-  static_assert(sizeof(int) == sizeof(int32_t), "ids are 32-bit");
-  const wp_status st = wp_decode(v, reinterpret_cast<const int32_t *>(ids.data()), ids.size(), &buf, &offs, &n, nullptr);
-  if (st != WP_OK) raise(st);
-  std::vector<std::string> result;
-  result.reserve(n);
-  for (size_t i = 0; i < n; i++) result.emplace_back(buf + offs[i], offs[i + 1] - offs[i]);
-  wp_free(buf);
-  wp_free(offs);
-  return result;
+  return decode_with(cache().get(read_vocab_lines(vocab_file)), ids);
 }
 
 void encodeExternal(const std::string &text_file,
@@ -261,6 +315,78 @@ void encodeExternal(const std::string &text_file,
     size -= batch;
   }
 }
+
+// ---- Encoder (extension): one vocabulary, resident on the GPU for the object's lifetime
+
+Encoder::Encoder(const std::vector<std::string> &vocab, int device) : handle_(create_handle(vocab, device)) {}
+
+Encoder Encoder::fromFile(const std::string &vocab_file, int device) {
+  return Encoder(static_cast<void *>(create_handle(read_vocab_lines(vocab_file), device)));
+}
+
+Encoder::~Encoder() { wp_vocab_destroy(static_cast<wp_vocab *>(handle_)); }
+
+Encoder::Encoder(Encoder &&other) noexcept : handle_(other.handle_) { other.handle_ = nullptr; }
+
+Encoder &Encoder::operator=(Encoder &&other) noexcept {
+  if (this != &other) {
+    wp_vocab_destroy(static_cast<wp_vocab *>(handle_));
+    handle_ = other.handle_;
+    other.handle_ = nullptr;
+  }
+  return *this;
+}
+
+std::vector<int> Encoder::encode(const std::string &text) const {
+  return encode_buffer(static_cast<wp_vocab *>(handle_), text.data(), text.size());
+}
+
+void Encoder::encodeBatch(const std::vector<std::string> &texts, std::vector<int> &ids, std::vector<size_t> &offsets) const {
+  wp_vocab *v = static_cast<wp_vocab *>(handle_);
+  std::vector<const char *> ptrs(texts.size());
+  std::vector<size_t> lens(texts.size());
+  size_t bytes = 0;
+  for (size_t i = 0; i < texts.size(); i++) {
+    ptrs[i] = texts[i].data();
+    lens[i] = texts[i].size();
+    bytes += lens[i];
+  }
+  offsets.assign(texts.size() + 1, 0);
+  // first guess: half an id per byte (English-like text needs a quarter); the call reports the exact count if short
+  size_t cap = bytes / 2 + 64;
+  for (int attempt = 0;; attempt++) {
+    ids.resize(cap);
+    size_t n = 0;
+    const wp_status st = wp_encode_batch(v, ptrs.data(), lens.data(), texts.size(), reinterpret_cast<int32_t *>(ids.data()),
+                                         ids.size(), offsets.data(), &n);
+    if (st == WP_ERR_CAPACITY && attempt == 0) {
+      cap = n;
+      continue;
+    }
+    if (st != WP_OK) raise(st);
+    ids.resize(n);
+    break;
+  }
+  wp_stats stats{};
+  wp_last_stats(v, &stats);
+  if (stats.dirty_tiles > 0)  // utf8.cpp:143-145
+    std::cerr << "WARNING Input contains invalid unicode characters." << std::endl;
+}
+
+std::vector<std::vector<int>> Encoder::encodeBatch(const std::vector<std::string> &texts) const {
+  std::vector<int> ids;
+  std::vector<size_t> offsets;
+  encodeBatch(texts, ids, offsets);
+  std::vector<std::vector<int>> out(texts.size());
+  for (size_t i = 0; i < texts.size(); i++) out[i].assign(ids.begin() + offsets[i], ids.begin() + offsets[i + 1]);
+  return out;
+}
+
+std::vector<std::string> Encoder::decode(const std::vector<int> &ids) const {
+  return decode_with(static_cast<wp_vocab *>(handle_), ids);
+}
+
+size_t Encoder::vocabSize() const { return wp_vocab_size(static_cast<wp_vocab *>(handle_)); }
 
 }  // namespace fast
 }  // namespace word_piece

@@ -4,12 +4,15 @@
 // CPU fallback — without a usable CUDA device every call fails loudly.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -24,6 +27,15 @@ namespace {
 thread_local std::string g_error;
 const char *const kHostOnly = "host-only vocabulary handle (device -1): encoding needs a CUDA device; there is no CPU path";
 std::atomic<uint64_t> g_launches{0};
+
+// WORDPIECE_B200_TRACE=1: wall-clock milestones of a process on stderr (where does a short job's time go?)
+void trace(const char *what) {
+  static const bool on = std::getenv("WORDPIECE_B200_TRACE") != nullptr;
+  if (!on) return;
+  static const auto t0 = std::chrono::steady_clock::now();
+  std::fprintf(stderr, "[wordpiece_b200 %8.2f ms] %s\n",
+               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), what);
+}
 
 wp_status fail(wp_status st, const std::string &msg) {
   g_error = msg;
@@ -82,11 +94,20 @@ struct wp_vocab {
   char *d_fmt = nullptr;  // wp_encode_text: the ids as decimal text
   size_t fmt_cap = 0;
   wp::CallCounters *h_call = nullptr;  // pinned
+  // wp_encode_batch: packed input (tile index, text starts, texts) in pinned host memory and its device
+  // mirror; per-text outputs (first segment, first id) on the device; the id offsets in pinned host memory
+  uint8_t *h_batch = nullptr, *d_batch = nullptr, *d_batch_out = nullptr;
+  size_t batch_cap = 0, batch_out_cap = 0;
+  unsigned long long *h_offsets = nullptr;
+  size_t offsets_cap = 0;
   // host-buffer pipeline (wp_encode_into on large texts): three chunks in flight
   struct PipeSlot {
     uint8_t *d_text = nullptr;
     int32_t *d_ids = nullptr;
     wp::CallCounters *h_call = nullptr;  // pinned
+    // staging for callers whose buffers are pageable (a std::string, a std::vector): pinned, allocated on demand
+    uint8_t *h_text = nullptr;
+    int32_t *h_ids = nullptr;
     cudaEvent_t h2d_done = nullptr, cmp_done = nullptr, d2h_done = nullptr;
   } slot[3];
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -222,6 +243,16 @@ wp_status ensure_work(wp_vocab *v, size_t need) {
   return WP_OK;
 }
 
+// A batch of texts packed into one buffer (wp_encode_batch): see EncodeParams::bounds.
+struct BatchArgs {
+  const unsigned long long *h_bounds = nullptr;  // host copy of the text starts (ascending), n_texts entries
+  size_t n_texts = 0;
+  const unsigned long long *d_bounds = nullptr;
+  const uint32_t *d_tile_bound = nullptr;
+  uint32_t *d_bound_seg = nullptr;
+  unsigned long long *d_offsets = nullptr;
+};
+
 struct EnqueueInfo {
   uint32_t n_tiles = 0;
   uint32_t n_ranges = 0;
@@ -233,7 +264,7 @@ struct EnqueueInfo {
 // `warm` = a later chunk of one pipelined call: the memo is neither cleared nor warmed up again.
 wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_t *d_ids, size_t capacity,
                          cudaStream_t stream, size_t spill_ids, EnqueueInfo *info, bool warm = false,
-                         size_t call_bytes = 0) {
+                         size_t call_bytes = 0, const BatchArgs *batch = nullptr) {
   const size_t tile = wp::encode_tile_bytes();
   const size_t n_tiles = (n_bytes + tile - 1) / tile;
   if (n_tiles > 0x7FFFFFFFull) return fail(WP_ERR_INVALID_ARG, "text too large for one call (> 2^31 tiles)");
@@ -297,6 +328,22 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   P.persist_words_ratio = use_memo ? v->persist_work_ratio : v->persist_words_ratio;
   P.persist_edges_bytes = v->persist_edges_bytes;
   P.persist_edges_ratio = v->persist_edges_ratio;
+  if (batch) {
+    P.bounds = batch->d_bounds;
+    P.tile_bound = batch->d_tile_bound;
+    P.bound_seg = batch->d_bound_seg;
+    P.id_offsets = batch->d_offsets;
+  }
+  // batch calls: the texts [i0, i1) that start in the range whose K3 was just enqueued get their id offsets
+  auto text_offsets = [&](cudaStream_t s) -> cudaError_t {
+    if (!batch) return cudaSuccess;
+    const unsigned long long lo = static_cast<unsigned long long>(P.first_tile) * tile;
+    const unsigned long long hi = lo + static_cast<unsigned long long>(P.n_tiles) * tile;
+    const unsigned long long *b = batch->h_bounds, *e = b + batch->n_texts;
+    const uint32_t i0 = static_cast<uint32_t>(std::lower_bound(b, e, lo) - b);
+    const uint32_t i1 = static_cast<uint32_t>(std::lower_bound(b, e, hi) - b);
+    return wp::launch_text_offsets(P, i0, i1, s, &launches);
+  };
   // Two small ranges first (2 MiB, 8 MiB): the first fills the word memo — its own unsettled words all go
   // through K2 — the second shows whether the text repeats its words (memo_worthwhile), so that the bulk of
   // the text, in full ranges, either finds the frequent repeats in the memo or does not pay for it.
@@ -318,17 +365,18 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   }
   const uint32_t n_ranges = static_cast<uint32_t>(ranges.size());
 
-  // OVERLAP of consecutive ranges.  K1 is bound by instruction issue, K2 and K3 by the latency of dependent
-  // loads, and none of them keeps more than half of an SM's warp slots busy, so the kernels of range r+1 and
-  // range r run side by side: every K1 goes to the caller's stream, K2/K2L/K3 to a second, higher-priority
-  // stream, and the scratch is doubled (range r uses half r & 1).  Order kept by events: K2(r) after K1(r);
-  // K1(r+2) after K3(r) (the scratch half is free); K3(r) after K3(r-1) (stream order: the id offset chain).
-  // The words K2 records while the next K1 is already running are tagged with their epoch and that K1 does
-  // not use them (wp_table.h), so no slot is read while it is written; during the warm-up ranges K1 waits
-  // for the K2 before it instead, because there the freshly recorded words are the point.  Ids do not depend
-  // on any of this: the word table is a cache of exact results.
-  bool overlap = n_ranges >= 3 && !v->timing;
-  if (const char *e = std::getenv("WORDPIECE_B200_OVERLAP")) overlap = overlap && std::atoi(e) != 0;
+  // OVERLAP of consecutive ranges — an EXPERIMENT, off unless WORDPIECE_B200_OVERLAP=1: every K1 goes to the
+  // caller's stream, K2/K2L/K3 to a second, higher-priority stream, and the scratch is doubled (range r uses
+  // half r & 1).  Order kept by events: K2(r) after K1(r); K1(r+2) after K3(r) (the scratch half is free);
+  // K3(r) after K3(r-1) (stream order: the id offset chain).  The words K2 records while the next K1 is
+  // already running are tagged with their epoch and that K1 does not use them (wp_table.h), so no slot is
+  // read while it is written; during the warm-up ranges K1 waits for the K2 before it instead.  Ids do not
+  // depend on any of this.  MEASURED (1 GiB English, B200): 9.97 ms against 7.48 ms serial.  K1's seven
+  // resident tiles hold 62 720 of an SM's 65 536 registers, so K2's and K3's persistent blocks (sized to fill
+  // the GPU on their own) only get in by pushing K1 tiles out, and all three are bound by latency at their
+  // resident warp count, not by issue slots someone else could use: sharing an SM slows each by what it gives.
+  bool overlap = false;
+  if (const char *e = std::getenv("WORDPIECE_B200_OVERLAP")) overlap = std::atoi(e) != 0 && n_ranges >= 3 && !v->timing;
   const size_t half = align_up(w.total, 256);
   st = ensure_work(v, overlap ? 2 * half : w.total);
   if (st != WP_OK) return st;
@@ -375,6 +423,7 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
         v->timing_used += 4;
       }
       WP_CUDA(wp::launch_encode_range(P, v->sm_count, stream, &launches, tev));
+      WP_CUDA(text_offsets(stream));
       continue;
     }
     // the K2 that ran (or runs) right before this K1: finished for the ranges after the warm-up ones (K1
@@ -391,6 +440,7 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
     WP_CUDA(wp::launch_encode_range(P, v->sm_count, v->s_aux, &launches, nullptr, wp::PHASE_MATCH));
     if (range < n_warmup) WP_CUDA(cudaEventRecord(v->ev_match, v->s_aux));
     WP_CUDA(wp::launch_encode_range(P, v->sm_count, v->s_aux, &launches, nullptr, wp::PHASE_SCATTER));
+    WP_CUDA(text_offsets(v->s_aux));
     WP_CUDA(cudaEventRecord(v->ev_scatter[b], v->s_aux));
   }
   if (overlap) {
@@ -436,6 +486,96 @@ wp_status run_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_t *d
     spill = n_bytes + 4096;
   }
   return fail(WP_ERR_CUDA, "internal scratch overflow");
+}
+
+// Host threads that copy between a caller's pageable memory and the pinned staging buffers of the pipeline.
+// One memcpy stream moves 5-10 GB/s (less into pages that are touched for the first time, e.g. the storage of
+// a fresh std::vector), a quarter of what PCIe 5 x16 takes: the copy is cut into one slice per thread.
+// Process-wide, started on first use, never joined (the threads sleep on a condition variable).
+class CopyPool {
+ public:
+  static CopyPool &get() {
+    static CopyPool *pool = new CopyPool();  // leaked on purpose: no static-destruction order to get wrong
+    return *pool;
+  }
+  // memcpy(dst, src, n) by all threads (the caller takes a slice too); returns when every slice is done
+  void copy(void *dst, const void *src, size_t n) {
+    if (n < (size_t(1) << 20) || n_workers_ == 0) {
+      std::memcpy(dst, src, n);
+      return;
+    }
+    std::unique_lock<std::mutex> call(call_mu_);  // one copy at a time
+    const size_t parts = n_workers_ + 1;
+    const size_t slice = ((n + parts - 1) / parts + 4095) & ~size_t(4095);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      dst_ = static_cast<char *>(dst);
+      src_ = static_cast<const char *>(src);
+      n_ = n;
+      slice_ = slice;
+      pending_ = n_workers_;
+      gen_++;
+    }
+    cv_work_.notify_all();
+    std::memcpy(dst, src, slice < n ? slice : n);  // slice 0
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [&] { return pending_ == 0; });
+  }
+
+ private:
+  CopyPool() {
+    size_t n = std::thread::hardware_concurrency() / 2;
+    if (n > 8) n = 8;
+    if (const char *e = std::getenv("WORDPIECE_B200_COPY_THREADS")) {
+      const int x = std::atoi(e);
+      if (x >= 1 && x <= 64) n = static_cast<size_t>(x);
+    }
+    n_workers_ = n > 1 ? n - 1 : 0;
+    for (size_t i = 0; i < n_workers_; i++) std::thread([this, i] { work(i + 1); }).detach();
+  }
+  void work(size_t index) {
+    uint64_t seen = 0;
+    for (;;) {
+      char *dst;
+      const char *src;
+      size_t n, slice;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_work_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        dst = dst_;
+        src = src_;
+        n = n_;
+        slice = slice_;
+      }
+      const size_t lo = index * slice;
+      if (lo < n) std::memcpy(dst + lo, src + lo, n - lo < slice ? n - lo : slice);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        pending_--;
+      }
+      cv_done_.notify_one();
+    }
+  }
+  std::mutex call_mu_, mu_;
+  std::condition_variable cv_work_, cv_done_;
+  size_t n_workers_ = 0;
+  uint64_t gen_ = 0;
+  size_t pending_ = 0;
+  char *dst_ = nullptr;
+  const char *src_ = nullptr;
+  size_t n_ = 0, slice_ = 0;
+};
+
+// Is this host pointer pageable memory (neither cudaMallocHost nor cudaHostRegister memory)?  Copies from and
+// to it are staged by the driver through one thread; the pipeline stages them itself, with several.
+bool is_pageable(const void *p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
 }
 
 constexpr size_t kPipeChunk = size_t(16) << 20;  // host-buffer pipeline: text bytes per chunk (16 MiB measured best: 8/16/32 MiB -> 41.6/43.6/40.5 GB/s e2e on one box)
@@ -534,10 +674,14 @@ bool plan_chunks(const char *text, size_t n, size_t chunk, std::vector<size_t> *
   return true;
 }
 
+constexpr size_t kStageIds = kPipeChunk / 2;  // ids per pinned staging slot (32 MiB; a chunk of ordinary text has a quarter of that)
+
 // Host text -> host ids through a three-stage pipeline: while chunk i is encoded, chunk i+1 is copied in
 // and the ids of chunk i-1 are copied out (the PCIe copies, not the kernels, bound this entry point).
-// *fell_back is set if the text could not be chunked or a chunk outgrew the scratch; nothing is lost then,
-// the caller runs the single-shot path.
+// Pageable caller memory (the reference's own signature hands over a std::string and expects a std::vector)
+// is staged through pinned slots by the CopyPool: chunk i+1 -> pinned before its H2D, and the ids of chunk
+// i-2 pinned -> caller after their D2H.  *fell_back is set if the text could not be chunked or a chunk
+// outgrew the scratch; nothing is lost then, the caller runs the single-shot path.
 wp_status encode_pipelined(wp_vocab *v, const char *text, size_t n_bytes, int32_t *ids, size_t capacity,
                            size_t *n_ids, bool *fell_back) {
   *fell_back = false;
@@ -548,13 +692,21 @@ wp_status encode_pipelined(wp_vocab *v, const char *text, size_t n_bytes, int32_
   }
   wp_status st = ensure_pipeline(v);
   if (st != WP_OK) return st;
+  const bool stage_in = is_pageable(text), stage_out = capacity > 0 && is_pageable(ids);
+  for (auto &sl : v->slot) {
+    if (stage_in && !sl.h_text) WP_CUDA(cudaMallocHost(&sl.h_text, kPipeChunk));
+    if (stage_out && !sl.h_ids) WP_CUDA(cudaMallocHost(&sl.h_ids, kStageIds * sizeof(int32_t)));
+  }
+  CopyPool &pool = CopyPool::get();
   const size_t n_chunks = cuts.size() - 1;
   std::vector<EnqueueInfo> infos(n_chunks);
+  std::vector<size_t> counts(n_chunks, 0), offsets(n_chunks, 0);
   size_t total = 0;
   bool overflow = false;
   wp_stats acc{};
 
-  auto finalize = [&](size_t j) -> wp_status {
+  // chunk j's kernels are done: read its count, start the copy of its ids device -> host
+  auto start_d2h = [&](size_t j) -> wp_status {
     wp_vocab::PipeSlot &sl = v->slot[j % kPipeSlots];
     WP_CUDA(cudaEventSynchronize(sl.cmp_done));
     const size_t cnt = static_cast<size_t>(sl.h_call->ids_total[infos[j].n_ranges & 1u]);
@@ -564,12 +716,35 @@ wp_status encode_pipelined(wp_vocab *v, const char *text, size_t n_bytes, int32_
     acc.long_segments += sl.h_call->long_segments;
     acc.memo_hits += sl.h_call->memo_hits;
     acc.kernel_launches += infos[j].launches;
+    counts[j] = cnt;
+    offsets[j] = total;
     if (!overflow && cnt > 0 && total + cnt <= capacity) {
       WP_CUDA(cudaStreamWaitEvent(v->s_d2h, sl.cmp_done, 0));
-      WP_CUDA(cudaMemcpyAsync(ids + total, sl.d_ids, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, v->s_d2h));
+      if (!stage_out) {
+        WP_CUDA(cudaMemcpyAsync(ids + total, sl.d_ids, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, v->s_d2h));
+      } else if (cnt <= kStageIds) {
+        WP_CUDA(cudaMemcpyAsync(sl.h_ids, sl.d_ids, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, v->s_d2h));
+      } else {
+        // more ids than the staging slot holds (text of one- and two-byte tokens): piece by piece, synchronously
+        for (size_t done = 0; done < cnt; done += kStageIds) {
+          const size_t part = cnt - done < kStageIds ? cnt - done : kStageIds;
+          WP_CUDA(cudaMemcpyAsync(sl.h_ids, sl.d_ids + done, part * sizeof(int32_t), cudaMemcpyDeviceToHost, v->s_d2h));
+          WP_CUDA(cudaStreamSynchronize(v->s_d2h));
+          pool.copy(ids + total + done, sl.h_ids, part * sizeof(int32_t));
+        }
+        counts[j] = 0;  // already delivered
+      }
     }
     WP_CUDA(cudaEventRecord(sl.d2h_done, v->s_d2h));
     total += cnt;
+    return WP_OK;
+  };
+  // chunk j's ids have arrived in its pinned slot: hand them to the caller
+  auto deliver = [&](size_t j) -> wp_status {
+    if (!stage_out || counts[j] == 0 || overflow || offsets[j] + counts[j] > capacity) return WP_OK;
+    wp_vocab::PipeSlot &sl = v->slot[j % kPipeSlots];
+    WP_CUDA(cudaEventSynchronize(sl.d2h_done));
+    pool.copy(ids + offsets[j], sl.h_ids, counts[j] * sizeof(int32_t));
     return WP_OK;
   };
 
@@ -580,19 +755,35 @@ wp_status encode_pipelined(wp_vocab *v, const char *text, size_t n_bytes, int32_
       WP_CUDA(cudaStreamWaitEvent(v->s_h2d, sl.d2h_done, 0));
       WP_CUDA(cudaStreamWaitEvent(v->stream, sl.d2h_done, 0));
     }
-    WP_CUDA(cudaMemcpyAsync(sl.d_text, text + begin, len, cudaMemcpyHostToDevice, v->s_h2d));
+    const char *src = text + begin;
+    if (stage_in) {
+      if (i >= kPipeSlots) WP_CUDA(cudaEventSynchronize(sl.h2d_done));  // the slot's previous text has left
+      pool.copy(sl.h_text, src, len);
+      src = reinterpret_cast<const char *>(sl.h_text);
+    }
+    WP_CUDA(cudaMemcpyAsync(sl.d_text, src, len, cudaMemcpyHostToDevice, v->s_h2d));
     WP_CUDA(cudaEventRecord(sl.h2d_done, v->s_h2d));
     WP_CUDA(cudaStreamWaitEvent(v->stream, sl.h2d_done, 0));
     st = enqueue_encode(v, sl.d_text, len, sl.d_ids, kPipeChunk, v->stream, 0, &infos[i], /*warm=*/i != 0, n_bytes);
     if (st != WP_OK) return st;
     WP_CUDA(cudaMemcpyAsync(sl.h_call, v->d_call, sizeof(wp::CallCounters), cudaMemcpyDeviceToHost, v->stream));
     WP_CUDA(cudaEventRecord(sl.cmp_done, v->stream));
+    if (i >= 2) {  // (before the slot of chunk i-2 is reused by chunk i+1; its D2H was started an iteration ago)
+      st = deliver(i - 2);
+      if (st != WP_OK) return st;
+    }
     if (i >= 1) {
-      st = finalize(i - 1);
+      st = start_d2h(i - 1);
       if (st != WP_OK) return st;
     }
   }
-  st = finalize(n_chunks - 1);
+  if (n_chunks >= 2) {
+    st = deliver(n_chunks - 2);
+    if (st != WP_OK) return st;
+  }
+  st = start_d2h(n_chunks - 1);
+  if (st != WP_OK) return st;
+  st = deliver(n_chunks - 1);
   if (st != WP_OK) return st;
   WP_CUDA(cudaStreamSynchronize(v->s_d2h));
   if (overflow) {
@@ -610,6 +801,7 @@ wp_status encode_pipelined(wp_vocab *v, const char *text, size_t n_bytes, int32_
 wp_status create_common(wp_vocab *v, const char *const *tokens, const size_t *lens, size_t n, int device,
                         wp_vocab **out) {
   std::string err;
+  trace("vocabulary: build tables (host)");
   if (!wp::build_host_vocab(tokens, lens, n, &v->host, &err)) {
     delete v;
     return fail(WP_ERR_EMPTY_VOCAB_WORD, err);
@@ -620,6 +812,7 @@ wp_status create_common(wp_vocab *v, const char *const *tokens, const size_t *le
     return WP_OK;
   }
   int count = 0;
+  trace("vocabulary: tables built; first CUDA call");
   if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
     delete v;
     return fail(WP_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
@@ -634,7 +827,9 @@ wp_status create_common(wp_vocab *v, const char *const *tokens, const size_t *le
     delete v;
     return fail(WP_ERR_CUDA, "cudaSetDevice failed");
   }
+  trace("vocabulary: device selected; upload");
   wp_status st = upload(v);
+  trace("vocabulary: on the device");
   if (st != WP_OK) {
     std::string keep = g_error;
     wp_vocab_destroy(v);
@@ -701,10 +896,16 @@ void wp_vocab_destroy(wp_vocab *v) {
     cudaFree(v->d_text);
     cudaFree(v->d_ids);
     if (v->h_call) cudaFreeHost(v->h_call);
+    if (v->h_batch) cudaFreeHost(v->h_batch);
+    if (v->h_offsets) cudaFreeHost(v->h_offsets);
+    cudaFree(v->d_batch);
+    cudaFree(v->d_batch_out);
     for (auto &sl : v->slot) {
       cudaFree(sl.d_text);
       cudaFree(sl.d_ids);
       if (sl.h_call) cudaFreeHost(sl.h_call);
+      if (sl.h_text) cudaFreeHost(sl.h_text);
+      if (sl.h_ids) cudaFreeHost(sl.h_ids);
       if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
       if (sl.cmp_done) cudaEventDestroy(sl.cmp_done);
       if (sl.d2h_done) cudaEventDestroy(sl.d2h_done);
@@ -791,6 +992,7 @@ wp_status wp_encode_into(wp_vocab *v, const char *text, size_t n_bytes, int32_t 
     return WP_OK;
   }
   DeviceGuard g(v->device);
+  trace("wp_encode_into: begin");
   if (n_bytes > 2 * pipe_chunk_bytes()) {
     bool fell_back = false;
     const wp_status pst = encode_pipelined(v, text, n_bytes, ids, capacity, n_ids, &fell_back);
@@ -820,10 +1022,12 @@ wp_status wp_encode_into(wp_vocab *v, const char *text, size_t n_bytes, int32_t 
   if (st != WP_OK) return st;
   *n_ids = static_cast<size_t>(v->stats.n_ids);
   if (v->stats.n_ids > capacity) return fail(WP_ERR_CAPACITY, "id buffer too small");
+  trace("wp_encode_into: ids on the device");
   if (*n_ids > 0) {
     WP_CUDA(cudaMemcpyAsync(ids, v->d_ids, *n_ids * sizeof(int32_t), cudaMemcpyDeviceToHost, v->stream));
     WP_CUDA(cudaStreamSynchronize(v->stream));
   }
+  trace("wp_encode_into: ids on the host");
   return WP_OK;
 }
 
@@ -870,8 +1074,10 @@ wp_status wp_encode(wp_vocab *v, const char *text, size_t n_bytes, int32_t **ids
     return WP_OK;
   }
   DeviceGuard g(v->device);
+  trace("wp_encode: begin");
   const wp_status st = encode_to_device_buffer(v, text, n_bytes);
   if (st != WP_OK) return st;
+  trace("wp_encode: ids on the device");
   const size_t cnt = static_cast<size_t>(v->stats.n_ids);
   int32_t *host = static_cast<int32_t *>(std::malloc(cnt ? cnt * sizeof(int32_t) : 1));
   if (!host) return fail(WP_ERR_NOMEM, "out of memory");
@@ -885,6 +1091,156 @@ wp_status wp_encode(wp_vocab *v, const char *text, size_t n_bytes, int32_t **ids
   }
   *ids_out = host;
   *n_ids = cnt;
+  return WP_OK;
+}
+
+/* ------------------------------------------------------------------ batch of texts
+ * The texts are packed into one buffer, each followed by one space: a space ends every word and resets the
+ * matcher's state (fast.cpp:89-91), a byte sequence cut short at the end of a text stays invalid in front of
+ * it, so the ids of the packed buffer are the ids of the texts one after the other.  K1 numbers the first
+ * segment of every text, K5 turns the numbers into id offsets (wp_encode.h). */
+wp_status wp_encode_batch(wp_vocab *v, const char *const *texts, const size_t *lens, size_t n_texts, int32_t *ids,
+                          size_t capacity, size_t *offsets, size_t *n_ids) {
+  if (!v || !n_ids || !offsets || (n_texts > 0 && (!texts || !lens)) || (capacity > 0 && !ids))
+    return fail(WP_ERR_INVALID_ARG, "null argument");
+  *n_ids = 0;
+  offsets[0] = 0;
+  if (v->device < 0) return fail(WP_ERR_NO_DEVICE, kHostOnly);
+  if (n_texts == 0) {
+    v->stats = wp_stats{};
+    return WP_OK;
+  }
+  if (n_texts >= (size_t(1) << 31)) return fail(WP_ERR_INVALID_ARG, "too many texts in one batch (>= 2^31)");
+  size_t packed = n_texts;  // one separator per text
+  for (size_t i = 0; i < n_texts; i++) {
+    if (lens[i] > 0 && !texts[i]) return fail(WP_ERR_INVALID_ARG, "null text");
+    if (packed + lens[i] < packed) return fail(WP_ERR_INVALID_ARG, "batch too large");
+    packed += lens[i];
+  }
+  DeviceGuard g(v->device);
+  const size_t tile = wp::encode_tile_bytes();
+  const size_t n_tiles = (packed + tile - 1) / tile;
+  // input block: tile index | text starts | packed texts (16-byte aligned for K1's vector loads)
+  const size_t off_bounds = align_up((n_tiles + 1) * sizeof(uint32_t), 256);
+  const size_t off_text = align_up(off_bounds + n_texts * sizeof(unsigned long long), 256);
+  const size_t in_bytes = off_text + packed;
+  if (in_bytes > v->batch_cap) {
+    if (v->h_batch) cudaFreeHost(v->h_batch);
+    cudaFree(v->d_batch);
+    v->h_batch = v->d_batch = nullptr;
+    v->batch_cap = 0;
+    const size_t cap = in_bytes + in_bytes / 4 + 4096;
+    WP_CUDA(cudaMallocHost(&v->h_batch, cap));
+    WP_CUDA(cudaMalloc(&v->d_batch, cap));
+    v->batch_cap = cap;
+  }
+  const size_t off_offsets = align_up(n_texts * sizeof(uint32_t), 256);
+  const size_t out_bytes = off_offsets + (n_texts + 1) * sizeof(unsigned long long);
+  if (out_bytes > v->batch_out_cap) {
+    cudaFree(v->d_batch_out);
+    v->d_batch_out = nullptr;
+    v->batch_out_cap = 0;
+    const size_t cap = out_bytes + out_bytes / 4 + 256;
+    WP_CUDA(cudaMalloc(&v->d_batch_out, cap));
+    v->batch_out_cap = cap;
+  }
+  if (n_texts + 1 > v->offsets_cap) {
+    if (v->h_offsets) cudaFreeHost(v->h_offsets);
+    v->h_offsets = nullptr;
+    v->offsets_cap = 0;
+    const size_t cap = n_texts + 1 + n_texts / 4 + 64;
+    WP_CUDA(cudaMallocHost(&v->h_offsets, cap * sizeof(unsigned long long)));
+    v->offsets_cap = cap;
+  }
+  uint32_t *h_tile_bound = reinterpret_cast<uint32_t *>(v->h_batch);
+  unsigned long long *h_bounds = reinterpret_cast<unsigned long long *>(v->h_batch + off_bounds);
+  char *h_text = reinterpret_cast<char *>(v->h_batch + off_text);
+  {
+    unsigned long long at = 0;
+    for (size_t i = 0; i < n_texts; i++) {
+      h_bounds[i] = at;
+      at += lens[i] + 1;
+    }
+    // the copies themselves: several host threads for a large batch (one memcpy stream fills ~1/4 of PCIe)
+    auto pack = [&](size_t i0, size_t i1) {
+      for (size_t i = i0; i < i1; i++) {
+        char *dst = h_text + h_bounds[i];
+        if (lens[i]) std::memcpy(dst, texts[i], lens[i]);
+        dst[lens[i]] = ' ';
+      }
+    };
+    size_t n_thr = 1;
+    if (packed >= (size_t(4) << 20)) {
+      n_thr = std::thread::hardware_concurrency() / 2;
+      if (n_thr > 8) n_thr = 8;
+      if (n_thr < 1) n_thr = 1;
+    }
+    if (n_thr == 1) {
+      pack(0, n_texts);
+    } else {
+      std::vector<std::thread> pool;
+      size_t begin = 0;
+      for (size_t t = 0; t < n_thr; t++) {  // equal byte shares
+        const unsigned long long until = static_cast<unsigned long long>(packed) * (t + 1) / n_thr;
+        const size_t end = t + 1 == n_thr ? n_texts : static_cast<size_t>(std::lower_bound(h_bounds, h_bounds + n_texts, until) - h_bounds);
+        if (end > begin) pool.emplace_back(pack, begin, end);
+        begin = end > begin ? end : begin;
+      }
+      for (auto &t : pool) t.join();
+    }
+    // tile_bound[t] = first text that starts at or after byte t * tile
+    size_t i = 0;
+    for (size_t t = 0; t <= n_tiles; t++) {
+      const unsigned long long lo = static_cast<unsigned long long>(t) * tile;
+      while (i < n_texts && h_bounds[i] < lo) i++;
+      h_tile_bound[t] = static_cast<uint32_t>(i);
+    }
+  }
+  size_t want = capacity < packed ? capacity : packed;  // one id per byte is the worst case
+  if (want == 0) want = 1;
+  if (want > v->ids_cap) {
+    cudaFree(v->d_ids);
+    v->d_ids = nullptr;
+    v->ids_cap = 0;
+    WP_CUDA(cudaMalloc(&v->d_ids, want * sizeof(int32_t)));
+    v->ids_cap = want;
+  }
+  BatchArgs batch;
+  batch.h_bounds = h_bounds;
+  batch.n_texts = n_texts;
+  batch.d_tile_bound = reinterpret_cast<const uint32_t *>(v->d_batch);
+  batch.d_bounds = reinterpret_cast<const unsigned long long *>(v->d_batch + off_bounds);
+  batch.d_bound_seg = reinterpret_cast<uint32_t *>(v->d_batch_out);
+  batch.d_offsets = reinterpret_cast<unsigned long long *>(v->d_batch_out + off_offsets);
+  WP_CUDA(cudaMemcpyAsync(v->d_batch, v->h_batch, in_bytes, cudaMemcpyHostToDevice, v->stream));
+  size_t spill = 0;
+  for (int attempt = 0;; attempt++) {
+    EnqueueInfo info;
+    wp_status st = enqueue_encode(v, v->d_batch + off_text, packed, v->d_ids, v->ids_cap, v->stream, spill, &info, false, 0, &batch);
+    if (st != WP_OK) return st;
+    uint64_t launches = 0;
+    WP_CUDA(wp::launch_publish_count(v->d_call, info.n_ranges & 1u, batch.d_offsets + n_texts, v->stream, &launches));
+    WP_CUDA(cudaEventRecord(v->last_done, v->stream));
+    g_launches.fetch_add(launches, std::memory_order_relaxed);
+    WP_CUDA(cudaMemcpyAsync(v->h_offsets, batch.d_offsets, (n_texts + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                            v->stream));
+    bool overflow = false;
+    st = finish_stats(v, packed, info, v->stream, &overflow);
+    if (st != WP_OK) return st;
+    v->stats.kernel_launches += launches;
+    if (!overflow) break;
+    if (attempt) return fail(WP_ERR_CUDA, "internal scratch overflow");
+    spill = packed + 4096;
+  }
+  const size_t total = static_cast<size_t>(v->h_offsets[n_texts]);
+  static_assert(sizeof(size_t) == sizeof(unsigned long long), "offsets are copied as they are");
+  std::memcpy(offsets, v->h_offsets, (n_texts + 1) * sizeof(size_t));
+  *n_ids = total;
+  if (total > capacity) return fail(WP_ERR_CAPACITY, "id buffer too small");
+  if (total > 0) {
+    WP_CUDA(cudaMemcpyAsync(ids, v->d_ids, total * sizeof(int32_t), cudaMemcpyDeviceToHost, v->stream));
+    WP_CUDA(cudaStreamSynchronize(v->stream));
+  }
   return WP_OK;
 }
 

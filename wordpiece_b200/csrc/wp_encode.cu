@@ -64,7 +64,7 @@ constexpr uint32_t SLOW_LONG = 0x8000u;          // tile slow-list flag: matched
 
 // tuning knobs (make variant DEFS=...)
 #ifndef WP_K2_BLOCKS
-#define WP_K2_BLOCKS 4                           // K2 CTAs per SM (launch bound and grid)
+#define WP_K2_BLOCKS 5                           // K2 CTAs per SM (launch bound and grid); 5 x 8 warps x 48 registers fill the register file (4: +3 %, 6 spills: +5 %)
 #endif
 #ifndef WP_K2_THREADS
 #define WP_K2_THREADS 256
@@ -80,6 +80,7 @@ constexpr int SCATTER_THREADS = 256;             // K3
 constexpr int SCATTER_ITEMS = 8;                 // segments per thread and block iteration
 constexpr int SCATTER_SEGS = SCATTER_THREADS * SCATTER_ITEMS;  // 2048
 constexpr int SCATTER_STAGE = 6144;              // ids staged in shared memory per block iteration
+constexpr int SCATTER_BIG = 64;                  // a segment with more ids (a URL, a blob) is copied by the whole block
 
 static_assert(RAW_BYTES % 16 == 0, "raw buffer is loaded in 16-byte units");
 static_assert(WORD_KEY_BYTES + 4 <= LOOKAHEAD, "key window reads stay inside the loaded bytes");
@@ -755,6 +756,12 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     const uint32_t at = static_cast<uint32_t>(sc1);
     totals = static_cast<uint32_t>(sc1 >> 32);
     uint32_t at_s = at & 0xFFFFu, at_e = at >> 16;
+    if (P.bounds != nullptr && c < NCHUNK) {
+      // batch call: the text starts of this tile are numbered after the look-back walk from the chunk's start
+      // bits and their prefix (the class masks are not needed any more; the scan above was a barrier)
+      sm.m_space[c] = starts;
+      sm.m_punct[c] = at_s;
+    }
     while (starts) {
       const int j = __ffs(starts) - 1;
       starts &= starts - 1;
@@ -918,6 +925,17 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   if (seg_base + n_segs > P.seg_capacity) {
     if (tid == 0) P.call->overflow = 1u;
     return;  // uniform
+  }
+  if (P.bounds != nullptr) {
+    // batch call: for every text that starts in this tile, the number of the first segment at or after its start
+    const size_t abs_tile = static_cast<size_t>(P.first_tile) + rel_tile;
+    const uint32_t b0 = P.tile_bound[abs_tile], b1 = P.tile_bound[abs_tile + 1];
+#pragma unroll 1
+    for (uint32_t i = b0 + tid; i < b1; i += THREADS) {
+      uint32_t q = static_cast<uint32_t>(P.bounds[i] - t0);  // < TILE, raw window position
+      if (dirty) q = sm.kept_scan[q >> 5] + __popc(sm.m_kept[q >> 5] & ((1u << (q & 31u)) - 1u));  // -> compacted
+      P.bound_seg[i] = static_cast<uint32_t>(seg_base) + sm.m_punct[q >> 5] + __popc(sm.m_space[q >> 5] & ((1u << (q & 31u)) - 1u));
+    }
   }
   // (every segment is written: the words of the unsettled ones are garbage here and are overwritten below,
   // behind a barrier, when their slow entries exist)
@@ -1228,21 +1246,30 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
 //   rounds of LONG_BLOCK raw bytes:
 //     A  every thread takes positions of the block: is it a valid ordinary-char lead, and if so the longest
 //        "##" match that starts there (all positions in parallel — only those on the greedy chain are used);
-//     B  one thread follows the chain through the block (position -> position behind its match), staging
-//        the ids; a position without a match turns the whole word into UNK (fast.cpp:79-88);
-//     C  the staged ids go to the arena, coalesced.
-constexpr int LONG_THREADS = 128;
+//     B  the chain through the block (position -> first valid lead behind its match) is a linked list; it is
+//        ranked by POINTER JUMPING instead of being followed by one thread: jump[k][i] = the piece start 2^k
+//        pieces behind i (LONG_LEVELS rounds of doubling), then the start of the chain gets rank 0 and, from
+//        the largest stride down, every ranked position ranks the position 2^k behind it — after the last
+//        round exactly the positions on the chain carry their piece number.  A chain position without a match
+//        turns the whole word into UNK (fast.cpp:79-88);
+//     C  the ids of the ranked positions go to the arena at their rank.
+constexpr int LONG_THREADS = 256;
 constexpr int LONG_BLOCK = 1024;
+constexpr int LONG_LEVELS = 10;            // 2^10 = LONG_BLOCK >= the pieces of a chain through one block
+constexpr uint32_t LONG_END = 0xFFFFu;     // jump: no successor inside the block; rank: not on the chain
+static_assert((1 << LONG_LEVELS) >= LONG_BLOCK, "the strides must reach across a whole block");
 
 struct LongSmem {
+  uint16_t jump[LONG_LEVELS][LONG_BLOCK];
+  uint16_t rank[LONG_BLOCK];
   uint32_t delta[LONG_BLOCK];  // raw bytes from a piece start to the position behind its longest match (0 = none)
   int32_t id[LONG_BLOCK];
-  int32_t stage[LONG_BLOCK];
   uint8_t code[LONG_BLOCK];    // 0 = dropped / continuation byte, 1 = lead of an ordinary char
   unsigned long long seg_end;  // raw position of the spacing char that ends the segment (or the text size)
   unsigned long long cur;      // raw position of the next piece
+  unsigned long long cur_next;
   uint32_t entry;              // index into the long list
-  uint32_t n_stage, n_out, word_first, off, finished, failed;
+  uint32_t n_round, n_out, word_first, off, finished, failed;
 };
 
 __global__ void __launch_bounds__(LONG_THREADS) wp_long_kernel(EncodeParams P) {
@@ -1265,7 +1292,6 @@ __global__ void __launch_bounds__(LONG_THREADS) wp_long_kernel(EncodeParams P) {
     gnext(tv, start, &len0, &cls0);  // the start is a valid lead of a non-space class
     if (tid == 0) {
       sm.seg_end = tv.n;
-      sm.n_stage = 0;
       sm.n_out = 0;
       sm.word_first = 0;
       sm.finished = 0;
@@ -1358,13 +1384,16 @@ __global__ void __launch_bounds__(LONG_THREADS) wp_long_kernel(EncodeParams P) {
 
     // ---- rounds
     const TextView seg{P.text, seg_end};
+    int32_t *const out = reinterpret_cast<int32_t *>(P.arena + sm.off);
     while (!sm.finished) {
       const size_t b0 = static_cast<size_t>(sm.cur);
       if (b0 >= seg_end) break;
-      const size_t b1 = min(seg_end, b0 + LONG_BLOCK);
+      const uint32_t n = static_cast<uint32_t>(min(seg_end - b0, static_cast<size_t>(LONG_BLOCK)));
+      const uint32_t n_out = sm.n_out;
       // A: every position of the block
 #pragma unroll 1
-      for (size_t q = b0 + tid; q < b1; q += LONG_THREADS) {
+      for (uint32_t i = tid; i < n; i += LONG_THREADS) {
+        const size_t q = b0 + i;
         uint32_t cls, code = 0, delta = 0;
         int32_t id = 0;
         const uint32_t b = tv.t[q];
@@ -1372,41 +1401,76 @@ __global__ void __launch_bounds__(LONG_THREADS) wp_long_kernel(EncodeParams P) {
           code = 1;
           delta = static_cast<uint32_t>(longest_match_global(V, seg, q, WP_KIND_SUFFIX, &id) - q);
         }
-        sm.code[q - b0] = static_cast<uint8_t>(code);
-        sm.delta[q - b0] = delta;
-        sm.id[q - b0] = id;
+        sm.code[i] = static_cast<uint8_t>(code);
+        sm.delta[i] = delta;
+        sm.id[i] = id;
+        sm.rank[i] = static_cast<uint16_t>(LONG_END);
       }
-      __syncthreads();
-      // B: the greedy chain through the block
       if (tid == 0) {
-        size_t cur = b0;
-        uint32_t n = 0;
-        while (cur < b1) {
-          const uint32_t i = static_cast<uint32_t>(cur - b0);
-          if (sm.code[i] == 0) {
-            cur++;
-            continue;
-          }
-          const uint32_t dl = sm.delta[i];
-          if (dl == 0) {
-            sm.failed = 1;
-            break;
-          }
-          sm.stage[n++] = sm.id[i];
-          cur += dl;
+        sm.n_round = 0;
+        sm.cur_next = b0 + n;  // (a block without a piece start: only dropped bytes)
+      }
+      __syncthreads();
+      // B: successors (the first valid lead at or behind the end of the match), doubled LONG_LEVELS - 1 times
+#pragma unroll 1
+      for (uint32_t i = tid; i < n; i += LONG_THREADS) {
+        uint32_t nx = LONG_END;
+        const uint32_t dl = sm.delta[i];
+        if (dl != 0 && dl < n - i) {
+          uint32_t t = i + dl;
+          while (t < n && sm.code[t] == 0) t++;
+          if (t < n) nx = t;
         }
-        sm.n_stage = n;
-        sm.cur = cur;
-        if (sm.failed || cur >= seg_end) sm.finished = 1;
+        sm.jump[0][i] = static_cast<uint16_t>(nx);
+      }
+      if (tid == 0) {
+        uint32_t t = 0;
+        while (t < n && sm.code[t] == 0) t++;
+        if (t < n) sm.rank[t] = 0;  // the round's first piece
       }
       __syncthreads();
-      // C: staged ids -> arena
-      if (!sm.failed) {
-        int32_t *out = reinterpret_cast<int32_t *>(P.arena + sm.off) + sm.n_out;
-        for (uint32_t i = tid; i < sm.n_stage; i += LONG_THREADS) out[i] = sm.stage[i];
+#pragma unroll 1
+      for (int k = 1; k < LONG_LEVELS; k++) {
+        for (uint32_t i = tid; i < n; i += LONG_THREADS) {
+          const uint32_t j = sm.jump[k - 1][i];
+          sm.jump[k][i] = j == LONG_END ? static_cast<uint16_t>(LONG_END) : sm.jump[k - 1][j];
+        }
+        __syncthreads();
+      }
+      // (a position ranked during a round may rank its own 2^k-th successor in the same round: the value it
+      // writes is right whenever it is written, so rounds need no stricter separation than the barrier)
+#pragma unroll 1
+      for (int k = LONG_LEVELS - 1; k >= 0; k--) {
+        for (uint32_t i = tid; i < n; i += LONG_THREADS) {
+          const uint32_t r = sm.rank[i];
+          if (r == LONG_END) continue;
+          const uint32_t j = sm.jump[k][i];
+          if (j != LONG_END) sm.rank[j] = static_cast<uint16_t>(r + (1u << k));
+        }
+        __syncthreads();
+      }
+      // C: ids of the chain; its last piece says where the next round begins
+#pragma unroll 1
+      for (uint32_t i = tid; i < n; i += LONG_THREADS) {
+        const uint32_t r = sm.rank[i];
+        if (r == LONG_END) continue;
+        const uint32_t dl = sm.delta[i];
+        if (dl == 0) {
+          sm.failed = 1;  // fast.cpp:79-88 (the chain ends here: a position without a match has no successor)
+        } else {
+          out[n_out + r] = sm.id[i];
+          if (sm.jump[0][i] == LONG_END) {
+            sm.n_round = r + 1;
+            sm.cur_next = b0 + i + dl;
+          }
+        }
       }
       __syncthreads();
-      if (tid == 0) sm.n_out += sm.n_stage;
+      if (tid == 0) {
+        sm.n_out = n_out + sm.n_round;
+        sm.cur = sm.cur_next;
+        if (sm.failed || sm.cur_next >= seg_end) sm.finished = 1;
+      }
       __syncthreads();
     }
     if (tid == 0) {
@@ -1429,6 +1493,8 @@ struct ScatterSmem {
   uint32_t desc_pos[SCATTER_SEGS];     // segments not settled by K1: stage position << 16 | id count
   uint32_t desc_src[SCATTER_SEGS];     // ... and their seg_result word (where the ids are)
   uint32_t n_desc;
+  uint32_t n_big;                      // segments with more than SCATTER_BIG ids: copied by the whole block
+  uint16_t big[SCATTER_STAGE / SCATTER_BIG + 2];  // staged path: their indices in desc_pos / desc_src
   uint32_t warp_sums[SCATTER_THREADS / 32];
   uint32_t block_index[2];
   unsigned long long base;
@@ -1460,10 +1526,12 @@ __device__ __forceinline__ void scatter_fetch(const EncodeParams &P, uint32_t re
 }
 
 // The rare block whose ids do not fit the staging buffer: every thread writes the ids of its own segments
-// straight to the output, starting at `o`.  Rolled (it re-reads its seg_result words instead of indexing registers): it
+// straight to the output, starting at `out0 + at` (segments with more than SCATTER_BIG ids are only listed).  Rolled (it re-reads its seg_result words instead of indexing registers): it
 // must not bloat the kernel's hot loop.
 __device__ __forceinline__ void scatter_direct(const EncodeParams &P, unsigned long long first, unsigned long long n_segs,
-                                            unsigned long long o) {
+                                            unsigned long long out0, uint32_t at, uint32_t *big_at, uint32_t *big_si,
+                                            uint32_t *n_big) {
+  unsigned long long o = out0 + at;
 #pragma unroll 1
   for (int j = 0; j < SCATTER_ITEMS; j++) {
     if (first + j >= n_segs) break;
@@ -1479,6 +1547,10 @@ __device__ __forceinline__ void scatter_direct(const EncodeParams &P, unsigned l
     if (cnt == 0) continue;
     if (res < SEG_RESULT_WORD) {
       if (o < P.capacity) P.ids[o] = static_cast<int32_t>(res) - 1;
+    } else if ((res & SEG_RESULT_SLOW) && cnt > SCATTER_BIG && (res & SEG_SLOW_INDEX_MASK) < P.slow_capacity) {
+      const uint32_t b = atomicAdd(n_big, 1u);  // left to the whole block (the caller copies the listed segments)
+      big_at[b] = static_cast<uint32_t>(o - out0);
+      big_si[b] = res & SEG_SLOW_INDEX_MASK;
     } else if (o + cnt <= P.capacity) {
       scatter_fetch(P, res, cnt, P.ids + o);
     } else {
@@ -1529,6 +1601,7 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
     if (tid == 0) {
       sm.block_index[(it + 1u) & 1u] = atomicAdd(&P.counters->scatter_ticket, 1u);
       sm.n_desc = 0;
+      sm.n_big = 0;
     }
     const unsigned long long first = static_cast<unsigned long long>(b) * SCATTER_SEGS + tid * SCATTER_ITEMS;
     {
@@ -1596,8 +1669,12 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
       __syncthreads();
       const uint32_t n_desc = sm.n_desc;
       for (uint32_t i = tid; i < n_desc; i += SCATTER_THREADS) {
-        const uint32_t dp = sm.desc_pos[i];
-        scatter_fetch(P, sm.desc_src[i], dp & 0xFFFFu, sm.stage + (dp >> 16));
+        const uint32_t dp = sm.desc_pos[i], src = sm.desc_src[i];
+        if ((src & SEG_RESULT_SLOW) && (dp & 0xFFFFu) > SCATTER_BIG) {
+          sm.big[atomicAdd(&sm.n_big, 1u)] = static_cast<uint16_t>(i);  // (ids in the arena; one thread would take ages)
+        } else {
+          scatter_fetch(P, src, dp & 0xFFFFu, sm.stage + (dp >> 16));
+        }
       }
       // the ids are staged; only now the block needs its place in the output
       if (warp == 0) {
@@ -1608,6 +1685,17 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
         }
       }
       __syncthreads();
+      if (sm.n_big) {  // uniform, rare: the long segments of this block, one after the other, all threads copying
+        for (uint32_t bi = 0; bi < sm.n_big; bi++) {
+          const uint32_t dp = sm.desc_pos[sm.big[bi]], si = sm.desc_src[sm.big[bi]] & SEG_SLOW_INDEX_MASK;
+          if (si >= P.slow_capacity) continue;
+          const uint4 e = *reinterpret_cast<const uint4 *>(&P.slow[si]);
+          const uint32_t cnt = dp & 0xFFFFu;
+          if ((e.x & SLOW_RESULT_INLINE) || static_cast<unsigned long long>(e.y) + cnt > P.arena_capacity) continue;
+          for (uint32_t t = tid; t < cnt; t += SCATTER_THREADS) sm.stage[(dp >> 16) + t] = static_cast<int32_t>(P.arena[e.y + t]);
+        }
+        __syncthreads();
+      }
       const unsigned long long out0 = ids_in + sm.base;
       if (out0 + total <= P.capacity) {
         // 16-byte stores: a scalar head up to the first 16-byte boundary of the output, vectors, a scalar tail
@@ -1636,9 +1724,64 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
         }
       }
       __syncthreads();
-      scatter_direct(P, first, n_segs, ids_in + sm.base + at);
+      const unsigned long long out0 = ids_in + sm.base;
+      scatter_direct(P, first, n_segs, out0, at, sm.desc_pos, sm.desc_src, &sm.n_big);
+      __syncthreads();
+      for (uint32_t bi = 0; bi < sm.n_big; bi++) {  // its long segments: (offset in the block's ids, slow index)
+        const uint32_t si = sm.desc_src[bi];
+        const unsigned long long o = out0 + sm.desc_pos[bi];
+        const uint4 e = *reinterpret_cast<const uint4 *>(&P.slow[si]);
+        const uint32_t cnt = e.x & ~SLOW_RESULT_INLINE;
+        if (static_cast<unsigned long long>(e.y) + cnt > P.arena_capacity) continue;
+        for (uint32_t t = tid; t < cnt; t += SCATTER_THREADS) {
+          if (o + t < P.capacity) P.ids[o + t] = static_cast<int32_t>(P.arena[e.y + t]);
+        }
+      }
     }
   }
+}
+
+// ======================================================= K5: text id offsets
+//
+// Batch calls (wp_encode_batch): where do the ids of every text begin?  K1 has numbered the first segment of
+// every text (bound_seg); the ids before segment s are the inclusive prefix K3 left in block_state for the
+// block before s's, plus the id counts of the segments of s's block that lie before s.  One warp per text.
+__device__ __forceinline__ uint32_t seg_id_count(const EncodeParams &P, uint32_t res) {
+  if (res < SEG_RESULT_WORD) return 1u;
+  uint32_t c = (res >> SEG_SLOW_INDEX_BITS) & ((res & SEG_RESULT_SLOW) ? SEG_SLOW_COUNT_MAX : 0xFu);
+  if (c == SEG_SLOW_COUNT_MAX && (res & SEG_RESULT_SLOW)) {  // rare: 31 ids or more, the count is in the slow entry
+    const uint32_t si = res & SEG_SLOW_INDEX_MASK;
+    c = si < P.slow_capacity ? (P.slow[si].off & ~SLOW_RESULT_INLINE) : 0u;
+  }
+  return c;
+}
+
+constexpr int OFFSET_THREADS = 128;
+
+__global__ void __launch_bounds__(OFFSET_THREADS) wp_text_offsets_kernel(EncodeParams P, uint32_t i0, uint32_t i1) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t i = i0 + blockIdx.x * (OFFSET_THREADS / 32) + (threadIdx.x >> 5);
+  if (i >= i1 || P.call->overflow) return;
+  const unsigned long long n_segs = min(P.counters->n_segs, static_cast<unsigned long long>(P.seg_capacity));
+  const unsigned long long s = min(static_cast<unsigned long long>(P.bound_seg[i]), n_segs);
+  const uint32_t blk = static_cast<uint32_t>(s / SCATTER_SEGS);
+  const unsigned long long first = static_cast<unsigned long long>(blk) * SCATTER_SEGS;
+  unsigned long long sum = 0;
+  for (unsigned long long k = first + lane; k < s; k += 32) sum += seg_id_count(P, P.seg_result[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+  if (lane == 0) {
+    const unsigned long long before = blk ? (P.block_state[blk - 1] & ((1ull << 62) - 1)) : 0ull;
+    P.id_offsets[i] = P.call->ids_total[P.range_parity] + before + sum;  // ([parity] still holds the range's first id)
+  }
+}
+
+cudaError_t launch_text_offsets(const EncodeParams &P, uint32_t i0, uint32_t i1, cudaStream_t stream, uint64_t *launches) {
+  if (i1 <= i0) return cudaSuccess;
+  const uint32_t per = OFFSET_THREADS / 32;
+  wp_text_offsets_kernel<<<(i1 - i0 + per - 1) / per, OFFSET_THREADS, 0, stream>>>(P, i0, i1);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
 }
 
 // ============================================================== K4: format

@@ -123,6 +123,14 @@ struct EncodeParams {
   uint32_t range_index;             // 0, 1, 2, ... within the call
   uint32_t accept_epoch;            // K1 uses word slots of an epoch <= this (wp_table.h); WORD_EPOCH_MAX = all
   uint32_t record_epoch;            // epoch K2 tags its recordings with (range index + 1)
+  // batch of texts in one buffer (wp_encode_batch), else bounds = nullptr: bounds[i] = byte offset at which
+  // text i starts (ascending, each preceded by a space); tile_bound[t] = index of the first text that starts in
+  // absolute tile t or later (n_tiles_total + 1 entries); K1 writes bound_seg[i] = the number, within the
+  // range, of the first segment that starts at or after bounds[i]; K5 turns that into id_offsets[i]
+  const unsigned long long *bounds;
+  const uint32_t *tile_bound;
+  uint32_t *bound_seg;
+  unsigned long long *id_offsets;
   // L2 residency hint (0 bytes = none): K1 and K3 keep the word table, K2 the edge table
   size_t persist_words_bytes, persist_edges_bytes;
   float persist_words_ratio, persist_edges_ratio;
@@ -135,6 +143,10 @@ cudaError_t launch_seed_words(const WordSlot *image, uint32_t image_slots, WordS
 // *d_out <- the id count of the call whose counters are `call` (UINT64_MAX if its scratch overflowed).
 cudaError_t launch_publish_count(const CallCounters *call, uint32_t parity, unsigned long long *d_out, cudaStream_t stream,
                                  uint64_t *launches);
+
+// K5 (batch calls): id_offsets[i] = index of the first id of text i, for the texts [i0, i1) that start in the
+// range whose K3 has just run on `stream` (same EncodeParams).
+cudaError_t launch_text_offsets(const EncodeParams &P, uint32_t i0, uint32_t i1, cudaStream_t stream, uint64_t *launches);
 
 uint32_t encode_tile_bytes();
 uint32_t scatter_block_segments();
