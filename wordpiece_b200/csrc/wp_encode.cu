@@ -27,8 +27,8 @@
 //              to the global slow list together with their clean bytes.
 // K2 wp_match_kernel (whole GPU, no tiles, no barriers)
 //   S2b match: every lane owns many slow segments and runs the greedy matcher as
-//              a FLATTENED state machine over the EDGE TRIE — one trie step (a
-//              16-byte load) per loop iteration — so a warp stays converged on
+//              a FLATTENED state machine over the EDGE TRIE — one trie step (one
+//              char, a 16-byte load) per loop iteration — so a warp stays converged on
 //              the step and chains of very different length average out over a
 //              lane's share.  Segments that left their tile's window or are very
 //              long are matched from the raw text in global memory.
@@ -175,19 +175,21 @@ __device__ __forceinline__ uint32_t class_of(uint32_t cp) { return cp_class(cp);
 
 // ------------------------------------------------------------------ trie step
 
-// One descent step: the edge (node, byte), or false.  e = {key, child, term_id, flags}.
-__device__ __forceinline__ bool trie_step(const DeviceVocab &V, uint32_t node, uint32_t byte, uint4 *e) {
-  const uint32_t key = edge_key(node, byte);
+// One descent step: the edge (node, char), or false.  e = {parent, char, child | flags, term_id}.
+__device__ __forceinline__ bool trie_step(const DeviceVocab &V, uint32_t node, uint32_t ch, uint4 *e) {
   const uint4 *tab = reinterpret_cast<const uint4 *>(V.edges);
-  uint32_t idx = edge_hash(key, V.edge_shift);
+  uint32_t idx = edge_hash(node, ch, V.edge_shift);
   uint4 v = __ldg(tab + idx);
-  while (v.x != key && v.x != EDGE_EMPTY) {  // linear probing, load factor <= 0.5
+  while (!(v.x == node && v.y == ch) && v.x != EDGE_EMPTY) {  // linear probing, load factor <= 0.25
     idx = (idx + 1) & V.edge_mask;
     v = __ldg(tab + idx);
   }
   *e = v;
-  return v.x == key;
+  return v.x == node;  // (a node number is never EDGE_EMPTY)
 }
+__device__ __forceinline__ uint32_t edge_child(const uint4 &e) { return e.z & EDGE_CHILD_MASK; }
+__device__ __forceinline__ bool edge_extends(const uint4 &e) { return (e.z & EDGE_HAS_CHILDREN) != 0; }
+__device__ __forceinline__ int32_t edge_term(const uint4 &e) { return static_cast<int32_t>(e.w); }
 
 // ------------------------------------------- raw-text lane (long segments, K2L)
 // Decoding and matching straight from the text in global memory, dropping invalid
@@ -256,19 +258,17 @@ __device__ size_t longest_match_global(const DeviceVocab &V, const TextView &tv,
     uint32_t len, cls;
     q = gnext(tv, q, &len, &cls);
     if (q >= tv.n || (!first && cls != CLS_OTHER)) break;
-    uint4 e = make_uint4(0, 0, 0, 0);
-    bool ok = true;
-    for (uint32_t i = 0; i < len && ok; i++) {
-      ok = trie_step(V, node, tv.t[q + i], &e);
-      node = e.y;
-    }
-    if (!ok) break;
+    uint4 e;
+    uint32_t ch = 0;
+    for (uint32_t i = 0; i < len; i++) ch |= static_cast<uint32_t>(tv.t[q + i]) << (8 * i);
+    if (!trie_step(V, node, ch, &e)) break;
+    node = edge_child(e);
     q += len;
-    if (static_cast<int32_t>(e.z) != WP_NO_ID) {  // tokens are whole chars: terminals sit at char ends
+    if (edge_term(e) != WP_NO_ID) {
       best = q;
-      *id = static_cast<int32_t>(e.z);
+      *id = edge_term(e);
     }
-    if (!(e.w & EDGE_HAS_CHILDREN) || (first && cls == CLS_PUNCT)) break;
+    if (!edge_extends(e) || (first && cls == CLS_PUNCT)) break;
     first = false;
   }
   return best;
@@ -1125,15 +1125,20 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
     // -- one trie step
     bool closed = true;
     if (ext && p + d < seg_len) {
+      // the char at p + d of the clean bytes (word-aligned in the arena; the word behind the text is in bounds)
+      const uint32_t at = p + d;
+      const uint32_t *tw = reinterpret_cast<const uint32_t *>(txt) + (at >> 2);
+      const uint32_t raw = __funnelshift_r(tw[0], tw[1], (at & 3u) * 8u);
+      const uint32_t cl = utf8_lead_len(raw & 0xFFu);
       uint4 e;
-      if (trie_step(V, node, txt[p + d], &e)) {
-        node = e.y;
-        d++;
-        if (static_cast<int32_t>(e.z) != WP_NO_ID) {
+      if (trie_step(V, node, edge_char(raw, cl), &e)) {
+        node = edge_child(e);
+        d += cl;
+        if (edge_term(e) != WP_NO_ID) {
           last_d = d;
-          last_id = static_cast<int32_t>(e.z);
+          last_id = edge_term(e);
         }
-        ext = (e.w & EDGE_HAS_CHILDREN) != 0;
+        ext = edge_extends(e);
         closed = !ext || p + d >= seg_len;
       }
     }

@@ -8,15 +8,17 @@
 // returns the same longest match yields the same ids.  Two structures here,
 // both over canonical UTF-8 BYTES:
 //
-//   E  the EDGE TRIE (K2, the walker): every byte-prefix of a kept token is a
-//      node; an edge (parent node, byte) -> child node lives in one open-
-//      addressed table of 16-byte slots, hashed on the 32-bit word
-//      parent << 8 | byte.  The edge carries the id of the token that ends at
-//      the child (term_id), so a longest match is a descent that remembers the
-//      last terminal seen: one dependent 16-byte load per text byte, ~15
-//      instructions a step, no key material, no length limit (tokens of any
-//      length are just deeper paths).  Node 0 is the root of the word-initial
-//      map, node 1 the root of the "##" map.
+//   E  the EDGE TRIE (K2, the walker): every CHAR-prefix of a kept token is a
+//      node; an edge (parent node, char) -> child node lives in one open-
+//      addressed table of 16-byte slots, hashed on the pair.  The char is its
+//      UTF-8 bytes packed into a word, so Cyrillic, kana and Han text walks one
+//      edge per char instead of two or three per char (tokens are whole chars,
+//      utils.cpp:81-85, so nothing ever ends inside one).  The edge carries the
+//      id of the token that ends at the child (term_id), so a longest match is a
+//      descent that remembers the last terminal seen: one dependent 16-byte
+//      load per char, no key material, no length limit (tokens of any length are
+//      just deeper paths).  Node 0 is the root of the word-initial map, node 1
+//      the root of the "##" map.
 //
 //   W  the WORD TABLE (K1): whole segment bytes (<= 16) -> the segment's ids.
 //      Its STATIC part is built from the vocabulary: a segment whose bytes are
@@ -39,19 +41,27 @@ constexpr uint32_t WP_KIND_SUFFIX = 1;       // "##" map (suffix_to_id); also it
 
 // ------------------------------------------------------------------ edge trie
 struct Edge {
-  uint32_t key;      // parent << 8 | byte; EDGE_EMPTY = free slot
-  uint32_t child;    // node reached
+  uint32_t parent;   // node the edge leaves; EDGE_EMPTY = free slot
+  uint32_t ch;       // the char: its 1..4 UTF-8 bytes, first byte in the low bits
+  uint32_t child;    // node reached (low 24 bits) | EDGE_HAS_CHILDREN: a descent that reaches a leaf stops without another probe
   int32_t term_id;   // token that ends at the child (WP_NO_ID if none); duplicates: last index wins (fast.cpp:34)
-  uint32_t flags;    // bit 0: the child has children (a descent that reaches a leaf stops without another probe)
 };
 static_assert(sizeof(Edge) == 16, "an edge is one 16-byte load");
 constexpr uint32_t EDGE_EMPTY = 0xFFFFFFFFu;
-constexpr uint32_t EDGE_HAS_CHILDREN = 1u;
+constexpr uint32_t EDGE_HAS_CHILDREN = 0x80000000u;
+constexpr uint32_t EDGE_CHILD_MASK = 0x00FFFFFFu;
 constexpr uint32_t EDGE_MAX_NODES = 1u << 24;
 
-WP_HD uint32_t edge_key(uint32_t parent, uint32_t byte) { return (parent << 8) | byte; }
-// Multiplicative hash, index from the HIGH bits (shift = 32 - log2(slots)).
-WP_HD uint32_t edge_hash(uint32_t key, uint32_t shift) { return (key * 0x9E3779B1u) >> shift; }
+// Multiply-add over the pair, one fold, index from the HIGH bits (shift = 32 - log2(slots)).
+WP_HD uint32_t edge_hash(uint32_t parent, uint32_t ch, uint32_t shift) {
+  uint32_t h = parent * 0x9E3779B1u + ch * 0x85EBCA77u;
+  h ^= h >> 15;
+  return (h * 0x2C1B3C6Du) >> shift;
+}
+// The char that starts with byte b0 of the little-endian word `raw` (bytes behind the char are ignored).
+WP_HD uint32_t edge_char(uint32_t raw, uint32_t lead_len) {
+  return lead_len >= 4u ? raw : (raw & ((1u << (8u * lead_len)) - 1u));
+}
 
 // ----------------------------------------------------------------- word table
 constexpr uint32_t WORD_KEY_BYTES = 16;
