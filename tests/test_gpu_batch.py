@@ -104,3 +104,23 @@ def test_batch_capacity_error_reports_the_count(gpu_device):
     ids, offs = v.encode_batch([b"a a a", b"a a"])
     assert ids.tolist() == [0] * 5 and offs.tolist() == [0, 3, 5]
     v.close()
+
+
+@pytest.mark.parametrize("part", [4096, 50_000])
+def test_batch_pipeline_of_parts(gpu_device, monkeypatch, part):
+    """A batch cut into many parts (part size forced down): packed, copied and encoded in a pipeline over three
+    buffer sets; offsets of later parts are rebased on the ids of the earlier ones."""
+    from wordpiece_b200 import Vocab
+
+    monkeypatch.setenv("WORDPIECE_B200_BATCH_PART", str(part))
+    rng = random.Random(part)
+    vocab = textgen.mixed_vocab(rng, 300, long_tokens=2)
+    texts = []
+    for _ in range(700):
+        n = rng.choice([0, 1, 5, 40, 300, 2000, 9000])
+        texts.append(textgen.mixed_text(rng, rng.randint(0, n), vocab, invalid_rate=0.005, long_run_rate=0.01) if n else b"")
+    v = Vocab(vocab, device=gpu_device)
+    o = Oracle(vocab)
+    _check_batch(v, o, texts, f"parts of {part}")
+    _check_batch(v, o, texts[:5], "then a small batch on the same handle")
+    v.close()

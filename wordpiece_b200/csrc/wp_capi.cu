@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <mutex>
 #include <new>
 #include <string>
@@ -96,10 +97,17 @@ struct wp_vocab {
   wp::CallCounters *h_call = nullptr;  // pinned
   // wp_encode_batch: packed input (tile index, text starts, texts) in pinned host memory and its device
   // mirror; per-text outputs (first segment, first id) on the device; the id offsets in pinned host memory
-  uint8_t *h_batch = nullptr, *d_batch = nullptr, *d_batch_out = nullptr;
-  size_t batch_cap = 0, batch_out_cap = 0;
-  unsigned long long *h_offsets = nullptr;
-  size_t offsets_cap = 0;
+  // (three sets: a large batch is cut into parts that are packed, copied and encoded in a pipeline)
+  struct BatchSlot {
+    uint8_t *h_in = nullptr, *d_in = nullptr, *d_out = nullptr;
+    size_t in_cap = 0, out_cap = 0;
+    unsigned long long *h_offsets = nullptr;
+    size_t offsets_cap = 0;
+    int32_t *d_ids = nullptr;
+    size_t ids_cap = 0;
+    wp::CallCounters *h_call = nullptr;  // pinned
+    cudaEvent_t h2d_done = nullptr, cmp_done = nullptr, d2h_done = nullptr;
+  } bslot[3];
   // host-buffer pipeline (wp_encode_into on large texts): three chunks in flight
   struct PipeSlot {
     uint8_t *d_text = nullptr;
@@ -498,28 +506,38 @@ class CopyPool {
     static CopyPool *pool = new CopyPool();  // leaked on purpose: no static-destruction order to get wrong
     return *pool;
   }
-  // memcpy(dst, src, n) by all threads (the caller takes a slice too); returns when every slice is done
+  // job(part, parts) on every thread of the pool and on the caller (part 0); returns when all parts are done
+  template <class F>
+  void run(F &&job) {
+    if (n_workers_ == 0) {
+      job(size_t(0), size_t(1));
+      return;
+    }
+    std::unique_lock<std::mutex> call(call_mu_);  // one job at a time
+    std::function<void(size_t, size_t)> f = std::ref(job);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      job_ = &f;
+      pending_ = n_workers_;
+      gen_++;
+    }
+    cv_work_.notify_all();
+    job(size_t(0), n_workers_ + 1);
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [&] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+  // memcpy(dst, src, n) in one slice per thread
   void copy(void *dst, const void *src, size_t n) {
     if (n < (size_t(1) << 20) || n_workers_ == 0) {
       std::memcpy(dst, src, n);
       return;
     }
-    std::unique_lock<std::mutex> call(call_mu_);  // one copy at a time
-    const size_t parts = n_workers_ + 1;
-    const size_t slice = ((n + parts - 1) / parts + 4095) & ~size_t(4095);
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      dst_ = static_cast<char *>(dst);
-      src_ = static_cast<const char *>(src);
-      n_ = n;
-      slice_ = slice;
-      pending_ = n_workers_;
-      gen_++;
-    }
-    cv_work_.notify_all();
-    std::memcpy(dst, src, slice < n ? slice : n);  // slice 0
-    std::unique_lock<std::mutex> lk(mu_);
-    cv_done_.wait(lk, [&] { return pending_ == 0; });
+    run([&](size_t part, size_t parts) {
+      const size_t slice = ((n + parts - 1) / parts + 4095) & ~size_t(4095);
+      const size_t lo = part * slice;
+      if (lo < n) std::memcpy(static_cast<char *>(dst) + lo, static_cast<const char *>(src) + lo, n - lo < slice ? n - lo : slice);
+    });
   }
 
  private:
@@ -536,20 +554,14 @@ class CopyPool {
   void work(size_t index) {
     uint64_t seen = 0;
     for (;;) {
-      char *dst;
-      const char *src;
-      size_t n, slice;
+      std::function<void(size_t, size_t)> *f;
       {
         std::unique_lock<std::mutex> lk(mu_);
         cv_work_.wait(lk, [&] { return gen_ != seen; });
         seen = gen_;
-        dst = dst_;
-        src = src_;
-        n = n_;
-        slice = slice_;
+        f = job_;
       }
-      const size_t lo = index * slice;
-      if (lo < n) std::memcpy(dst + lo, src + lo, n - lo < slice ? n - lo : slice);
+      (*f)(index, n_workers_ + 1);
       {
         std::lock_guard<std::mutex> lk(mu_);
         pending_--;
@@ -562,9 +574,7 @@ class CopyPool {
   size_t n_workers_ = 0;
   uint64_t gen_ = 0;
   size_t pending_ = 0;
-  char *dst_ = nullptr;
-  const char *src_ = nullptr;
-  size_t n_ = 0, slice_ = 0;
+  std::function<void(size_t, size_t)> *job_ = nullptr;
 };
 
 // Is this host pointer pageable memory (neither cudaMallocHost nor cudaHostRegister memory)?  Copies from and
@@ -896,10 +906,17 @@ void wp_vocab_destroy(wp_vocab *v) {
     cudaFree(v->d_text);
     cudaFree(v->d_ids);
     if (v->h_call) cudaFreeHost(v->h_call);
-    if (v->h_batch) cudaFreeHost(v->h_batch);
-    if (v->h_offsets) cudaFreeHost(v->h_offsets);
-    cudaFree(v->d_batch);
-    cudaFree(v->d_batch_out);
+    for (auto &b : v->bslot) {
+      if (b.h_in) cudaFreeHost(b.h_in);
+      if (b.h_offsets) cudaFreeHost(b.h_offsets);
+      if (b.h_call) cudaFreeHost(b.h_call);
+      cudaFree(b.d_in);
+      cudaFree(b.d_out);
+      cudaFree(b.d_ids);
+      if (b.h2d_done) cudaEventDestroy(b.h2d_done);
+      if (b.cmp_done) cudaEventDestroy(b.cmp_done);
+      if (b.d2h_done) cudaEventDestroy(b.d2h_done);
+    }
     for (auto &sl : v->slot) {
       cudaFree(sl.d_text);
       cudaFree(sl.d_ids);
@@ -1098,7 +1115,162 @@ wp_status wp_encode(wp_vocab *v, const char *text, size_t n_bytes, int32_t **ids
  * The texts are packed into one buffer, each followed by one space: a space ends every word and resets the
  * matcher's state (fast.cpp:89-91), a byte sequence cut short at the end of a text stays invalid in front of
  * it, so the ids of the packed buffer are the ids of the texts one after the other.  K1 numbers the first
- * segment of every text, K5 turns the numbers into id offsets (wp_encode.h). */
+ * segment of every text, K5 turns the numbers into id offsets (wp_encode.h).  A large batch is cut into parts
+ * of whole texts that go through a pipeline like the one of wp_encode_into: part k+1 is packed (all threads
+ * of the CopyPool) and copied in while part k is encoded and the ids of part k-1 are copied out. */
+}  // extern "C"
+
+namespace {
+
+constexpr size_t kBatchPart = size_t(8) << 20;  // packed bytes per part of a large batch
+
+size_t batch_part_bytes() {
+  if (const char *e = std::getenv("WORDPIECE_B200_BATCH_PART")) {  // test hook: pipeline small batches
+    const long long x = std::atoll(e);
+    if (x >= 256 && static_cast<size_t>(x) <= kBatchPart) return static_cast<size_t>(x);
+  }
+  return kBatchPart;
+}
+
+// Layout of a part's input block: tile index | text starts | packed texts (16-byte aligned for K1's vector loads)
+struct PartPlan {
+  size_t first = 0, last = 0;  // texts [first, last)
+  size_t packed = 0;           // bytes incl. one separator per text
+  size_t n_tiles = 0, off_bounds = 0, off_text = 0, in_bytes = 0, off_offsets = 0, out_bytes = 0;
+};
+
+PartPlan plan_part(const size_t *lens, size_t first, size_t last) {
+  PartPlan p;
+  p.first = first;
+  p.last = last;
+  const size_t n = last - first;
+  p.packed = n;
+  for (size_t i = first; i < last; i++) p.packed += lens[i];
+  const size_t tile = wp::encode_tile_bytes();
+  p.n_tiles = (p.packed + tile - 1) / tile;
+  p.off_bounds = align_up((p.n_tiles + 1) * sizeof(uint32_t), 256);
+  p.off_text = align_up(p.off_bounds + n * sizeof(unsigned long long), 256);
+  p.in_bytes = p.off_text + p.packed;
+  p.off_offsets = align_up(n * sizeof(uint32_t), 256);
+  p.out_bytes = p.off_offsets + (n + 1) * sizeof(unsigned long long);
+  return p;
+}
+
+wp_status ensure_batch_slot(wp_vocab::BatchSlot &b, const PartPlan &p, size_t ids_want) {
+  const size_t n = p.last - p.first;
+  if (p.in_bytes > b.in_cap) {
+    if (b.h_in) cudaFreeHost(b.h_in);
+    cudaFree(b.d_in);
+    b.h_in = b.d_in = nullptr;
+    b.in_cap = 0;
+    const size_t cap = p.in_bytes + p.in_bytes / 4 + 4096;
+    WP_CUDA(cudaMallocHost(&b.h_in, cap));
+    WP_CUDA(cudaMalloc(&b.d_in, cap));
+    b.in_cap = cap;
+  }
+  if (p.out_bytes > b.out_cap) {
+    cudaFree(b.d_out);
+    b.d_out = nullptr;
+    b.out_cap = 0;
+    const size_t cap = p.out_bytes + p.out_bytes / 4 + 256;
+    WP_CUDA(cudaMalloc(&b.d_out, cap));
+    b.out_cap = cap;
+  }
+  if (n + 1 > b.offsets_cap) {
+    if (b.h_offsets) cudaFreeHost(b.h_offsets);
+    b.h_offsets = nullptr;
+    b.offsets_cap = 0;
+    const size_t cap = n + 1 + n / 4 + 64;
+    WP_CUDA(cudaMallocHost(&b.h_offsets, cap * sizeof(unsigned long long)));
+    b.offsets_cap = cap;
+  }
+  if (ids_want > b.ids_cap) {
+    cudaFree(b.d_ids);
+    b.d_ids = nullptr;
+    b.ids_cap = 0;
+    const size_t cap = ids_want + ids_want / 8 + 256;
+    WP_CUDA(cudaMalloc(&b.d_ids, cap * sizeof(int32_t)));
+    b.ids_cap = cap;
+  }
+  if (!b.h_call) {
+    WP_CUDA(cudaMallocHost(&b.h_call, sizeof(wp::CallCounters)));
+    WP_CUDA(cudaEventCreateWithFlags(&b.h2d_done, cudaEventDisableTiming));
+    WP_CUDA(cudaEventCreateWithFlags(&b.cmp_done, cudaEventDisableTiming));
+    WP_CUDA(cudaEventCreateWithFlags(&b.d2h_done, cudaEventDisableTiming));
+  }
+  return WP_OK;
+}
+
+// texts -> the part's pinned input block (text starts, tile index, the texts with their separators)
+void pack_part(wp_vocab::BatchSlot &b, const PartPlan &p, const char *const *texts, const size_t *lens) {
+  const size_t n = p.last - p.first;
+  uint32_t *tile_bound = reinterpret_cast<uint32_t *>(b.h_in);
+  unsigned long long *bounds = reinterpret_cast<unsigned long long *>(b.h_in + p.off_bounds);
+  char *text = reinterpret_cast<char *>(b.h_in + p.off_text);
+  unsigned long long at = 0;
+  for (size_t i = 0; i < n; i++) {
+    bounds[i] = at;
+    at += lens[p.first + i] + 1;
+  }
+  auto pack = [&](size_t part, size_t parts) {  // equal byte shares, whole texts
+    const unsigned long long lo = static_cast<unsigned long long>(p.packed) * part / parts;
+    const unsigned long long hi = static_cast<unsigned long long>(p.packed) * (part + 1) / parts;
+    size_t i = static_cast<size_t>(std::lower_bound(bounds, bounds + n, lo) - bounds);
+    const size_t end = part + 1 == parts ? n : static_cast<size_t>(std::lower_bound(bounds, bounds + n, hi) - bounds);
+    for (; i < end; i++) {
+      char *dst = text + bounds[i];
+      const size_t len = lens[p.first + i];
+      if (len) std::memcpy(dst, texts[p.first + i], len);
+      dst[len] = ' ';
+    }
+  };
+  if (p.packed >= (size_t(1) << 20)) {
+    CopyPool::get().run(pack);
+  } else {
+    pack(0, 1);
+  }
+  const size_t tile = wp::encode_tile_bytes();
+  size_t i = 0;
+  for (size_t t = 0; t <= p.n_tiles; t++) {  // tile_bound[t] = first text that starts at or after byte t * tile
+    const unsigned long long lo = static_cast<unsigned long long>(t) * tile;
+    while (i < n && bounds[i] < lo) i++;
+    tile_bound[t] = static_cast<uint32_t>(i);
+  }
+}
+
+// Enqueue one part: H2D of its input block on `copy_stream`, kernels + id offsets + counters on v->stream.
+wp_status enqueue_part(wp_vocab *v, wp_vocab::BatchSlot &b, const PartPlan &p, cudaStream_t copy_stream, size_t spill,
+                       bool warm, size_t call_bytes, EnqueueInfo *info) {
+  const size_t n = p.last - p.first;
+  BatchArgs batch;
+  batch.h_bounds = reinterpret_cast<const unsigned long long *>(b.h_in + p.off_bounds);
+  batch.n_texts = n;
+  batch.d_tile_bound = reinterpret_cast<const uint32_t *>(b.d_in);
+  batch.d_bounds = reinterpret_cast<const unsigned long long *>(b.d_in + p.off_bounds);
+  batch.d_bound_seg = reinterpret_cast<uint32_t *>(b.d_out);
+  batch.d_offsets = reinterpret_cast<unsigned long long *>(b.d_out + p.off_offsets);
+  WP_CUDA(cudaMemcpyAsync(b.d_in, b.h_in, p.in_bytes, cudaMemcpyHostToDevice, copy_stream));
+  if (copy_stream != v->stream) {
+    WP_CUDA(cudaEventRecord(b.h2d_done, copy_stream));
+    WP_CUDA(cudaStreamWaitEvent(v->stream, b.h2d_done, 0));
+  }
+  wp_status st = enqueue_encode(v, b.d_in + p.off_text, p.packed, b.d_ids, b.ids_cap, v->stream, spill, info, warm, call_bytes, &batch);
+  if (st != WP_OK) return st;
+  uint64_t launches = 0;
+  WP_CUDA(wp::launch_publish_count(v->d_call, info->n_ranges & 1u, batch.d_offsets + n, v->stream, &launches));
+  WP_CUDA(cudaEventRecord(v->last_done, v->stream));
+  g_launches.fetch_add(launches, std::memory_order_relaxed);
+  info->launches += launches;
+  WP_CUDA(cudaMemcpyAsync(b.h_offsets, batch.d_offsets, (n + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, v->stream));
+  WP_CUDA(cudaMemcpyAsync(b.h_call, v->d_call, sizeof(wp::CallCounters), cudaMemcpyDeviceToHost, v->stream));
+  WP_CUDA(cudaEventRecord(b.cmp_done, v->stream));
+  return WP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 wp_status wp_encode_batch(wp_vocab *v, const char *const *texts, const size_t *lens, size_t n_texts, int32_t *ids,
                           size_t capacity, size_t *offsets, size_t *n_ids) {
   if (!v || !n_ids || !offsets || (n_texts > 0 && (!texts || !lens)) || (capacity > 0 && !ids))
@@ -1118,129 +1290,115 @@ wp_status wp_encode_batch(wp_vocab *v, const char *const *texts, const size_t *l
     packed += lens[i];
   }
   DeviceGuard g(v->device);
-  const size_t tile = wp::encode_tile_bytes();
-  const size_t n_tiles = (packed + tile - 1) / tile;
-  // input block: tile index | text starts | packed texts (16-byte aligned for K1's vector loads)
-  const size_t off_bounds = align_up((n_tiles + 1) * sizeof(uint32_t), 256);
-  const size_t off_text = align_up(off_bounds + n_texts * sizeof(unsigned long long), 256);
-  const size_t in_bytes = off_text + packed;
-  if (in_bytes > v->batch_cap) {
-    if (v->h_batch) cudaFreeHost(v->h_batch);
-    cudaFree(v->d_batch);
-    v->h_batch = v->d_batch = nullptr;
-    v->batch_cap = 0;
-    const size_t cap = in_bytes + in_bytes / 4 + 4096;
-    WP_CUDA(cudaMallocHost(&v->h_batch, cap));
-    WP_CUDA(cudaMalloc(&v->d_batch, cap));
-    v->batch_cap = cap;
-  }
-  const size_t off_offsets = align_up(n_texts * sizeof(uint32_t), 256);
-  const size_t out_bytes = off_offsets + (n_texts + 1) * sizeof(unsigned long long);
-  if (out_bytes > v->batch_out_cap) {
-    cudaFree(v->d_batch_out);
-    v->d_batch_out = nullptr;
-    v->batch_out_cap = 0;
-    const size_t cap = out_bytes + out_bytes / 4 + 256;
-    WP_CUDA(cudaMalloc(&v->d_batch_out, cap));
-    v->batch_out_cap = cap;
-  }
-  if (n_texts + 1 > v->offsets_cap) {
-    if (v->h_offsets) cudaFreeHost(v->h_offsets);
-    v->h_offsets = nullptr;
-    v->offsets_cap = 0;
-    const size_t cap = n_texts + 1 + n_texts / 4 + 64;
-    WP_CUDA(cudaMallocHost(&v->h_offsets, cap * sizeof(unsigned long long)));
-    v->offsets_cap = cap;
-  }
-  uint32_t *h_tile_bound = reinterpret_cast<uint32_t *>(v->h_batch);
-  unsigned long long *h_bounds = reinterpret_cast<unsigned long long *>(v->h_batch + off_bounds);
-  char *h_text = reinterpret_cast<char *>(v->h_batch + off_text);
-  {
-    unsigned long long at = 0;
+  trace("wp_encode_batch: begin");
+  // parts of whole texts, about kBatchPart packed bytes each (one part: the whole batch in one go)
+  std::vector<PartPlan> parts;
+  const size_t part_bytes = batch_part_bytes();
+  if (packed <= 3 * part_bytes / 2) {
+    parts.push_back(plan_part(lens, 0, n_texts));
+  } else {
+    size_t first = 0, bytes = 0;
     for (size_t i = 0; i < n_texts; i++) {
-      h_bounds[i] = at;
-      at += lens[i] + 1;
-    }
-    // the copies themselves: several host threads for a large batch (one memcpy stream fills ~1/4 of PCIe)
-    auto pack = [&](size_t i0, size_t i1) {
-      for (size_t i = i0; i < i1; i++) {
-        char *dst = h_text + h_bounds[i];
-        if (lens[i]) std::memcpy(dst, texts[i], lens[i]);
-        dst[lens[i]] = ' ';
+      bytes += lens[i] + 1;
+      if (bytes >= part_bytes || i + 1 == n_texts) {
+        parts.push_back(plan_part(lens, first, i + 1));
+        first = i + 1;
+        bytes = 0;
       }
-    };
-    size_t n_thr = 1;
-    if (packed >= (size_t(4) << 20)) {
-      n_thr = std::thread::hardware_concurrency() / 2;
-      if (n_thr > 8) n_thr = 8;
-      if (n_thr < 1) n_thr = 1;
-    }
-    if (n_thr == 1) {
-      pack(0, n_texts);
-    } else {
-      std::vector<std::thread> pool;
-      size_t begin = 0;
-      for (size_t t = 0; t < n_thr; t++) {  // equal byte shares
-        const unsigned long long until = static_cast<unsigned long long>(packed) * (t + 1) / n_thr;
-        const size_t end = t + 1 == n_thr ? n_texts : static_cast<size_t>(std::lower_bound(h_bounds, h_bounds + n_texts, until) - h_bounds);
-        if (end > begin) pool.emplace_back(pack, begin, end);
-        begin = end > begin ? end : begin;
-      }
-      for (auto &t : pool) t.join();
-    }
-    // tile_bound[t] = first text that starts at or after byte t * tile
-    size_t i = 0;
-    for (size_t t = 0; t <= n_tiles; t++) {
-      const unsigned long long lo = static_cast<unsigned long long>(t) * tile;
-      while (i < n_texts && h_bounds[i] < lo) i++;
-      h_tile_bound[t] = static_cast<uint32_t>(i);
     }
   }
-  size_t want = capacity < packed ? capacity : packed;  // one id per byte is the worst case
-  if (want == 0) want = 1;
-  if (want > v->ids_cap) {
-    cudaFree(v->d_ids);
-    v->d_ids = nullptr;
-    v->ids_cap = 0;
-    WP_CUDA(cudaMalloc(&v->d_ids, want * sizeof(int32_t)));
-    v->ids_cap = want;
-  }
-  BatchArgs batch;
-  batch.h_bounds = h_bounds;
-  batch.n_texts = n_texts;
-  batch.d_tile_bound = reinterpret_cast<const uint32_t *>(v->d_batch);
-  batch.d_bounds = reinterpret_cast<const unsigned long long *>(v->d_batch + off_bounds);
-  batch.d_bound_seg = reinterpret_cast<uint32_t *>(v->d_batch_out);
-  batch.d_offsets = reinterpret_cast<unsigned long long *>(v->d_batch_out + off_offsets);
-  WP_CUDA(cudaMemcpyAsync(v->d_batch, v->h_batch, in_bytes, cudaMemcpyHostToDevice, v->stream));
-  size_t spill = 0;
-  for (int attempt = 0;; attempt++) {
-    EnqueueInfo info;
-    wp_status st = enqueue_encode(v, v->d_batch + off_text, packed, v->d_ids, v->ids_cap, v->stream, spill, &info, false, 0, &batch);
+  const size_t n_parts = parts.size();
+  if (n_parts > 1) {
+    const wp_status st = ensure_pipeline(v);  // (its copy streams)
     if (st != WP_OK) return st;
-    uint64_t launches = 0;
-    WP_CUDA(wp::launch_publish_count(v->d_call, info.n_ranges & 1u, batch.d_offsets + n_texts, v->stream, &launches));
-    WP_CUDA(cudaEventRecord(v->last_done, v->stream));
-    g_launches.fetch_add(launches, std::memory_order_relaxed);
-    WP_CUDA(cudaMemcpyAsync(v->h_offsets, batch.d_offsets, (n_texts + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                            v->stream));
-    bool overflow = false;
-    st = finish_stats(v, packed, info, v->stream, &overflow);
-    if (st != WP_OK) return st;
-    v->stats.kernel_launches += launches;
-    if (!overflow) break;
-    if (attempt) return fail(WP_ERR_CUDA, "internal scratch overflow");
-    spill = packed + 4096;
   }
-  const size_t total = static_cast<size_t>(v->h_offsets[n_texts]);
+  std::vector<EnqueueInfo> infos(n_parts);
+  wp_stats acc{};
+  size_t total = 0;
   static_assert(sizeof(size_t) == sizeof(unsigned long long), "offsets are copied as they are");
-  std::memcpy(offsets, v->h_offsets, (n_texts + 1) * sizeof(size_t));
+
+  // part j's kernels are done: its offsets go to the caller (rebased), its ids start their way device -> host
+  auto finish_part = [&](size_t j, bool *overflow) -> wp_status {
+    wp_vocab::BatchSlot &b = v->bslot[j % 3];
+    const PartPlan &p = parts[j];
+    const size_t n = p.last - p.first;
+    WP_CUDA(cudaEventSynchronize(b.cmp_done));
+    *overflow = b.h_call->overflow != 0;
+    if (*overflow) return WP_OK;
+    const size_t cnt = static_cast<size_t>(b.h_offsets[n]);
+    for (size_t i = 0; i < n; i++) offsets[p.first + i] = total + static_cast<size_t>(b.h_offsets[i]);
+    acc.n_tiles += infos[j].n_tiles;
+    acc.dirty_tiles += b.h_call->dirty_tiles;
+    acc.long_segments += b.h_call->long_segments;
+    acc.memo_hits += b.h_call->memo_hits;
+    acc.kernel_launches += infos[j].launches;
+    cudaStream_t out_stream = n_parts > 1 ? v->s_d2h : v->stream;
+    if (cnt > 0 && total + cnt <= capacity) {
+      if (n_parts > 1) WP_CUDA(cudaStreamWaitEvent(out_stream, b.cmp_done, 0));
+      WP_CUDA(cudaMemcpyAsync(ids + total, b.d_ids, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, out_stream));
+    }
+    WP_CUDA(cudaEventRecord(b.d2h_done, out_stream));
+    total += cnt;
+    return WP_OK;
+  };
+
+  bool overflow = false;
+  for (size_t k = 0; k < n_parts && !overflow; k++) {
+    wp_vocab::BatchSlot &b = v->bslot[k % 3];
+    const PartPlan &p = parts[k];
+    const size_t want = p.packed;  // one id per byte is the worst case
+    if (k >= 3) WP_CUDA(cudaEventSynchronize(b.d2h_done));  // the slot's previous part has left (host and device buffers)
+    wp_status st = ensure_batch_slot(b, p, want);
+    if (st != WP_OK) return st;
+    pack_part(b, p, texts, lens);
+    if (k == 0) trace("wp_encode_batch: first part packed");
+    st = enqueue_part(v, b, p, n_parts > 1 ? v->s_h2d : v->stream, 0, /*warm=*/k != 0, packed, &infos[k]);
+    if (st != WP_OK) return st;
+    if (k >= 1) {
+      st = finish_part(k - 1, &overflow);
+      if (st != WP_OK) return st;
+    }
+  }
+  if (!overflow) {
+    const wp_status st = finish_part(n_parts - 1, &overflow);
+    if (st != WP_OK) return st;
+  }
+  if (overflow) {
+    // a long segment outgrew the default id spill of some part (rare): the whole batch again as ONE part with a
+    // spill as large as the text, nothing pipelined
+    WP_CUDA(cudaStreamSynchronize(v->stream));
+    if (n_parts > 1) WP_CUDA(cudaStreamSynchronize(v->s_d2h));
+    parts.assign(1, plan_part(lens, 0, n_texts));
+    infos.assign(1, EnqueueInfo{});
+    acc = wp_stats{};
+    total = 0;
+    wp_vocab::BatchSlot &b = v->bslot[0];
+    wp_status st = ensure_batch_slot(b, parts[0], packed);
+    if (st != WP_OK) return st;
+    pack_part(b, parts[0], texts, lens);
+    st = enqueue_part(v, b, parts[0], v->stream, packed + 4096, false, packed, &infos[0]);
+    if (st != WP_OK) return st;
+    WP_CUDA(cudaEventSynchronize(b.cmp_done));
+    if (b.h_call->overflow) return fail(WP_ERR_CUDA, "internal scratch overflow");
+    const size_t cnt = static_cast<size_t>(b.h_offsets[n_texts]);
+    for (size_t i = 0; i < n_texts; i++) offsets[i] = static_cast<size_t>(b.h_offsets[i]);
+    acc.n_tiles = infos[0].n_tiles;
+    acc.dirty_tiles = b.h_call->dirty_tiles;
+    acc.long_segments = b.h_call->long_segments;
+    acc.memo_hits = b.h_call->memo_hits;
+    acc.kernel_launches = infos[0].launches;
+    if (cnt > 0 && cnt <= capacity) WP_CUDA(cudaMemcpyAsync(ids, b.d_ids, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, v->stream));
+    total = cnt;
+  }
+  WP_CUDA(cudaStreamSynchronize(v->stream));
+  if (n_parts > 1) WP_CUDA(cudaStreamSynchronize(v->s_d2h));
+  trace("wp_encode_batch: ids on the host");
+  offsets[n_texts] = total;
+  v->stats = acc;
+  v->stats.n_bytes = packed;
+  v->stats.n_ids = total;
   *n_ids = total;
   if (total > capacity) return fail(WP_ERR_CAPACITY, "id buffer too small");
-  if (total > 0) {
-    WP_CUDA(cudaMemcpyAsync(ids, v->d_ids, total * sizeof(int32_t), cudaMemcpyDeviceToHost, v->stream));
-    WP_CUDA(cudaStreamSynchronize(v->stream));
-  }
   return WP_OK;
 }
 

@@ -80,7 +80,7 @@ constexpr int SCATTER_THREADS = 256;             // K3
 constexpr int SCATTER_ITEMS = 8;                 // segments per thread and block iteration
 constexpr int SCATTER_SEGS = SCATTER_THREADS * SCATTER_ITEMS;  // 2048
 constexpr int SCATTER_STAGE = 6144;              // ids staged in shared memory per block iteration
-constexpr int SCATTER_BIG = 64;                  // a segment with more ids (a URL, a blob) is copied by the whole block
+constexpr int SCATTER_BIG = 8;                   // a segment with more ids (a long word, a URL, a blob) is copied by a whole warp
 
 static_assert(RAW_BYTES % 16 == 0, "raw buffer is loaded in 16-byte units");
 static_assert(WORD_KEY_BYTES + 4 <= LOOKAHEAD, "key window reads stay inside the loaded bytes");
@@ -270,6 +270,49 @@ __device__ size_t longest_match_global(const DeviceVocab &V, const TextView &tv,
     }
     if (!edge_extends(e) || (first && cls == CLS_PUNCT)) break;
     first = false;
+  }
+  return best;
+}
+
+// The char at pos as its packed UTF-8 bytes (the edge trie's key); returns its length, 0 = invalid byte.  No class
+// is computed: for text whose chars are known to be ordinary (inside a long segment, whose end has been found).
+__device__ __forceinline__ uint32_t gchar(const TextView &tv, size_t pos, uint32_t *ch) {
+  const uint32_t b0 = tv.t[pos];
+  if (b0 < 0x80u) {
+    *ch = b0;
+    return 1;
+  }
+  const size_t rem = tv.n - pos;
+  const uint32_t b1 = rem > 1 ? tv.t[pos + 1] : 0u;
+  const uint32_t b2 = rem > 2 ? tv.t[pos + 2] : 0u;
+  const uint32_t b3 = rem > 3 ? tv.t[pos + 3] : 0u;
+  uint32_t cp = 0;
+  const uint32_t len = utf8_decode(b0, b1, b2, b3, rem > 4 ? 4u : static_cast<uint32_t>(rem), &cp);
+  *ch = edge_char(b0 | (b1 << 8) | (b2 << 16) | (b3 << 24), len);
+  return len;
+}
+
+// longest_match_global for a window inside a long segment: every valid char before tv.n (the segment's end) is an
+// ordinary char, so the walk only skips invalid bytes and never looks at classes.
+__device__ size_t longest_match_inside(const DeviceVocab &V, const TextView &tv, size_t p, uint32_t kind, int32_t *id) {
+  uint32_t node = kind;
+  size_t q = p, best = p;
+  while (q < tv.n) {
+    uint32_t ch;
+    const uint32_t len = gchar(tv, q, &ch);
+    if (len == 0) {  // dropped by the strict decoder (utf8.cpp:130-147)
+      q++;
+      continue;
+    }
+    uint4 e;
+    if (!trie_step(V, node, ch, &e)) break;
+    node = edge_child(e);
+    q += len;
+    if (edge_term(e) != WP_NO_ID) {
+      best = q;
+      *id = edge_term(e);
+    }
+    if (!edge_extends(e)) break;
   }
   return best;
 }
@@ -1084,6 +1127,16 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
   uint32_t p = 0, d = 0, node = 0, last_d = 0;          // piece start, depth, trie node, depth of the last terminal
   uint32_t nid = 0, word_first = 0, kind = WP_KIND_PREFIX, flags = 0;
   int32_t last_id = WP_NO_ID, t0 = 0, t1 = 0, t2 = 0;   // the first three ids of the segment stay in registers
+  // The text runs one char ahead of the trie: raw_cur = the four bytes at p + d, loaded while the table lookup
+  // of the char before it was in flight; raw_term = the four bytes behind the last terminal, i.e. the start of
+  // the next piece if that terminal stays the longest match.  The walk so depends on one load per char (the
+  // edge) instead of two in a row (text word, then edge).
+  uint32_t raw_cur = 0, raw_term = 0;
+  // four clean bytes at offset `at` of the segment (word-aligned in the arena; the word behind the text is in bounds)
+  auto text_at = [&](uint32_t at) {
+    const uint32_t *tw = reinterpret_cast<const uint32_t *>(txt) + (at >> 2);
+    return __funnelshift_r(tw[0], tw[1], (at & 3u) * 8u);
+  };
 
   for (;;) {
     // -- refill: lanes without a segment take the next entries of this warp's share
@@ -1102,7 +1155,8 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
           seg_len = meta & 0xFFFFu;
           out = reinterpret_cast<int32_t *>(P.arena + area);
           txt = reinterpret_cast<const uint8_t *>(P.arena + area + seg_len);
-          first_len = utf8_lead_len(txt[0]);
+          raw_cur = text_at(0);
+          first_len = utf8_lead_len(raw_cur & 0xFFu);
           have = true;
           ext = true;
           p = 0;
@@ -1125,18 +1179,17 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
     // -- one trie step
     bool closed = true;
     if (ext && p + d < seg_len) {
-      // the char at p + d of the clean bytes (word-aligned in the arena; the word behind the text is in bounds)
-      const uint32_t at = p + d;
-      const uint32_t *tw = reinterpret_cast<const uint32_t *>(txt) + (at >> 2);
-      const uint32_t raw = __funnelshift_r(tw[0], tw[1], (at & 3u) * 8u);
-      const uint32_t cl = utf8_lead_len(raw & 0xFFu);
+      const uint32_t cl = utf8_lead_len(raw_cur & 0xFFu);
+      const uint32_t raw_next = text_at(p + d + cl);  // (independent of the lookup below: both loads are in flight together)
       uint4 e;
-      if (trie_step(V, node, edge_char(raw, cl), &e)) {
+      if (trie_step(V, node, edge_char(raw_cur, cl), &e)) {
         node = edge_child(e);
         d += cl;
+        raw_cur = raw_next;
         if (edge_term(e) != WP_NO_ID) {
           last_d = d;
           last_id = edge_term(e);
+          raw_term = raw_next;
         }
         ext = edge_extends(e);
         closed = !ext || p + d >= seg_len;
@@ -1185,6 +1238,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
       kind = WP_KIND_SUFFIX;
     }
     if (!done && p < seg_len) {
+      raw_cur = mlen ? raw_term : text_at(p);  // (no match: only behind an out-of-vocabulary Han char, fast.cpp:85-88)
       d = 0;
       last_d = 0;
       node = kind;
@@ -1399,12 +1453,11 @@ __global__ void __launch_bounds__(LONG_THREADS) wp_long_kernel(EncodeParams P) {
 #pragma unroll 1
       for (uint32_t i = tid; i < n; i += LONG_THREADS) {
         const size_t q = b0 + i;
-        uint32_t cls, code = 0, delta = 0;
+        uint32_t ch, code = 0, delta = 0;
         int32_t id = 0;
-        const uint32_t b = tv.t[q];
-        if (!is_cont_byte(b) && gdecode(seg, q, &cls)) {  // (no spacing char before seg_end)
+        if (!is_cont_byte(tv.t[q]) && gchar(seg, q, &ch)) {  // a valid lead (no spacing char before seg_end: an ordinary char)
           code = 1;
-          delta = static_cast<uint32_t>(longest_match_global(V, seg, q, WP_KIND_SUFFIX, &id) - q);
+          delta = static_cast<uint32_t>(longest_match_inside(V, seg, q, WP_KIND_SUFFIX, &id) - q);
         }
         sm.code[i] = static_cast<uint8_t>(code);
         sm.delta[i] = delta;
@@ -1595,16 +1648,16 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
     if (blockIdx.x == 0 && tid == 0) P.call->ids_total[P.range_parity ^ 1u] = ids_in;
     return;
   }
-  // The ticket of the NEXT block is taken at the start of an iteration, so that its round trip is hidden
-  // behind the work on this one (two slots, used alternately).  A CTA that holds a ticket while it still
-  // works on an earlier block cannot stall the chain: its current block only waits for smaller indices.
+  // The ticket of the NEXT block is taken when only the stores of this one are left, so that its round trip is
+  // hidden behind them (two slots, used alternately).  Not earlier: every CTA with a later ticket waits in its
+  // look-back for the total of the block whose ticket is being held, and a block that copies the ids of long
+  // segments holds it for a long time (on blob-heavy text a quarter of the kernel's instructions were that spin).
   if (tid == 0) sm.block_index[0] = atomicAdd(&P.counters->scatter_ticket, 1u);
   for (uint32_t it = 0;; it++) {
     __syncthreads();
     const uint32_t b = sm.block_index[it & 1u];
     if (b >= n_blocks) break;
     if (tid == 0) {
-      sm.block_index[(it + 1u) & 1u] = atomicAdd(&P.counters->scatter_ticket, 1u);
       sm.n_desc = 0;
       sm.n_big = 0;
     }
@@ -1690,17 +1743,18 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
         }
       }
       __syncthreads();
-      if (sm.n_big) {  // uniform, rare: the long segments of this block, one after the other, all threads copying
-        for (uint32_t bi = 0; bi < sm.n_big; bi++) {
+      if (sm.n_big) {  // uniform: the longer segments of this block, one warp each
+        for (uint32_t bi = warp; bi < sm.n_big; bi += SCATTER_THREADS / 32) {
           const uint32_t dp = sm.desc_pos[sm.big[bi]], si = sm.desc_src[sm.big[bi]] & SEG_SLOW_INDEX_MASK;
           if (si >= P.slow_capacity) continue;
           const uint4 e = *reinterpret_cast<const uint4 *>(&P.slow[si]);
           const uint32_t cnt = dp & 0xFFFFu;
           if ((e.x & SLOW_RESULT_INLINE) || static_cast<unsigned long long>(e.y) + cnt > P.arena_capacity) continue;
-          for (uint32_t t = tid; t < cnt; t += SCATTER_THREADS) sm.stage[(dp >> 16) + t] = static_cast<int32_t>(P.arena[e.y + t]);
+          for (uint32_t t = lane; t < cnt; t += 32) sm.stage[(dp >> 16) + t] = static_cast<int32_t>(P.arena[e.y + t]);
         }
         __syncthreads();
       }
+      if (tid == 0) sm.block_index[(it + 1u) & 1u] = atomicAdd(&P.counters->scatter_ticket, 1u);
       const unsigned long long out0 = ids_in + sm.base;
       if (out0 + total <= P.capacity) {
         // 16-byte stores: a scalar head up to the first 16-byte boundary of the output, vectors, a scalar tail
@@ -1732,16 +1786,17 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
       const unsigned long long out0 = ids_in + sm.base;
       scatter_direct(P, first, n_segs, out0, at, sm.desc_pos, sm.desc_src, &sm.n_big);
       __syncthreads();
-      for (uint32_t bi = 0; bi < sm.n_big; bi++) {  // its long segments: (offset in the block's ids, slow index)
+      for (uint32_t bi = warp; bi < sm.n_big; bi += SCATTER_THREADS / 32) {  // its longer segments: (offset in the block's ids, slow index)
         const uint32_t si = sm.desc_src[bi];
         const unsigned long long o = out0 + sm.desc_pos[bi];
         const uint4 e = *reinterpret_cast<const uint4 *>(&P.slow[si]);
         const uint32_t cnt = e.x & ~SLOW_RESULT_INLINE;
-        if (static_cast<unsigned long long>(e.y) + cnt > P.arena_capacity) continue;
-        for (uint32_t t = tid; t < cnt; t += SCATTER_THREADS) {
+        if ((e.x & SLOW_RESULT_INLINE) || static_cast<unsigned long long>(e.y) + cnt > P.arena_capacity) continue;
+        for (uint32_t t = lane; t < cnt; t += 32) {
           if (o + t < P.capacity) P.ids[o + t] = static_cast<int32_t>(P.arena[e.y + t]);
         }
       }
+      if (tid == 0) sm.block_index[(it + 1u) & 1u] = atomicAdd(&P.counters->scatter_ticket, 1u);
     }
   }
 }
@@ -2000,14 +2055,16 @@ cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_
   }
   if (timing) cudaEventRecord(timing[1], stream);
   if (phases & PHASE_MATCH) {
-    cfg.gridDim = dim3(sm_count * WP_K2_BLOCKS);  // = resident capacity (see the launch bound): one wave, large shares
+    // = resident capacity (see the launch bound): one wave, large shares; a small range (a 4 KiB call is ONE tile)
+    // gets a grid to match — a tile has at most MAX_TILE_SLOW unsettled segments, 8 warps x 32 lanes take 256 at a time
+    cfg.gridDim = dim3(min(static_cast<unsigned>(sm_count * WP_K2_BLOCKS), P.n_tiles * 4u));
     cfg.blockDim = dim3(MATCH_THREADS);
     cfg.dynamicSmemBytes = 0;
     cfg.numAttrs = window(P.vocab.edges, P.persist_edges_bytes, P.persist_edges_ratio);
     e = cudaLaunchKernelEx(&cfg, wp_match_kernel, P);
     if (e != cudaSuccess) return e;
 
-    cfg.gridDim = dim3(sm_count * 8);
+    cfg.gridDim = dim3(min(static_cast<unsigned>(sm_count * 8), P.n_tiles * 2u + 2u));  // (one CTA per long segment, by ticket)
     cfg.blockDim = dim3(LONG_THREADS);
     e = cudaLaunchKernelEx(&cfg, wp_long_kernel, P);
     if (e != cudaSuccess) return e;
@@ -2015,7 +2072,7 @@ cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_
   }
   if (timing) cudaEventRecord(timing[2], stream);
   if (phases & PHASE_SCATTER) {
-    cfg.gridDim = dim3(sm_count * WP_K3_BLOCKS);
+    cfg.gridDim = dim3(min(static_cast<unsigned>(sm_count * WP_K3_BLOCKS), P.n_tiles * 2u));  // a tile has at most two blocks of segments
     cfg.blockDim = dim3(SCATTER_THREADS);
     cfg.dynamicSmemBytes = 0;
     cfg.numAttrs = window(P.words, P.persist_words_bytes, P.persist_words_ratio);
