@@ -590,3 +590,13 @@ def test_id_text_formatted_on_device(gpu_device):
     assert (exp == -1).any() and (exp >= 100_000).any() and (exp < 10).any()
     assert v.encode_text(b"") == b""
     v.close()
+
+
+def test_ticket_mode_is_exact(gpu_device, monkeypatch):
+    """K1's fallback order of tiles (an atomic ticket instead of the block index; the host switches to it when a
+    look-back walk gives up waiting) gives the same ids: several ranges, dirty tiles, long segments."""
+    monkeypatch.setenv("WORDPIECE_B200_TICKET", "1")
+    monkeypatch.setenv("WORDPIECE_B200_RANGE_BYTES", str(256 * 1024))
+    text, vocab = textgen.case(41, 1_500_000, invalid_rate=0.002, long_run_rate=0.01, long_tokens=4)
+    st = _check(text, vocab, gpu_device, "ticket mode")
+    assert st.n_tiles > 300

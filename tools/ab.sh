@@ -8,6 +8,7 @@ for rep in 1 2; do
   for lib in wordpiece_b200/lib/variants/libwordpiece_b200_*.so; do
     [ -e "$lib" ] || continue
     name=$(basename $lib .so); name=${name#libwordpiece_b200_}
+    [ "$name" = bounds ] && continue   # the debug build is for tools/gpu_bounds.sh
     WORDPIECE_B200_LIB=$PWD/$lib timeout -k 10 300 $B > $OUT/ab_${TAG}_${name}_$rep.json 2> $OUT/ab_${TAG}_${name}_$rep.err
   done
 done

@@ -123,6 +123,7 @@ struct wp_vocab {
   // every call on a handle shares its scratch, counters and word table: the kernels of one call must have
   // finished before those of the next begin, on whatever streams the caller enqueues them
   cudaEvent_t last_done = nullptr;
+  bool use_ticket = false;  // K1 hands its tiles out by ticket (set for good once a look-back has stalled, see wp_encode.cu)
   // overlap of consecutive ranges (see enqueue_encode): K2/K2L/K3 run on a second, high-priority stream
   cudaStream_t s_aux = nullptr;
   cudaEvent_t ev_split[2] = {nullptr, nullptr};    // K1 of the range in scratch half b is done
@@ -332,6 +333,8 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   P.word_mask = (1u << words_log2) - 1u;
   P.word_shift = 32 - words_log2;
   P.record_words = use_memo ? 1u : 0u;
+  P.use_ticket = v->use_ticket ? 1u : 0u;
+  if (const char *e = std::getenv("WORDPIECE_B200_TICKET")) P.use_ticket = std::atoi(e) != 0 ? 1u : 0u;  // test hook
   P.persist_words_bytes = use_memo ? v->persist_work_bytes : v->persist_words_bytes;
   P.persist_words_ratio = use_memo ? v->persist_work_ratio : v->persist_words_ratio;
   P.persist_edges_bytes = v->persist_edges_bytes;
@@ -476,6 +479,7 @@ wp_status finish_stats(wp_vocab *v, size_t n_bytes, const EnqueueInfo &info, cud
   v->stats.memo_hits = v->h_call->memo_hits;
   v->stats.kernel_launches = info.launches;
   *overflow = v->h_call->overflow != 0;
+  if (v->h_call->stalled) v->use_ticket = true;  // a K1 look-back gave up: from now on tiles go by ticket
   return WP_OK;
 }
 
@@ -483,7 +487,7 @@ wp_status finish_stats(wp_vocab *v, size_t n_bytes, const EnqueueInfo &info, cud
 wp_status run_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_t *d_ids, size_t capacity,
                      cudaStream_t stream) {
   size_t spill = 0;
-  for (int attempt = 0; attempt < 2; attempt++) {
+  for (int attempt = 0; attempt < 3; attempt++) {
     EnqueueInfo info;
     wp_status st = enqueue_encode(v, d_text, n_bytes, d_ids, capacity, stream, spill, &info);
     if (st != WP_OK) return st;
@@ -491,7 +495,7 @@ wp_status run_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_t *d
     st = finish_stats(v, n_bytes, info, stream, &overflow);
     if (st != WP_OK) return st;
     if (!overflow) return WP_OK;
-    spill = n_bytes + 4096;
+    if (!v->h_call->stalled) spill = n_bytes + 4096;  // (a stalled look-back: the same call again, by ticket)
   }
   return fail(WP_ERR_CUDA, "internal scratch overflow");
 }
@@ -721,6 +725,7 @@ wp_status encode_pipelined(wp_vocab *v, const char *text, size_t n_bytes, int32_
     WP_CUDA(cudaEventSynchronize(sl.cmp_done));
     const size_t cnt = static_cast<size_t>(sl.h_call->ids_total[infos[j].n_ranges & 1u]);
     overflow = overflow || sl.h_call->overflow != 0;
+    if (sl.h_call->stalled) v->use_ticket = true;
     acc.n_tiles += infos[j].n_tiles;
     acc.dirty_tiles += sl.h_call->dirty_tiles;
     acc.long_segments += sl.h_call->long_segments;
@@ -1324,6 +1329,7 @@ wp_status wp_encode_batch(wp_vocab *v, const char *const *texts, const size_t *l
     const size_t n = p.last - p.first;
     WP_CUDA(cudaEventSynchronize(b.cmp_done));
     *overflow = b.h_call->overflow != 0;
+    if (b.h_call->stalled) v->use_ticket = true;
     if (*overflow) return WP_OK;
     const size_t cnt = static_cast<size_t>(b.h_offsets[n]);
     for (size_t i = 0; i < n; i++) offsets[p.first + i] = total + static_cast<size_t>(b.h_offsets[i]);
@@ -1350,13 +1356,16 @@ wp_status wp_encode_batch(wp_vocab *v, const char *const *texts, const size_t *l
     if (k >= 3) WP_CUDA(cudaEventSynchronize(b.d2h_done));  // the slot's previous part has left (host and device buffers)
     wp_status st = ensure_batch_slot(b, p, want);
     if (st != WP_OK) return st;
+    trace("wp_encode_batch: part: buffers ready");
     pack_part(b, p, texts, lens);
-    if (k == 0) trace("wp_encode_batch: first part packed");
+    trace("wp_encode_batch: part packed");
     st = enqueue_part(v, b, p, n_parts > 1 ? v->s_h2d : v->stream, 0, /*warm=*/k != 0, packed, &infos[k]);
     if (st != WP_OK) return st;
+    trace("wp_encode_batch: part enqueued");
     if (k >= 1) {
       st = finish_part(k - 1, &overflow);
       if (st != WP_OK) return st;
+      trace("wp_encode_batch: previous part finished (ids on their way out)");
     }
   }
   if (!overflow) {

@@ -42,6 +42,25 @@
 #include "wp_encode.h"
 #include "wp_table.h"
 
+// Debug build (make variant NAME=bounds DEFS=-DWP_DEBUG_BOUNDS): every index into the scratch arrays, the lists in
+// shared memory and the output is checked where it is used; a violation prints its place and traps.  The
+// parity suites and the fuzz sweep are run under this build once per round (tools/gpu_bounds.sh).
+#ifdef WP_DEBUG_BOUNDS
+#include <cstdio>
+#define WP_CHECK(cond)                                                                                              \
+  do {                                                                                                              \
+    if (!(cond)) {                                                                                                  \
+      printf("WP_CHECK failed: %s (wp_encode.cu:%d, block %d, thread %d)\n", #cond, __LINE__, static_cast<int>(blockIdx.x), \
+             static_cast<int>(threadIdx.x));                                                                        \
+      __trap();                                                                                                     \
+    }                                                                                                               \
+  } while (0)
+#else
+#define WP_CHECK(cond) \
+  do {                 \
+  } while (0)
+#endif
+
 namespace wp {
 
 // ------------------------------------------------------------------ geometry
@@ -75,7 +94,14 @@ constexpr uint32_t SLOW_LONG = 0x8000u;          // tile slow-list flag: matched
 #ifndef WP_K3_BLOCKS
 #define WP_K3_BLOCKS 4
 #endif
+#ifndef WP_K1_SEG_CAP
+#define WP_K1_SEG_CAP 4096                       // EXPERIMENT ONLY when smaller than TILE: list capacity per tile
+#endif
 constexpr int MATCH_THREADS = WP_K2_THREADS;     // K2
+#ifndef WP_K2_CHUNK
+#define WP_K2_CHUNK 64
+#endif
+constexpr uint32_t MATCH_CHUNK = WP_K2_CHUNK;    // slow entries a K2 warp takes from the dispenser at a time
 constexpr int SCATTER_THREADS = 256;             // K3
 constexpr int SCATTER_ITEMS = 8;                 // segments per thread and block iteration
 constexpr int SCATTER_SEGS = SCATTER_THREADS * SCATTER_ITEMS;  // 2048
@@ -92,8 +118,8 @@ static_assert(NCHUNK < 256, "chunk indices are kept in bytes (hi_list)");
 
 struct __align__(16) TileSmem {
   uint8_t raw[RAW_BYTES];              // [0,LEFT) left halo, then the window, then look-ahead
-  uint16_t seg_s[TILE];                // owned segment k (text order): start position | class << 14
-  uint16_t seg_e[WINDOW + 64];         // j-th segment end in the window
+  uint16_t seg_s[WP_K1_SEG_CAP];       // owned segment k (text order): start position | class << 14
+  uint16_t seg_e[WP_K1_SEG_CAP + HALO + 64];  // j-th segment end in the window
   uint16_t slow[MAX_TILE_SLOW];        // segments the whole-window probe did not settle: ordinal | flags
   uint32_t dyn_hits;                   // segments settled by a word K2 recorded during this call
   uint32_t n_eligible;                 // slow segments short enough for the word table (recording statistics)
@@ -108,6 +134,7 @@ struct __align__(16) TileSmem {
   uint8_t spill[NCHUNK + 1];           // bytes by which the chunk's last sequence runs into the next chunk
   uint8_t hi_list[NCHUNK + 8];         // chunks that hold a byte >= 0x80 (classification pass 2)
   uint32_t n_hi;
+  uint32_t tile_ticket;                // ticket mode: the tile this CTA took
   uint4 key_mask[WORD_KEY_BYTES + 1];  // row k: byte masks of the four key words for a k-byte key
   uint32_t warp_sums[WARPS];
   uint32_t prev_class;                 // class of the last valid char before the tile
@@ -121,6 +148,9 @@ struct __align__(16) TileSmem {
 };
 
 static_assert(sizeof(TileSmem) + 1024 <= 233472 / 7, "seven K1 tiles must fit one SM's shared memory");
+#if WP_K1_SEG_CAP < 4096
+static_assert(sizeof(TileSmem) + 1024 <= 233472 / 8, "the experiment is about eight tiles per SM");
+#endif
 
 // ------------------------------------------------------------------- helpers
 
@@ -486,6 +516,7 @@ __device__ __noinline__ void classify_window(TileSmem &sm, const uint8_t *buf, i
     const int leader = __ffs(hm) - 1;
     if (lane == leader) at = smem_add(&sm.n_hi, static_cast<uint32_t>(__popc(hm)));
     at = __shfl_sync(FULL, at, leader);
+    WP_CHECK(!high || at + __popc(hm & ((1u << lane) - 1u)) < NCHUNK + 8);
     if (high) sm.hi_list[at + __popc(hm & ((1u << lane) - 1u))] = static_cast<uint8_t>(tid);
   }
   __syncthreads();
@@ -538,8 +569,13 @@ __device__ __forceinline__ void lookback_publish(volatile unsigned long long *st
   state[index] = ((index == 0 ? 2ull : 1ull) << 62) | total;
 }
 
+// A walk that has spun this long on one predecessor has lost its forward-progress guarantee (see K1 about the
+// order in which tiles are taken): it gives up, reports it, and the host repeats the call in ticket mode.
+constexpr uint32_t LOOKBACK_SPIN_LIMIT = 1u << 24;  // (a spin is an L2 round trip, ~1 us: many seconds)
+
 __device__ __forceinline__ unsigned long long lookback_walk(volatile unsigned long long *state, uint32_t index,
-                                                            unsigned long long total, int lane) {
+                                                            unsigned long long total, int lane,
+                                                            unsigned int *stalled = nullptr, unsigned int *void_call = nullptr) {
   constexpr unsigned long long VALUE_MASK = (1ull << 62) - 1;
   unsigned long long base = 0;
   if (index == 0) return 0;
@@ -547,8 +583,14 @@ __device__ __forceinline__ unsigned long long lookback_walk(volatile unsigned lo
   for (;;) {
     unsigned long long sv = 2ull << 62;  // units before 0 count as a zero prefix
     if (pred >= 0) {
+      uint32_t spins = 0;
       do {
         sv = state[pred];
+        if (++spins > LOOKBACK_SPIN_LIMIT && stalled != nullptr) {
+          *stalled = 1u;
+          if (void_call != nullptr) *void_call = 1u;  // (the kernels behind this one do nothing)
+          sv = 2ull << 62;  // give up: the result is wrong and the call is void
+        }
       } while ((sv >> 62) == 0);
     }
     const uint32_t is_prefix = __ballot_sync(FULL, (sv >> 62) == 2);
@@ -618,9 +660,13 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   const int warp = tid >> 5;
   const DeviceVocab &V = P.vocab;
 
-  // tile = block index: blocks of a 1-D grid are dispatched in index order, so a tile's predecessors are
-  // always already running (decoupled look-back needs forward progress); no ticket round trip
+  // tile = block index: blocks of a 1-D grid are dispatched in index order on every GPU so far, so a tile's
+  // predecessors are always already running (decoupled look-back needs that forward progress) and no ticket
+  // round trip sits in front of the tile's loads.  CUDA does not PROMISE the order (time slicing, debuggers),
+  // so the look-back spin is bounded: a walk that gives up voids the call (CALL_STALLED), and the host repeats
+  // it with P.use_ticket, where tiles are handed out by an atomic counter and the guarantee holds by construction.
   if (tid == 0) {
+    if (P.use_ticket) sm.tile_ticket = atomicAdd(&P.counters->split_ticket, 1u);
     sm.left_spill = 0;
     sm.n_slow = 0;
     sm.dyn_hits = 0;
@@ -630,7 +676,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   }
   init_key_mask(sm.key_mask, tid);
   __syncthreads();
-  const uint32_t rel_tile = blockIdx.x;                    // within the range
+  const uint32_t rel_tile = P.use_ticket ? sm.tile_ticket : blockIdx.x;  // within the range
   const size_t t0 = (static_cast<size_t>(P.first_tile) + rel_tile) * TILE;
   const size_t n = P.n_bytes;
   const size_t avail = n - t0;  // > 0
@@ -810,11 +856,13 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       starts &= starts - 1;
       const uint32_t bit = 1u << j;
       const uint32_t cls = (pu & bit) ? CLS_PUNCT : ((ha & bit) ? CLS_HAN : CLS_OTHER);
+      WP_CHECK(at_s < WP_K1_SEG_CAP);
       sm.seg_s[at_s++] = static_cast<uint16_t>((c * CHUNK + j) | (cls << 14));
     }
     while (ends) {
       const int j = __ffs(ends) - 1;
       ends &= ends - 1;
+      WP_CHECK(at_e < WP_K1_SEG_CAP + HALO + 64);
       sm.seg_e[at_e++] = static_cast<uint16_t>(c * CHUNK + j);
     }
     if (tid == 0) {
@@ -867,6 +915,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       wlen[u] = len;
       const uint32_t lc = min(len, WORD_KEY_BYTES);
       uint32_t r[4];
+      WP_CHECK(s >= 0 && s + 20 <= WINDOW + LOOKAHEAD && e > s && j <= TILE);
       load_window(buf, s, r);
       const uint4 km = sm.key_mask[lc];
       key[u][0] = r[0] & km.x;
@@ -874,6 +923,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       key[u][2] = r[2] & km.z;
       key[u][3] = r[3] & km.w;
       idx[u] = word_hash(key[u][0], key[u][1], key[u][2], key[u][3], lc, P.word_shift);
+      WP_CHECK(idx[u] <= P.word_mask);
       ld_word_slot(wtab, idx[u], &sa[u], &sb[u]);
     }
 #pragma unroll
@@ -922,6 +972,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
         const int leader = __ffs(slowm) - 1;
         if (lane == leader) at = smem_add(&sm.n_slow, static_cast<uint32_t>(__popc(slowm)));
         at = __shfl_sync(FULL, at, leader);
+        WP_CHECK(state[u] < 2u || at + __popc(slowm & ((1u << lane) - 1u)) < MAX_TILE_SLOW);
         if (state[u] >= 2u)
           sm.slow[at + __popc(slowm & ((1u << lane) - 1u))] =
               static_cast<uint16_t>((base + u * THREADS + tid) | (state[u] == 3u ? SLOW_LONG : 0u));
@@ -957,7 +1008,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
 
   // ---- the walk back over earlier tiles (short by now), then the settled results go out coalesced
   if (warp == 0) {
-    const unsigned long long base = lookback_walk(P.tile_state, rel_tile, n_segs, lane);
+    const unsigned long long base = lookback_walk(P.tile_state, rel_tile, n_segs, lane, &P.call->stalled, &P.call->overflow);
     if (lane == 0) {
       sm.seg_base = base;
       if (rel_tile == P.n_tiles - 1) P.counters->n_segs = base + n_segs;
@@ -976,6 +1027,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
 #pragma unroll 1
     for (uint32_t i = b0 + tid; i < b1; i += THREADS) {
       uint32_t q = static_cast<uint32_t>(P.bounds[i] - t0);  // < TILE, raw window position
+      WP_CHECK(P.bounds[i] >= t0 && q < TILE);
       if (dirty) q = sm.kept_scan[q >> 5] + __popc(sm.m_kept[q >> 5] & ((1u << (q & 31u)) - 1u));  // -> compacted
       P.bound_seg[i] = static_cast<uint32_t>(seg_base) + sm.m_punct[q >> 5] + __popc(sm.m_space[q >> 5] & ((1u << (q & 31u)) - 1u));
     }
@@ -983,6 +1035,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   // (every segment is written: the words of the unsettled ones are garbage here and are overwritten below,
   // behind a barrier, when their slow entries exist)
 #pragma unroll 1
+  WP_CHECK(seg_base + n_segs <= P.seg_capacity);
   for (uint32_t k = tid; k < n_segs; k += THREADS)
     P.seg_result[seg_base + k] = static_cast<uint32_t>(sm.seg_s[k]) | (static_cast<uint32_t>(sm.seg_e[k + skip]) << 16);
   if (tid == 0 && P.record_words && P.range_index >= 1) {
@@ -1068,6 +1121,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
         const int e = k + skip < n_ends ? static_cast<int>(sm.seg_e[k + skip]) : limit;
         const uint32_t len = static_cast<uint32_t>(e - wpos);
         out.off = arena_base + run;
+        WP_CHECK(static_cast<unsigned long long>(out.off) + len + ((len + 3u) >> 2) <= P.arena_capacity && len >= 1 && len <= LONG_SEGMENT_BYTES);
         out.meta = len | ((sv >> 14) << 16);
         out.pos_lo = 0;
         uint32_t *dst = P.arena + out.off + len;
@@ -1085,6 +1139,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
         }
         run += len + nw;
       }
+      WP_CHECK(slow_base + i < P.slow_capacity && out.seg < P.seg_capacity);
       *reinterpret_cast<uint4 *>(&P.slow[slow_base + i]) = *reinterpret_cast<const uint4 *>(&out);
       P.seg_result[seg_base + k] = SEG_RESULT_SLOW | (slow_base + i);
     }
@@ -1108,11 +1163,11 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
 
   if (P.call->overflow) return;  // a K1 tile gave up (scratch too small): its entries are unwritten, the host retries
   const uint32_t n_slow = min(P.counters->n_slow, P.slow_capacity);
-  const uint32_t n_warps = gridDim.x * (MATCH_THREADS / 32);
-  const uint32_t gw = blockIdx.x * (MATCH_THREADS / 32) + (tid >> 5);
-  const uint32_t per = ((n_slow + n_warps - 1) / n_warps + 31u) & ~31u;
-  uint32_t cursor = min(n_slow, gw * per);             // warp-uniform: next unassigned entry of this warp
-  const uint32_t cursor_end = min(n_slow, cursor + per);
+  // Entries are handed out to warps MATCH_CHUNK at a time by one atomic counter: chains differ a lot in length
+  // (a kana run of twenty chars next to a two-piece word), and with fixed shares per warp half of a warp's
+  // lanes sat idle while the last entries of its share finished (16 of 32 threads active on Japanese text).
+  uint32_t cursor = 0, cursor_end = 0;                 // warp-uniform: the unassigned entries of this warp's chunk
+  bool drained = false;                                // warp-uniform: the dispenser has nothing left
 
   // K1 of this range is done, so the counters are final: every lane reads the same verdict
   const bool worth = memo_worthwhile(P.call->memo_lookups, P.call->memo_hits, P.range_index <= 1);
@@ -1141,10 +1196,19 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
   for (;;) {
     // -- refill: lanes without a segment take the next entries of this warp's share
     const uint32_t needm = __ballot_sync(FULL, !have);
+    if (needm && cursor >= cursor_end && !drained) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&P.counters->match_cursor, static_cast<unsigned int>(MATCH_CHUNK));
+      base = __shfl_sync(FULL, base, 0);
+      cursor = min(base, n_slow);
+      cursor_end = min(base + MATCH_CHUNK, n_slow);
+      drained = cursor >= cursor_end;
+      if (cursor + lane < cursor_end) prefetch_l1(&P.slow[cursor + lane]);
+    }
     if (needm && cursor < cursor_end) {
       const uint32_t i = cursor + __popc(needm & ((1u << lane) - 1u));
       cursor += __popc(needm);  // may pass cursor_end; entries beyond it are simply not taken
-      if (cursor + lane < cursor_end) prefetch_l1(&P.slow[cursor + lane]);  // the next 32 entries of this share
+      if (cursor + lane < cursor_end) prefetch_l1(&P.slow[cursor + lane]);  // the next entries of this chunk
       if (!have && i < cursor_end) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(&P.slow[i]));
         const uint32_t meta = raw.y;
@@ -1153,6 +1217,8 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
           area = raw.x;
           seg = raw.w;
           seg_len = meta & 0xFFFFu;
+          WP_CHECK(static_cast<unsigned long long>(area) + seg_len + ((seg_len + 3u) >> 2) <= P.arena_capacity && seg_len >= 1 &&
+                   seg < P.seg_capacity);
           out = reinterpret_cast<int32_t *>(P.arena + area);
           txt = reinterpret_cast<const uint8_t *>(P.arena + area + seg_len);
           raw_cur = text_at(0);
@@ -1171,7 +1237,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
       }
     }
     if (!__any_sync(FULL, have)) {
-      if (cursor >= cursor_end) break;
+      if (drained) break;
       continue;
     }
     if (!have) continue;
@@ -1202,6 +1268,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
     bool done = false;
     // ids 0..2 go to registers, later ones straight to the id scratch
     auto put = [&](uint32_t index, int32_t v) {
+      WP_CHECK(index < seg_len);  // a segment never has more ids than bytes
       if (index == 0) t0 = v;
       else if (index == 1) t1 = v;
       else if (index == 2) t2 = v;
@@ -1268,6 +1335,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
       uint32_t idx = word_hash(k0, k1, k2, k3, seg_len, P.word_shift);
       bool placed = false;
       for (uint32_t t = 0; t < WORD_PROBES && !placed; t++) {
+        WP_CHECK(idx <= P.word_mask);
         WordSlot *slot = P.words + idx;
         const unsigned int old = atomicCAS(&slot->meta, 0u, WORD_CLAIMED);
         if (old == 0u) {
@@ -1503,6 +1571,7 @@ __global__ void __launch_bounds__(LONG_THREADS) wp_long_kernel(EncodeParams P) {
           const uint32_t r = sm.rank[i];
           if (r == LONG_END) continue;
           const uint32_t j = sm.jump[k][i];
+          WP_CHECK(j == LONG_END || (j < n && j > i && r + (1u << k) < LONG_BLOCK));
           if (j != LONG_END) sm.rank[j] = static_cast<uint16_t>(r + (1u << k));
         }
         __syncthreads();
@@ -1516,6 +1585,7 @@ __global__ void __launch_bounds__(LONG_THREADS) wp_long_kernel(EncodeParams P) {
         if (dl == 0) {
           sm.failed = 1;  // fast.cpp:79-88 (the chain ends here: a position without a match has no successor)
         } else {
+          WP_CHECK(static_cast<unsigned long long>(sm.off) + n_out + r < P.arena_capacity && b0 + i - start >= n_out + r);
           out[n_out + r] = sm.id[i];
           if (sm.jump[0][i] == LONG_END) {
             sm.n_round = r + 1;
@@ -1635,7 +1705,7 @@ __device__ __forceinline__ void scatter_direct(const EncodeParams &P, unsigned l
   }
 }
 
-__global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParams P) {
+__global__ void __launch_bounds__(SCATTER_THREADS, WP_K3_BLOCKS) wp_scatter_kernel(EncodeParams P) {
   __shared__ ScatterSmem sm;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -1715,9 +1785,11 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
       d = d - n_other + __shfl_sync(FULL, wbase, 31);
 #pragma unroll
       for (int j = 0; j < SCATTER_ITEMS; j++) {
+        WP_CHECK(at + cnt[j] <= total && total <= SCATTER_STAGE);
         if (res[j] < SEG_RESULT_WORD) {
           sm.stage[at] = static_cast<int32_t>(res[j]) - 1;
         } else if (cnt[j] != 0) {
+          WP_CHECK(d < SCATTER_SEGS);
           sm.desc_pos[d] = (at << 16) | cnt[j];
           sm.desc_src[d] = res[j];
           d++;
@@ -1729,7 +1801,9 @@ __global__ void __launch_bounds__(SCATTER_THREADS) wp_scatter_kernel(EncodeParam
       for (uint32_t i = tid; i < n_desc; i += SCATTER_THREADS) {
         const uint32_t dp = sm.desc_pos[i], src = sm.desc_src[i];
         if ((src & SEG_RESULT_SLOW) && (dp & 0xFFFFu) > SCATTER_BIG) {
-          sm.big[atomicAdd(&sm.n_big, 1u)] = static_cast<uint16_t>(i);  // (ids in the arena; one thread would take ages)
+          const uint32_t slot = atomicAdd(&sm.n_big, 1u);  // (ids in the arena; one thread would take ages)
+          WP_CHECK(slot < SCATTER_STAGE / SCATTER_BIG + 2);
+          sm.big[slot] = static_cast<uint16_t>(i);
         } else {
           scatter_fetch(P, src, dp & 0xFFFFu, sm.stage + (dp >> 16));
         }
