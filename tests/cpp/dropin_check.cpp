@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <map>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -61,6 +62,8 @@ int main(int argc, char **argv) {
   in >> n_cases;
   double encode_seconds = 0;
   size_t encode_bytes = 0;
+  // cases grouped by vocabulary for the Encoder class (a vocabulary that stays on the GPU; batch call)
+  std::map<std::vector<std::string>, std::vector<std::pair<std::string, std::vector<int>>>> by_vocab;
   for (size_t c = 0; c < n_cases; c++) {
     const std::string text = read_blob(in);
     size_t n_vocab = 0;
@@ -87,6 +90,7 @@ int main(int argc, char **argv) {
     encode_bytes += text.size();
     expect(got == expected, "case " + std::to_string(c) + ": fast::encode(text, vocab) ids differ (" +
                                 std::to_string(got.size()) + " vs " + std::to_string(expected.size()) + " expected)");
+    by_vocab[vocab].emplace_back(text, expected);
     if (newline_in_token) continue;
 
     // (2) the file overload, fast.cpp:159-163, and decode, fast.cpp:165-187
@@ -109,6 +113,27 @@ int main(int argc, char **argv) {
     }
     std::remove(vocab_file.c_str());
     std::remove(text_file.c_str());
+  }
+  // (3) Encoder (extension): encode == fast::encode, encodeBatch == one encode per text, decode round trip
+  for (const auto &group : by_vocab) {
+    word_piece::fast::Encoder enc(group.first);
+    std::vector<std::string> texts;
+    for (const auto &item : group.second) {
+      texts.push_back(item.first);
+      expect(enc.encode(item.first) == item.second, "Encoder::encode differs from the expected ids");
+    }
+    const std::vector<std::vector<int>> batch = enc.encodeBatch(texts);
+    expect(batch.size() == texts.size(), "Encoder::encodeBatch: wrong number of results");
+    for (size_t i = 0; i < batch.size() && i < texts.size(); i++)
+      expect(batch[i] == group.second[i].second, "Encoder::encodeBatch: text " + std::to_string(i) + " differs");
+    std::vector<int> ids;
+    std::vector<size_t> offsets;
+    enc.encodeBatch(texts, ids, offsets);
+    expect(offsets.size() == texts.size() + 1 && offsets.front() == 0 && offsets.back() == ids.size(),
+           "Encoder::encodeBatch: offsets are not a partition of the ids");
+    word_piece::fast::Encoder moved = std::move(enc);
+    expect(moved.vocabSize() == group.first.size(), "Encoder: vocabulary size after a move");
+    expect(moved.encode(texts.front()) == group.second.front().second, "Encoder: encode after a move");
   }
   std::cout << "Passed " << (checks - failures) << " of " << checks << " checks; in-memory encode: " << encode_bytes
             << " bytes in " << encode_seconds << " s" << std::endl;

@@ -600,3 +600,34 @@ def test_ticket_mode_is_exact(gpu_device, monkeypatch):
     text, vocab = textgen.case(41, 1_500_000, invalid_rate=0.002, long_run_rate=0.01, long_tokens=4)
     st = _check(text, vocab, gpu_device, "ticket mode")
     assert st.n_tiles > 300
+
+
+def test_dense_tiles_fall_back_to_full_lists(gpu_device):
+    """A tile of punctuation holds one segment per byte — more than the segment lists of the regular K1 (3 072 per
+    4 KiB tile, which is what lets eight tiles share an SM).  The call is flagged dense and repeated with the
+    full-capacity kernel; ids are the oracle's, also for later calls on the same handle and for a batch."""
+    from wordpiece_b200 import Vocab
+
+    vocab = ["[UNK]", ".", ",", "!", "?", "a", "b", "ab", "##b", "(", ")", "中"]
+    dense = (b".,!?()" * 3000)[:15000]
+    text = b"ab ab " + dense + b" ab a" + "中中中".encode() * 700 + b" b " + dense[:5000]
+    o = Oracle(vocab)
+    v = Vocab(vocab, device=gpu_device)
+    assert np.array_equal(o.encode(text), v.encode(text))
+    assert np.array_equal(o.encode(b"ab ab. a"), v.encode(b"ab ab. a"))      # the handle stays usable (and exact)
+    ids, offs = v.encode_batch([b"ab", dense, b"", b"a.b"])
+    for i, t in enumerate([b"ab", dense, b"", b"a.b"]):
+        assert np.array_equal(o.encode(t), ids[int(offs[i]):int(offs[i + 1])]), i
+    v.close()
+    v2 = Vocab(vocab, device=gpu_device)                                        # a fresh handle, dense batch first
+    ids, offs = v2.encode_batch([dense[:9000], b"ab"])
+    assert np.array_equal(o.encode(dense[:9000]), ids[int(offs[0]):int(offs[1])])
+    assert np.array_equal(o.encode(b"ab"), ids[int(offs[1]):int(offs[2])])
+    import torch
+
+    d_text = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda(gpu_device)
+    v3 = Vocab(vocab, device=gpu_device)                                        # device-resident entry
+    d_ids, n = v3.encode_device(d_text)
+    assert np.array_equal(o.encode(text), d_ids[:n].cpu().numpy())
+    v2.close()
+    v3.close()

@@ -124,6 +124,7 @@ struct wp_vocab {
   // finished before those of the next begin, on whatever streams the caller enqueues them
   cudaEvent_t last_done = nullptr;
   bool use_ticket = false;  // K1 hands its tiles out by ticket (set for good once a look-back has stalled, see wp_encode.cu)
+  bool dense_tiles = false; // K1 with full-capacity segment lists (set for good once a tile overflowed the regular ones)
   // overlap of consecutive ranges (see enqueue_encode): K2/K2L/K3 run on a second, high-priority stream
   cudaStream_t s_aux = nullptr;
   cudaEvent_t ev_split[2] = {nullptr, nullptr};    // K1 of the range in scratch half b is done
@@ -334,6 +335,7 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
   P.word_shift = 32 - words_log2;
   P.record_words = use_memo ? 1u : 0u;
   P.use_ticket = v->use_ticket ? 1u : 0u;
+  P.dense_tiles = v->dense_tiles ? 1u : 0u;
   if (const char *e = std::getenv("WORDPIECE_B200_TICKET")) P.use_ticket = std::atoi(e) != 0 ? 1u : 0u;  // test hook
   P.persist_words_bytes = use_memo ? v->persist_work_bytes : v->persist_words_bytes;
   P.persist_words_ratio = use_memo ? v->persist_work_ratio : v->persist_words_ratio;
@@ -480,6 +482,7 @@ wp_status finish_stats(wp_vocab *v, size_t n_bytes, const EnqueueInfo &info, cud
   v->stats.kernel_launches = info.launches;
   *overflow = v->h_call->overflow != 0;
   if (v->h_call->stalled) v->use_ticket = true;  // a K1 look-back gave up: from now on tiles go by ticket
+  if (v->h_call->dense) v->dense_tiles = true;   // a tile with more segments than the regular K1's lists hold
   return WP_OK;
 }
 
@@ -495,7 +498,7 @@ wp_status run_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_t *d
     st = finish_stats(v, n_bytes, info, stream, &overflow);
     if (st != WP_OK) return st;
     if (!overflow) return WP_OK;
-    if (!v->h_call->stalled) spill = n_bytes + 4096;  // (a stalled look-back: the same call again, by ticket)
+    if (!v->h_call->stalled && !v->h_call->dense) spill = n_bytes + 4096;  // (else: the same call again, other K1 mode)
   }
   return fail(WP_ERR_CUDA, "internal scratch overflow");
 }
@@ -726,6 +729,7 @@ wp_status encode_pipelined(wp_vocab *v, const char *text, size_t n_bytes, int32_
     const size_t cnt = static_cast<size_t>(sl.h_call->ids_total[infos[j].n_ranges & 1u]);
     overflow = overflow || sl.h_call->overflow != 0;
     if (sl.h_call->stalled) v->use_ticket = true;
+    if (sl.h_call->dense) v->dense_tiles = true;
     acc.n_tiles += infos[j].n_tiles;
     acc.dirty_tiles += sl.h_call->dirty_tiles;
     acc.long_segments += sl.h_call->long_segments;
@@ -1330,6 +1334,7 @@ wp_status wp_encode_batch(wp_vocab *v, const char *const *texts, const size_t *l
     WP_CUDA(cudaEventSynchronize(b.cmp_done));
     *overflow = b.h_call->overflow != 0;
     if (b.h_call->stalled) v->use_ticket = true;
+    if (b.h_call->dense) v->dense_tiles = true;
     if (*overflow) return WP_OK;
     const size_t cnt = static_cast<size_t>(b.h_offsets[n]);
     for (size_t i = 0; i < n; i++) offsets[p.first + i] = total + static_cast<size_t>(b.h_offsets[i]);

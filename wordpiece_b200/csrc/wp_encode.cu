@@ -95,13 +95,9 @@ constexpr uint32_t SLOW_LONG = 0x8000u;          // tile slow-list flag: matched
 #define WP_K3_BLOCKS 4
 #endif
 #ifndef WP_K1_SEG_CAP
-#define WP_K1_SEG_CAP 4096                       // EXPERIMENT ONLY when smaller than TILE: list capacity per tile
+#define WP_K1_SEG_CAP 3072                       // segments per tile the lists of the regular K1 hold (see TileSmemT)
 #endif
 constexpr int MATCH_THREADS = WP_K2_THREADS;     // K2
-#ifndef WP_K2_CHUNK
-#define WP_K2_CHUNK 64
-#endif
-constexpr uint32_t MATCH_CHUNK = WP_K2_CHUNK;    // slow entries a K2 warp takes from the dispenser at a time
 constexpr int SCATTER_THREADS = 256;             // K3
 constexpr int SCATTER_ITEMS = 8;                 // segments per thread and block iteration
 constexpr int SCATTER_SEGS = SCATTER_THREADS * SCATTER_ITEMS;  // 2048
@@ -116,10 +112,15 @@ static_assert(WINDOW <= static_cast<int>(POS_MASK), "positions must fit the pack
 static_assert(TILE <= 4096, "segment ordinals must fit 12 bits of the tile slow list");
 static_assert(NCHUNK < 256, "chunk indices are kept in bytes (hi_list)");
 
-struct __align__(16) TileSmem {
+// The segment lists are sized for SEG_CAP owned segments.  A tile CAN hold TILE of them (every byte a
+// punctuation char), but text does not: with 3 072 a tile's shared memory shrinks enough for EIGHT tiles per
+// SM instead of seven (K1 -4.4 %, profiles/r2g_variants.txt).  A tile that holds more flags the call as
+// "dense"; the call is void and the host repeats it with the full-capacity instantiation (sticky per handle).
+template <int SEG_CAP>
+struct __align__(16) TileSmemT {
   uint8_t raw[RAW_BYTES];              // [0,LEFT) left halo, then the window, then look-ahead
-  uint16_t seg_s[WP_K1_SEG_CAP];       // owned segment k (text order): start position | class << 14
-  uint16_t seg_e[WP_K1_SEG_CAP + HALO + 64];  // j-th segment end in the window
+  uint16_t seg_s[SEG_CAP];             // owned segment k (text order): start position | class << 14
+  uint16_t seg_e[SEG_CAP + HALO + 64]; // j-th segment end in the window
   uint16_t slow[MAX_TILE_SLOW];        // segments the whole-window probe did not settle: ordinal | flags
   uint32_t dyn_hits;                   // segments settled by a word K2 recorded during this call
   uint32_t n_eligible;                 // slow segments short enough for the word table (recording statistics)
@@ -147,10 +148,9 @@ struct __align__(16) TileSmem {
   unsigned long long seg_base;         // segments of all earlier tiles of the range
 };
 
-static_assert(sizeof(TileSmem) + 1024 <= 233472 / 7, "seven K1 tiles must fit one SM's shared memory");
-#if WP_K1_SEG_CAP < 4096
-static_assert(sizeof(TileSmem) + 1024 <= 233472 / 8, "the experiment is about eight tiles per SM");
-#endif
+static_assert(sizeof(TileSmemT<TILE>) + 1024 <= 233472 / 7, "seven full-capacity K1 tiles must fit one SM's shared memory");
+static_assert(sizeof(TileSmemT<WP_K1_SEG_CAP>) + 1024 <= 233472 / 8, "eight regular K1 tiles must fit one SM's shared memory");
+static_assert(WP_K1_SEG_CAP <= TILE && WP_K1_SEG_CAP % 8 == 0, "list capacity");
 
 // ------------------------------------------------------------------- helpers
 
@@ -397,6 +397,7 @@ __device__ __forceinline__ uint32_t limit_mask(int c, int limit) {
   return left >= CHUNK ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
 }
 
+template <class TileSmem>
 __device__ __forceinline__ bool classify_ascii(TileSmem &sm, const uint8_t *buf, int c, int limit) {
   const uint8_t *cb = buf + c * CHUNK;
   uint32_t sp = 0, pu = 0, any_high = 0;
@@ -428,6 +429,7 @@ __device__ __forceinline__ bool classify_ascii(TileSmem &sm, const uint8_t *buf,
   return high;
 }
 
+template <class TileSmem>
 __device__ __forceinline__ void classify_multibyte(TileSmem &sm, const uint8_t *buf, int c, int limit) {
   const uint8_t *cb = buf + c * CHUNK;
   uint32_t lead = 0xFFFFFFFFu, sp = sm.m_space[c], pu = sm.m_punct[c], ha = 0, cover = 0xFFFFFFFFu, spill = 0;
@@ -506,6 +508,7 @@ __device__ __forceinline__ void classify_multibyte(TileSmem &sm, const uint8_t *
 
 // Both passes over the whole window (block-wide; sm.n_hi must be zero on entry; the caller synchronises
 // before it reads the masks).  Out of line: K1 calls it from two places.
+template <class TileSmem>
 __device__ __noinline__ void classify_window(TileSmem &sm, const uint8_t *buf, int limit) {
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -640,6 +643,9 @@ __device__ __forceinline__ void init_key_mask(uint4 *key_mask, int tid) {
 // returns the id or SINGLE_WALK_MISS.
 constexpr int32_t SINGLE_WALK_MISS = WP_NO_ID - 1;
 constexpr uint16_t PARK_PENDING = 0xFFFFu;  // parked high half of a result is < 0x8000
+// (a template only so that each instantiation of K1 has a copy of its own: ptxas 12.9 crashes on one
+// out-of-line function shared by the two)
+template <int SEG_CAP>
 __device__ __noinline__ int32_t single_char_walk(const WordSlot *tab, uint32_t mask, uint32_t idx, uint32_t k0,
                                                  uint32_t len) {
   for (uint32_t n = 0; n <= mask; n++) {  // (a working table that K2 has filled to the last slot has no empty one)
@@ -652,7 +658,9 @@ __device__ __noinline__ int32_t single_char_walk(const WordSlot *tab, uint32_t m
   return SINGLE_WALK_MISS;
 }
 
+template <int SEG_CAP>
 __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
+  using TileSmem = TileSmemT<SEG_CAP>;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
   const int tid = threadIdx.x;
@@ -845,6 +853,16 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     const uint32_t at = static_cast<uint32_t>(sc1);
     totals = static_cast<uint32_t>(sc1 >> 32);
     uint32_t at_s = at & 0xFFFFu, at_e = at >> 16;
+    if (SEG_CAP < TILE && ((totals & 0xFFFFu) > SEG_CAP || (totals >> 16) > SEG_CAP + HALO + 63)) {  // uniform
+      // a dense tile (more segments than the lists of this instantiation hold): the call is void, the host
+      // repeats it with the full-capacity kernel.  The tile still publishes a count: nobody may wait for it.
+      if (tid == 0) {
+        P.call->dense = 1u;
+        P.call->overflow = 1u;
+        lookback_publish(P.tile_state, rel_tile, totals & 0xFFFFu);
+      }
+      return;
+    }
     if (P.bounds != nullptr && c < NCHUNK) {
       // batch call: the text starts of this tile are numbered after the look-back walk from the chunk's start
       // bits and their prefix (the class masks are not needed any more; the scan above was a barrier)
@@ -856,13 +874,13 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       starts &= starts - 1;
       const uint32_t bit = 1u << j;
       const uint32_t cls = (pu & bit) ? CLS_PUNCT : ((ha & bit) ? CLS_HAN : CLS_OTHER);
-      WP_CHECK(at_s < WP_K1_SEG_CAP);
+      WP_CHECK(at_s < SEG_CAP);
       sm.seg_s[at_s++] = static_cast<uint16_t>((c * CHUNK + j) | (cls << 14));
     }
     while (ends) {
       const int j = __ffs(ends) - 1;
       ends &= ends - 1;
-      WP_CHECK(at_e < WP_K1_SEG_CAP + HALO + 64);
+      WP_CHECK(at_e < SEG_CAP + HALO + 64);
       sm.seg_e[at_e++] = static_cast<uint16_t>(c * CHUNK + j);
     }
     if (tid == 0) {
@@ -902,20 +920,24 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
 #pragma unroll
     for (int u = 0; u < PER_TURN; u++) {
       const uint32_t k = base + u * THREADS + tid;
-      const uint32_t kc = min(k, n_segs - 1u);
-      const int s = static_cast<int>(sm.seg_s[kc] & POS_MASK);
-      const uint32_t j = kc + skip;
+      const bool valid = k < n_segs;
+      const uint32_t kc = min(k, n_segs - 1u);  // (a lane past the last segment reads that one's entries: they may
+      const uint32_t j = kc + skip;             //  already hold a parked result, so what it reads is replaced below)
       const bool has_end = j < n_ends;
+      const int s0 = static_cast<int>(sm.seg_s[kc] & POS_MASK);
       const int e0 = sm.seg_e[j];  // (in bounds either way: j <= TILE)
-      const int e = has_end ? e0 : limit;
+      const int s = valid ? s0 : 0;
+      const int e = valid ? (has_end ? e0 : limit) : 1;
       const uint32_t len = static_cast<uint32_t>(e - s);
       const bool is_long = (!has_end && more_text) || len > LONG_SEGMENT_BYTES;  // no end inside the window / very long
       // 0 = no segment, 1 = looked up, 2 = slow, 3 = slow and LONG
-      state[u] = k >= n_segs ? 0u : (is_long ? 3u : (len > WORD_KEY_BYTES ? 2u : 1u));
+      state[u] = !valid ? 0u : (is_long ? 3u : (len > WORD_KEY_BYTES ? 2u : 1u));
       wlen[u] = len;
       const uint32_t lc = min(len, WORD_KEY_BYTES);
       uint32_t r[4];
-      WP_CHECK(s >= 0 && s + 20 <= WINDOW + LOOKAHEAD && e > s && j <= TILE);
+      WP_CHECK(s >= 0 && s + 20 <= WINDOW + LOOKAHEAD);
+      WP_CHECK(e > s);
+      WP_CHECK(j <= TILE);
       load_window(buf, s, r);
       const uint4 km = sm.key_mask[lc];
       key[u][0] = r[0] & km.x;
@@ -999,7 +1021,7 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
       load_window(buf, static_cast<int>(sm.seg_s[k] & POS_MASK), r);
       const uint32_t len = utf8_lead_len(r[0] & 0xFFu);
       const uint32_t k0 = r[0] & sm.key_mask[len].x;
-      const int32_t id = single_char_walk(wtab, P.word_mask, word_hash(k0, 0u, 0u, 0u, len, P.word_shift), k0, len);
+      const int32_t id = single_char_walk<SEG_CAP>(wtab, P.word_mask, word_hash(k0, 0u, 0u, 0u, len, P.word_shift), k0, len);
       const uint32_t res = static_cast<uint32_t>((id != SINGLE_WALK_MISS ? id : V.unk_id) + 1);
       sm.seg_s[k] = static_cast<uint16_t>(res);
       sm.seg_e[k + skip] = static_cast<uint16_t>(res >> 16);
@@ -1163,11 +1185,14 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
 
   if (P.call->overflow) return;  // a K1 tile gave up (scratch too small): its entries are unwritten, the host retries
   const uint32_t n_slow = min(P.counters->n_slow, P.slow_capacity);
-  // Entries are handed out to warps MATCH_CHUNK at a time by one atomic counter: chains differ a lot in length
-  // (a kana run of twenty chars next to a two-piece word), and with fixed shares per warp half of a warp's
-  // lanes sat idle while the last entries of its share finished (16 of 32 threads active on Japanese text).
-  uint32_t cursor = 0, cursor_end = 0;                 // warp-uniform: the unassigned entries of this warp's chunk
-  bool drained = false;                                // warp-uniform: the dispenser has nothing left
+  // Fixed shares: every warp owns one contiguous run of entries.  (Handing the entries out in chunks from an
+  // atomic counter was measured: with 32 per warp and fetch it is no faster than the shares — English +5 %,
+  // Japanese -5 % — and with 64 or 128 it is 1.6x / 2.8x SLOWER, profiles/r2g_variants.txt.)
+  const uint32_t n_warps = gridDim.x * (MATCH_THREADS / 32);
+  const uint32_t gw = blockIdx.x * (MATCH_THREADS / 32) + (tid >> 5);
+  const uint32_t per = ((n_slow + n_warps - 1) / n_warps + 31u) & ~31u;
+  uint32_t cursor = min(n_slow, gw * per);             // warp-uniform: next unassigned entry of this warp
+  const uint32_t cursor_end = min(n_slow, cursor + per);
 
   // K1 of this range is done, so the counters are final: every lane reads the same verdict
   const bool worth = memo_worthwhile(P.call->memo_lookups, P.call->memo_hits, P.range_index <= 1);
@@ -1196,19 +1221,10 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
   for (;;) {
     // -- refill: lanes without a segment take the next entries of this warp's share
     const uint32_t needm = __ballot_sync(FULL, !have);
-    if (needm && cursor >= cursor_end && !drained) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&P.counters->match_cursor, static_cast<unsigned int>(MATCH_CHUNK));
-      base = __shfl_sync(FULL, base, 0);
-      cursor = min(base, n_slow);
-      cursor_end = min(base + MATCH_CHUNK, n_slow);
-      drained = cursor >= cursor_end;
-      if (cursor + lane < cursor_end) prefetch_l1(&P.slow[cursor + lane]);
-    }
     if (needm && cursor < cursor_end) {
       const uint32_t i = cursor + __popc(needm & ((1u << lane) - 1u));
       cursor += __popc(needm);  // may pass cursor_end; entries beyond it are simply not taken
-      if (cursor + lane < cursor_end) prefetch_l1(&P.slow[cursor + lane]);  // the next entries of this chunk
+      if (cursor + lane < cursor_end) prefetch_l1(&P.slow[cursor + lane]);  // the next 32 entries of this share
       if (!have && i < cursor_end) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(&P.slow[i]));
         const uint32_t meta = raw.y;
@@ -1237,7 +1253,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
       }
     }
     if (!__any_sync(FULL, have)) {
-      if (drained) break;
+      if (cursor >= cursor_end) break;
       continue;
     }
     if (!have) continue;
@@ -2093,8 +2109,11 @@ cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    e = cudaFuncSetAttribute(wp_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(sizeof(TileSmem)));
+    e = cudaFuncSetAttribute(wp_split_kernel<WP_K1_SEG_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(sizeof(TileSmemT<WP_K1_SEG_CAP>)));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(wp_split_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(sizeof(TileSmemT<TILE>)));
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
@@ -2121,9 +2140,14 @@ cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_
   if (phases & PHASE_SPLIT) {
     cfg.gridDim = dim3(P.n_tiles);
     cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = sizeof(TileSmem);
     cfg.numAttrs = window(P.words, P.persist_words_bytes, P.persist_words_ratio);
-    e = cudaLaunchKernelEx(&cfg, wp_split_kernel, P);
+    if (P.dense_tiles) {
+      cfg.dynamicSmemBytes = sizeof(TileSmemT<TILE>);
+      e = cudaLaunchKernelEx(&cfg, wp_split_kernel<TILE>, P);
+    } else {
+      cfg.dynamicSmemBytes = sizeof(TileSmemT<WP_K1_SEG_CAP>);
+      e = cudaLaunchKernelEx(&cfg, wp_split_kernel<WP_K1_SEG_CAP>, P);
+    }
     if (e != cudaSuccess) return e;
     if (launches) *launches += 1;
   }

@@ -72,7 +72,7 @@ struct RangeCounters {
   unsigned int arena_spill;          // arena words reserved by K2L past the K1 part (ids of LONG entries)
   unsigned int n_long;               // LONG entries appended to long_list by K1
   unsigned int long_ticket;          // entry dispenser of K2L
-  unsigned int match_cursor;         // entry dispenser of K2 (warps take MATCH_CHUNK entries at a time)
+  unsigned int pad;
   unsigned long long n_segs;         // segments of the range (K1, last tile)
 };
 
@@ -85,7 +85,8 @@ struct CallCounters {
   unsigned int stalled;              // set if a K1 look-back gave up waiting (the host retries in ticket mode)
   unsigned long long memo_hits;      // segments settled in K1 by a word that K2 recorded during this call
   unsigned long long memo_lookups;   // those + the segments K1 left to K2, in ranges >= 1 (range 0 cannot hit)
-  unsigned int pad2[18];             // (the counters above are hit by atomics from every tile)
+  unsigned int dense;                // set if a K1 tile held more segments than its lists (the host retries with the full-capacity K1)
+  unsigned int pad2[17];             // (the counters above are hit by atomics from every tile)
   unsigned int memo_off;             // set by K2 once recording has shown not to pay (memo_worthwhile)
   unsigned int pad3[31];
 };
@@ -122,6 +123,7 @@ struct EncodeParams {
   uint32_t record_words;            // K2 records the words it matches (working table only)
   uint32_t range_index;             // 0, 1, 2, ... within the call
   uint32_t use_ticket;              // K1 takes its tiles from RangeCounters::split_ticket instead of blockIdx.x
+  uint32_t dense_tiles;             // K1 with full-capacity segment lists (seven tiles per SM instead of eight)
   uint32_t accept_epoch;            // K1 uses word slots of an epoch <= this (wp_table.h); WORD_EPOCH_MAX = all
   uint32_t record_epoch;            // epoch K2 tags its recordings with (range index + 1)
   // batch of texts in one buffer (wp_encode_batch), else bounds = nullptr: bounds[i] = byte offset at which
