@@ -28,12 +28,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=120.0)
     ap.add_argument("--seed0", type=int, default=1000)
+    ap.add_argument("--seeds", type=str, default="", help="comma-separated seeds to run (each --repeat times) instead of a sweep")
+    ap.add_argument("--repeat", type=int, default=1)
     args = ap.parse_args()
     tile = wordpiece_b200.tile_bytes()
     t_end = time.time() + args.seconds
     seed, fails, cases, total_bytes = args.seed0, 0, 0, 0
     by_entry = {}
-    while time.time() < t_end:
+    todo = [int(x) for x in args.seeds.split(",") if x] * args.repeat
+    while (todo or not args.seeds) and (args.seeds or time.time() < t_end):
+        if args.seeds:
+            seed = todo.pop(0)
         rng = random.Random(seed)
         n = int(10 ** rng.uniform(1.0, 6.4))
         kw = dict(invalid_rate=rng.choice([0.0, 0.0, 0.0005, 0.01, 0.2]),
@@ -81,6 +86,14 @@ def main():
             print(f"EXC seed={seed} entry={entry} n={n} kw={kw}: {e!r}", flush=True)
         if not ok:
             fails += 1
+            try:
+                m = min(len(exp), len(got))
+                diff = np.nonzero(exp[:m] != got[:m])[0]
+                k = int(diff[0]) if diff.size else m
+                print(f"  sizes oracle {len(exp)} gpu {len(got)}, first mismatch at {k}, mismatches {int(diff.size)}: oracle "
+                      f"{exp[max(0, k - 2):k + 6].tolist()} gpu {got[max(0, k - 2):k + 6].tolist()}", flush=True)
+            except Exception:  # noqa: BLE001
+                pass
             print(f"FAIL seed={seed} entry={entry} n={n} kw={kw} memo={os.environ['WORDPIECE_B200_MEMO']} "
                   f"range={os.environ['WORDPIECE_B200_RANGE_BYTES']} pipe={os.environ.get('WORDPIECE_B200_PIPE_CHUNK')}",
                   flush=True)

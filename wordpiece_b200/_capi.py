@@ -141,8 +141,9 @@ def load_library() -> C.CDLL:
     L.wp_encode_into.restype = C.c_int
     L.wp_encode_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), vp]
     L.wp_encode_device.restype = C.c_int
-    L.wp_encode_batch.argtypes = [vp, vp, vp, sz, vp, sz, vp, C.POINTER(sz)]
-    L.wp_encode_batch.restype = C.c_int
+    if hasattr(L, "wp_encode_batch"):  # (an older build loaded through WORDPIECE_B200_LIB for a bisect may lack it)
+        L.wp_encode_batch.argtypes = [vp, vp, vp, sz, vp, sz, vp, C.POINTER(sz)]
+        L.wp_encode_batch.restype = C.c_int
     L.wp_encode_device_async.argtypes = [vp, vp, sz, vp, sz, vp, vp]
     L.wp_encode_device_async.restype = C.c_int
     L.wp_plan_shards.argtypes = [vp, sz, sz, C.POINTER(sz)]

@@ -50,6 +50,21 @@ wp_status fail(wp_status st, const std::string &msg) {
       return fail(WP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorName(_e) + ": " + cudaGetErrorString(_e)); \
   } while (0)
 
+// WORDPIECE_B200_POISON=1 (tests): every device allocation of the library is filled with 0xCD bytes, so that a
+// kernel that reads scratch it has not written shows up in a fresh process as it would on recycled memory.
+// (value = bit mask of allocation classes: 1 scratch, 2 ids / text staging, 4 batch input, 8 batch output, 16 tables,
+// 32 call counters, 64 pipeline slots; "1" alone therefore poisons the scratch only, 127 everything)
+template <class T>
+cudaError_t dev_alloc(T **p, size_t bytes, int cls = 127) {
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), bytes);
+  static const int poison = std::getenv("WORDPIECE_B200_POISON") ? std::atoi(std::getenv("WORDPIECE_B200_POISON")) : 0;
+  if (e == cudaSuccess && (poison & cls)) {
+    e = cudaMemset(*p, 0xCD, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();  // (the library's streams do not wait for the null stream)
+  }
+  return e;
+}
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = false;
@@ -159,14 +174,14 @@ wp_status upload(wp_vocab *v) {
   const wp::HostVocab &h = v->host;
   const size_t b_edges = h.edges.size() * sizeof(wp::Edge);
   const size_t b_words = h.words.size() * sizeof(wp::WordSlot);
-  WP_CUDA(cudaMalloc(&v->d_edges, b_edges));
-  WP_CUDA(cudaMalloc(&v->d_words_static, b_words));
+  WP_CUDA(dev_alloc(&v->d_edges, b_edges, 16));
+  WP_CUDA(dev_alloc(&v->d_words_static, b_words, 16));
   WP_CUDA(cudaMemcpy(v->d_edges, h.edges.data(), b_edges, cudaMemcpyHostToDevice));
   WP_CUDA(cudaMemcpy(v->d_words_static, h.words.data(), b_words, cudaMemcpyHostToDevice));
   v->device_bytes = b_edges + b_words;
   WP_CUDA(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
   WP_CUDA(cudaMallocHost(&v->h_call, sizeof(wp::CallCounters)));
-  WP_CUDA(cudaMalloc(&v->d_call, sizeof(wp::CallCounters)));
+  WP_CUDA(dev_alloc(&v->d_call, sizeof(wp::CallCounters), 32));
   WP_CUDA(cudaDeviceGetAttribute(&v->sm_count, cudaDevAttrMultiProcessorCount, v->device));
   {
     // keep the table a kernel reads at random resident in L2 (best effort: an unsupported attribute only
@@ -247,7 +262,7 @@ wp_status ensure_work(wp_vocab *v, size_t need) {
     if (v->d_work) cudaFree(v->d_work);
     v->d_work = nullptr;
     v->work_bytes = 0;
-    WP_CUDA(cudaMalloc(&v->d_work, need));
+    WP_CUDA(dev_alloc(&v->d_work, need, 1));
     v->work_bytes = need;
   }
   return WP_OK;
@@ -302,7 +317,7 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
       }
       const uint32_t static_lg = log2_of(v->host.words.size());
       if (lg < static_lg) lg = static_lg;  // the static words must fit with room to spare
-      WP_CUDA(cudaMalloc(&v->d_words_work, (size_t(1) << lg) * sizeof(wp::WordSlot)));
+      WP_CUDA(dev_alloc(&v->d_words_work, (size_t(1) << lg) * sizeof(wp::WordSlot), 16));
       v->work_words_log2 = lg;
       if (v->persist_words_bytes) {
         const size_t b = (size_t(1) << lg) * sizeof(wp::WordSlot);
@@ -424,6 +439,9 @@ wp_status enqueue_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_
     P.record_epoch = P.range_index + 1u < wp::WORD_EPOCH_MAX ? P.range_index + 1u : wp::WORD_EPOCH_MAX;
     P.accept_epoch = wp::WORD_EPOCH_MAX;
     if (!overlap) {
+      static const bool poison_scratch = std::getenv("WORDPIECE_B200_POISON_SCRATCH") != nullptr;
+      if (poison_scratch)  // (tests) everything a range must write before it reads, filled with 0xCD on the launching stream
+        WP_CUDA(cudaMemsetAsync(scratch + w.off_seg, 0xCD, w.total - w.off_seg, stream));
       WP_CUDA(cudaMemsetAsync(scratch, 0, w.zero_bytes, stream));
       cudaEvent_t *tev = nullptr;
       if (v->timing) {
@@ -603,8 +621,8 @@ wp_status ensure_pipeline(wp_vocab *v) {
   WP_CUDA(cudaStreamCreateWithFlags(&v->s_h2d, cudaStreamNonBlocking));
   WP_CUDA(cudaStreamCreateWithFlags(&v->s_d2h, cudaStreamNonBlocking));
   for (auto &sl : v->slot) {
-    WP_CUDA(cudaMalloc(&sl.d_text, kPipeChunk + 256));
-    WP_CUDA(cudaMalloc(&sl.d_ids, kPipeChunk * sizeof(int32_t)));  // ids <= bytes
+    WP_CUDA(dev_alloc(&sl.d_text, kPipeChunk + 256, 64));
+    WP_CUDA(dev_alloc(&sl.d_ids, kPipeChunk * sizeof(int32_t), 64));  // ids <= bytes
     WP_CUDA(cudaMallocHost(&sl.h_call, sizeof(wp::CallCounters)));
     WP_CUDA(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
     WP_CUDA(cudaEventCreateWithFlags(&sl.cmp_done, cudaEventDisableTiming));
@@ -1029,7 +1047,7 @@ wp_status wp_encode_into(wp_vocab *v, const char *text, size_t n_bytes, int32_t 
     v->d_text = nullptr;
     v->text_cap = 0;
     const size_t cap = n_bytes + n_bytes / 8 + 256;
-    WP_CUDA(cudaMalloc(&v->d_text, cap));
+    WP_CUDA(dev_alloc(&v->d_text, cap, 2));
     v->text_cap = cap;
   }
   // One id per byte is the worst case (a run of single-byte tokens); allocate what the caller can take,
@@ -1040,7 +1058,7 @@ wp_status wp_encode_into(wp_vocab *v, const char *text, size_t n_bytes, int32_t 
     cudaFree(v->d_ids);
     v->d_ids = nullptr;
     v->ids_cap = 0;
-    WP_CUDA(cudaMalloc(&v->d_ids, want * sizeof(int32_t)));
+    WP_CUDA(dev_alloc(&v->d_ids, want * sizeof(int32_t), 2));
     v->ids_cap = want;
   }
   WP_CUDA(cudaMemcpyAsync(v->d_text, text, n_bytes, cudaMemcpyHostToDevice, v->stream));
@@ -1064,7 +1082,7 @@ static wp_status encode_to_device_buffer(wp_vocab *v, const char *text, size_t n
     v->d_text = nullptr;
     v->text_cap = 0;
     const size_t cap = n_bytes + n_bytes / 8 + 256;
-    WP_CUDA(cudaMalloc(&v->d_text, cap));
+    WP_CUDA(dev_alloc(&v->d_text, cap, 2));
     v->text_cap = cap;
   }
   // first guess: half an id per byte (English-like text needs ~0.25); exact retry if short
@@ -1076,7 +1094,7 @@ static wp_status encode_to_device_buffer(wp_vocab *v, const char *text, size_t n
       cudaFree(v->d_ids);
       v->d_ids = nullptr;
       v->ids_cap = 0;
-      WP_CUDA(cudaMalloc(&v->d_ids, guess * sizeof(int32_t)));
+      WP_CUDA(dev_alloc(&v->d_ids, guess * sizeof(int32_t), 2));
       v->ids_cap = guess;
     }
     const uint64_t before = v->stats.kernel_launches;
@@ -1174,7 +1192,7 @@ wp_status ensure_batch_slot(wp_vocab::BatchSlot &b, const PartPlan &p, size_t id
     b.in_cap = 0;
     const size_t cap = p.in_bytes + p.in_bytes / 4 + 4096;
     WP_CUDA(cudaMallocHost(&b.h_in, cap));
-    WP_CUDA(cudaMalloc(&b.d_in, cap));
+    WP_CUDA(dev_alloc(&b.d_in, cap, 4));
     b.in_cap = cap;
   }
   if (p.out_bytes > b.out_cap) {
@@ -1182,7 +1200,7 @@ wp_status ensure_batch_slot(wp_vocab::BatchSlot &b, const PartPlan &p, size_t id
     b.d_out = nullptr;
     b.out_cap = 0;
     const size_t cap = p.out_bytes + p.out_bytes / 4 + 256;
-    WP_CUDA(cudaMalloc(&b.d_out, cap));
+    WP_CUDA(dev_alloc(&b.d_out, cap, 8));
     b.out_cap = cap;
   }
   if (n + 1 > b.offsets_cap) {
@@ -1198,7 +1216,7 @@ wp_status ensure_batch_slot(wp_vocab::BatchSlot &b, const PartPlan &p, size_t id
     b.d_ids = nullptr;
     b.ids_cap = 0;
     const size_t cap = ids_want + ids_want / 8 + 256;
-    WP_CUDA(cudaMalloc(&b.d_ids, cap * sizeof(int32_t)));
+    WP_CUDA(dev_alloc(&b.d_ids, cap * sizeof(int32_t), 2));
     b.ids_cap = cap;
   }
   if (!b.h_call) {
@@ -1568,7 +1586,7 @@ wp_status wp_encode_text(wp_vocab *v, const char *text, size_t n_bytes, char **o
       v->d_fmt = nullptr;
       v->fmt_cap = 0;
       const size_t cap = static_cast<size_t>(total) + static_cast<size_t>(total) / 8 + 256;
-      WP_CUDA(cudaMalloc(&v->d_fmt, cap));
+      WP_CUDA(dev_alloc(&v->d_fmt, cap));
       v->fmt_cap = cap;
     }
     WP_CUDA(wp::launch_format(v->d_ids, cnt, v->d_fmt, w + 2, reinterpret_cast<unsigned int *>(w + 1), v->sm_count,

@@ -45,8 +45,10 @@
 // Debug build (make variant NAME=bounds DEFS=-DWP_DEBUG_BOUNDS): every index into the scratch arrays, the lists in
 // shared memory and the output is checked where it is used; a violation prints its place and traps.  The
 // parity suites and the fuzz sweep are run under this build once per round (tools/gpu_bounds.sh).
-#ifdef WP_DEBUG_BOUNDS
+#if defined(WP_DEBUG_BOUNDS) || defined(WP_K2L_TRACE)
 #include <cstdio>
+#endif
+#ifdef WP_DEBUG_BOUNDS
 #define WP_CHECK(cond)                                                                                              \
   do {                                                                                                              \
     if (!(cond)) {                                                                                                  \
@@ -102,7 +104,10 @@ constexpr int SCATTER_THREADS = 256;             // K3
 constexpr int SCATTER_ITEMS = 8;                 // segments per thread and block iteration
 constexpr int SCATTER_SEGS = SCATTER_THREADS * SCATTER_ITEMS;  // 2048
 constexpr int SCATTER_STAGE = 6144;              // ids staged in shared memory per block iteration
-constexpr int SCATTER_BIG = 8;                   // a segment with more ids (a long word, a URL, a blob) is copied by a whole warp
+#ifndef WP_SCATTER_BIG
+#define WP_SCATTER_BIG 8
+#endif
+constexpr int SCATTER_BIG = WP_SCATTER_BIG;      // a segment with more ids (a long word, a URL, a blob) is copied by a whole warp
 
 static_assert(RAW_BYTES % 16 == 0, "raw buffer is loaded in 16-byte units");
 static_assert(WORD_KEY_BYTES + 4 <= LOOKAHEAD, "key window reads stay inside the loaded bytes");
@@ -154,9 +159,12 @@ static_assert(WP_K1_SEG_CAP <= TILE && WP_K1_SEG_CAP % 8 == 0, "list capacity");
 
 // ------------------------------------------------------------------- helpers
 
+// Streaming 16-byte load of text: not kept in L1 — and NOT through the non-coherent path (.nc): the buffer the text
+// lives in is rewritten between calls (staging buffers, pipeline slots), and a .nc load may be served from a line
+// an earlier kernel left in the SM's cache.
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
   return r;
@@ -1224,9 +1232,12 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
     if (needm && cursor < cursor_end) {
       const uint32_t i = cursor + __popc(needm & ((1u << lane) - 1u));
       cursor += __popc(needm);  // may pass cursor_end; entries beyond it are simply not taken
-      if (cursor + lane < cursor_end) prefetch_l1(&P.slow[cursor + lane]);  // the next 32 entries of this share
+      if (cursor + lane < cursor_end) prefetch_l2(&P.slow[cursor + lane]);  // the next 32 entries of this share
       if (!have && i < cursor_end) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(&P.slow[i]));
+        // (L2, coherent: K2 itself rewrites entries of this array, and the array is rewritten by every call.  With
+        // a non-coherent load a lane could be served a line that an earlier call left in the SM's cache, take a
+        // LONG entry for the plain entry that used to sit there, and overwrite it with a result)
+        const uint4 raw = __ldcg(reinterpret_cast<const uint4 *>(&P.slow[i]));
         const uint32_t meta = raw.y;
         if (!(meta & SLOW_META_LONG)) {  // LONG entries are matched by K2L
           ent_index = i;
@@ -1404,7 +1415,11 @@ static_assert((1 << LONG_LEVELS) >= LONG_BLOCK, "the strides must reach across a
 
 struct LongSmem {
   uint16_t jump[LONG_LEVELS][LONG_BLOCK];
+#ifdef WP_K2L_RANK32
+  uint32_t rank[LONG_BLOCK];
+#else
   uint16_t rank[LONG_BLOCK];
+#endif
   uint32_t delta[LONG_BLOCK];  // raw bytes from a piece start to the position behind its longest match (0 = none)
   int32_t id[LONG_BLOCK];
   uint8_t code[LONG_BLOCK];    // 0 = dropped / continuation byte, 1 = lead of an ordinary char
@@ -1546,13 +1561,34 @@ __global__ void __launch_bounds__(LONG_THREADS) wp_long_kernel(EncodeParams P) {
         sm.code[i] = static_cast<uint8_t>(code);
         sm.delta[i] = delta;
         sm.id[i] = id;
-        sm.rank[i] = static_cast<uint16_t>(LONG_END);
+        sm.rank[i] = static_cast<decltype(sm.rank[0] + 0)>(LONG_END) & 0xFFFFu;
       }
       if (tid == 0) {
         sm.n_round = 0;
         sm.cur_next = b0 + n;  // (a block without a piece start: only dropped bytes)
       }
       __syncthreads();
+#ifdef WP_K2L_SERIAL
+      // (hunt build: the chain followed by one thread, as a cross-check of the ranking below)
+      if (tid == 0) {
+        uint32_t i = 0, cnt = 0;
+        while (i < n) {
+          if (sm.code[i] == 0) {
+            i++;
+            continue;
+          }
+          const uint32_t dl = sm.delta[i];
+          if (dl == 0) {
+            sm.failed = 1;
+            break;
+          }
+          out[n_out + cnt++] = sm.id[i];
+          i += dl;
+        }
+        sm.n_round = cnt;
+        sm.cur_next = b0 + i;
+      }
+#else
       // B: successors (the first valid lead at or behind the end of the match), doubled LONG_LEVELS - 1 times
 #pragma unroll 1
       for (uint32_t i = tid; i < n; i += LONG_THREADS) {
@@ -1588,7 +1624,25 @@ __global__ void __launch_bounds__(LONG_THREADS) wp_long_kernel(EncodeParams P) {
           if (r == LONG_END) continue;
           const uint32_t j = sm.jump[k][i];
           WP_CHECK(j == LONG_END || (j < n && j > i && r + (1u << k) < LONG_BLOCK));
+#ifdef WP_K2L_SNAP
+          (void)j;
+        }
+        // (hunt build: every thread first reads, then — behind a barrier — writes)
+        uint32_t tj[LONG_BLOCK / LONG_THREADS], tv2[LONG_BLOCK / LONG_THREADS];
+        int q = 0;
+        for (uint32_t i = tid; i < n; i += LONG_THREADS, q++) {
+          const uint32_t r = sm.rank[i];
+          const uint32_t j = r == LONG_END ? LONG_END : sm.jump[k][i];
+          tj[q] = j;
+          tv2[q] = r + (1u << k);
+        }
+        __syncthreads();
+        q = 0;
+        for (uint32_t i = tid; i < n; i += LONG_THREADS, q++) {
+          if (tj[q] != LONG_END) sm.rank[tj[q]] = static_cast<uint16_t>(tv2[q]);
+#else
           if (j != LONG_END) sm.rank[j] = static_cast<uint16_t>(r + (1u << k));
+#endif
         }
         __syncthreads();
       }
@@ -1609,8 +1663,14 @@ __global__ void __launch_bounds__(LONG_THREADS) wp_long_kernel(EncodeParams P) {
           }
         }
       }
+#endif
       __syncthreads();
       if (tid == 0) {
+#ifdef WP_K2L_TRACE
+        printf("K2L entry %u round b0 %llu n %u n_out %u n_round %u cur_next %llu failed %u seg_end %llu\n", sm.entry,
+               static_cast<unsigned long long>(b0), n, n_out, sm.n_round, sm.cur_next, sm.failed,
+               static_cast<unsigned long long>(seg_end));
+#endif
         sm.n_out = n_out + sm.n_round;
         sm.cur = sm.cur_next;
         if (sm.failed || sm.cur_next >= seg_end) sm.finished = 1;
@@ -1619,6 +1679,11 @@ __global__ void __launch_bounds__(LONG_THREADS) wp_long_kernel(EncodeParams P) {
     }
     if (tid == 0) {
       uint32_t cnt = sm.n_out;
+#ifdef WP_K2L_TRACE
+      printf("K2L entry %u done: start %llu seg_end %llu n_out %u failed %u word_first %u off %u\n", sm.entry,
+             static_cast<unsigned long long>(start), static_cast<unsigned long long>(seg_end), sm.n_out, sm.failed,
+             sm.word_first, sm.off);
+#endif
       if (sm.failed) {  // fast.cpp:79-88: the word's pieces are rolled back, one UNK stands for it
         cnt = sm.word_first + 1;
         P.arena[sm.off + sm.word_first] = static_cast<uint32_t>(V.unk_id);
@@ -1638,7 +1703,7 @@ struct ScatterSmem {
   uint32_t desc_src[SCATTER_SEGS];     // ... and their seg_result word (where the ids are)
   uint32_t n_desc;
   uint32_t n_big;                      // segments with more than SCATTER_BIG ids: copied by the whole block
-  uint16_t big[SCATTER_STAGE / SCATTER_BIG + 2];  // staged path: their indices in desc_pos / desc_src
+  uint16_t big[SCATTER_STAGE / (SCATTER_BIG < 6144 ? SCATTER_BIG : 6144) + 2];  // staged path: their indices in desc_pos / desc_src
   uint32_t warp_sums[SCATTER_THREADS / 32];
   uint32_t block_index[2];
   unsigned long long base;
@@ -2155,14 +2220,22 @@ cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_
   if (phases & PHASE_MATCH) {
     // = resident capacity (see the launch bound): one wave, large shares; a small range (a 4 KiB call is ONE tile)
     // gets a grid to match — a tile has at most MAX_TILE_SLOW unsettled segments, 8 warps x 32 lanes take 256 at a time
+#ifdef WP_NO_GRID_TRIM
+    cfg.gridDim = dim3(sm_count * WP_K2_BLOCKS);
+#else
     cfg.gridDim = dim3(min(static_cast<unsigned>(sm_count * WP_K2_BLOCKS), P.n_tiles * 4u));
+#endif
     cfg.blockDim = dim3(MATCH_THREADS);
     cfg.dynamicSmemBytes = 0;
     cfg.numAttrs = window(P.vocab.edges, P.persist_edges_bytes, P.persist_edges_ratio);
     e = cudaLaunchKernelEx(&cfg, wp_match_kernel, P);
     if (e != cudaSuccess) return e;
 
+#ifdef WP_NO_GRID_TRIM
+    cfg.gridDim = dim3(sm_count * 8);
+#else
     cfg.gridDim = dim3(min(static_cast<unsigned>(sm_count * 8), P.n_tiles * 2u + 2u));  // (one CTA per long segment, by ticket)
+#endif
     cfg.blockDim = dim3(LONG_THREADS);
     e = cudaLaunchKernelEx(&cfg, wp_long_kernel, P);
     if (e != cudaSuccess) return e;
@@ -2170,7 +2243,11 @@ cudaError_t launch_encode_range(const EncodeParams &P, int sm_count, cudaStream_
   }
   if (timing) cudaEventRecord(timing[2], stream);
   if (phases & PHASE_SCATTER) {
+#ifdef WP_NO_GRID_TRIM
+    cfg.gridDim = dim3(sm_count * WP_K3_BLOCKS);
+#else
     cfg.gridDim = dim3(min(static_cast<unsigned>(sm_count * WP_K3_BLOCKS), P.n_tiles * 2u));  // a tile has at most two blocks of segments
+#endif
     cfg.blockDim = dim3(SCATTER_THREADS);
     cfg.dynamicSmemBytes = 0;
     cfg.numAttrs = window(P.words, P.persist_words_bytes, P.persist_words_ratio);
