@@ -631,3 +631,33 @@ def test_dense_tiles_fall_back_to_full_lists(gpu_device):
     assert np.array_equal(o.encode(text), d_ids[:n].cpu().numpy())
     v2.close()
     v3.close()
+
+
+def test_repeated_calls_on_one_handle_with_long_runs(gpu_device):
+    """Regression (round 2): the last segment of a tile may have no end inside the tile's window; its end entry in
+    shared memory was then never written, and when the stale value there happened to be the "undecided single
+    char" marker, K1's pass for those overwrote the START of the long segment with a token id — wrong ids that
+    depended on the kernels that had run before.  Found by the randomised sweep (seed 1140); this is its small
+    form: texts with several long space-free runs, three calls each on ONE handle (the first call was right,
+    later ones wrong)."""
+    import re
+
+    from wordpiece_b200 import Vocab
+
+    text, vocab = textgen.case(1140, 1_192_536, invalid_rate=0.0, long_run_rate=0.02, long_tokens=5)
+    o = Oracle(vocab)
+    v = Vocab(vocab, device=gpu_device)
+    runs = [(m.start(), m.end()) for m in re.finditer(rb"[^ \n\t\r]{257,}", text)]
+    assert len(runs) > 100
+    for a, b in runs[:120:4]:
+        lo, hi = max(0, a - 3000), min(len(text), b + 3000)
+        while lo > 0 and text[lo - 1:lo] not in (b" ", b"\n"):
+            lo -= 1
+        while hi < len(text) and text[hi:hi + 1] not in (b" ", b"\n"):
+            hi += 1
+        t = text[lo:hi]
+        exp = o.encode(t)
+        for rep in range(3):
+            got = v.encode(t)
+            assert np.array_equal(exp, got), (a, b, rep, len(exp), len(got))
+    v.close()

@@ -30,6 +30,12 @@ const char *const kHostOnly = "host-only vocabulary handle (device -1): encoding
 std::atomic<uint64_t> g_launches{0};
 
 // WORDPIECE_B200_TRACE=1: wall-clock milestones of a process on stderr (where does a short job's time go?)
+// WORDPIECE_B200_TRACE=2 additionally waits for the stream at every stage of a batch part, so that the
+// differences between milestones are the stages' own durations (a diagnosis mode: it serialises the pipeline)
+bool trace_stage_sync() {
+  static const bool on = std::getenv("WORDPIECE_B200_TRACE") != nullptr && std::atoi(std::getenv("WORDPIECE_B200_TRACE")) >= 2;
+  return on;
+}
 void trace(const char *what) {
   static const bool on = std::getenv("WORDPIECE_B200_TRACE") != nullptr;
   if (!on) return;
@@ -1277,12 +1283,20 @@ wp_status enqueue_part(wp_vocab *v, wp_vocab::BatchSlot &b, const PartPlan &p, c
   batch.d_bound_seg = reinterpret_cast<uint32_t *>(b.d_out);
   batch.d_offsets = reinterpret_cast<unsigned long long *>(b.d_out + p.off_offsets);
   WP_CUDA(cudaMemcpyAsync(b.d_in, b.h_in, p.in_bytes, cudaMemcpyHostToDevice, copy_stream));
+  if (trace_stage_sync()) {
+    WP_CUDA(cudaStreamSynchronize(copy_stream));
+    trace("wp_encode_batch:   [stage] input block on the device");
+  }
   if (copy_stream != v->stream) {
     WP_CUDA(cudaEventRecord(b.h2d_done, copy_stream));
     WP_CUDA(cudaStreamWaitEvent(v->stream, b.h2d_done, 0));
   }
   wp_status st = enqueue_encode(v, b.d_in + p.off_text, p.packed, b.d_ids, b.ids_cap, v->stream, spill, info, warm, call_bytes, &batch);
   if (st != WP_OK) return st;
+  if (trace_stage_sync()) {
+    WP_CUDA(cudaStreamSynchronize(v->stream));
+    trace("wp_encode_batch:   [stage] kernels done");
+  }
   uint64_t launches = 0;
   WP_CUDA(wp::launch_publish_count(v->d_call, info->n_ranges & 1u, batch.d_offsets + n, v->stream, &launches));
   WP_CUDA(cudaEventRecord(v->last_done, v->stream));
@@ -1367,6 +1381,10 @@ wp_status wp_encode_batch(wp_vocab *v, const char *const *texts, const size_t *l
       WP_CUDA(cudaMemcpyAsync(ids + total, b.d_ids, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, out_stream));
     }
     WP_CUDA(cudaEventRecord(b.d2h_done, out_stream));
+    if (trace_stage_sync()) {
+      WP_CUDA(cudaStreamSynchronize(out_stream));
+      trace("wp_encode_batch:   [stage] ids on the host");
+    }
     total += cnt;
     return WP_OK;
   };

@@ -159,9 +159,8 @@ static_assert(WP_K1_SEG_CAP <= TILE && WP_K1_SEG_CAP % 8 == 0, "list capacity");
 
 // ------------------------------------------------------------------- helpers
 
-// Streaming 16-byte load of text: not kept in L1 — and NOT through the non-coherent path (.nc): the buffer the text
-// lives in is rewritten between calls (staging buffers, pipeline slots), and a .nc load may be served from a line
-// an earlier kernel left in the SM's cache.
+// Streaming 16-byte load of text: not kept in L1 (and through the coherent path: the buffers the text lives in are
+// rewritten between calls).
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
   uint4 r;
   asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -894,6 +893,12 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
     if (tid == 0) {
       sm.n_segs = totals & 0xFFFFu;
       sm.n_ends = totals >> 16;
+      // The last owned segment may have no end inside the window (it leaves the window, or the compacted text
+      // of a dirty tile ends with it): its end entry, seg_e[n_ends], is read below like any other and must not
+      // look like a parked PARK_PENDING.  (Left to whatever an earlier kernel had in this shared memory, it made
+      // the pass for undecided single-char segments overwrite the START of a long segment with a token id: wrong
+      // ids that depended on the kernels that had run before — found by the randomised sweep)
+      sm.seg_e[totals >> 16] = 0;
     }
   }
   __syncthreads();
@@ -1024,7 +1029,8 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
   if (sm.any_single) {  // uniform
 #pragma unroll 1
     for (uint32_t k = tid; k < n_segs; k += THREADS) {
-      if (sm.seg_e[k + skip] != PARK_PENDING) continue;  // (an end position and a parked high half are smaller)
+      if (sm.seg_e[k + skip] != PARK_PENDING) continue;  // (an end position and a parked high half are smaller; the
+                                                         //  entry of a segment without an end was zeroed in S1d)
       uint32_t r[4];
       load_window(buf, static_cast<int>(sm.seg_s[k] & POS_MASK), r);
       const uint32_t len = utf8_lead_len(r[0] & 0xFFu);
@@ -1145,6 +1151,10 @@ __global__ void __launch_bounds__(THREADS) wp_split_kernel(EncodeParams P) {
         out.off = 0;
         out.meta = ((sv >> 14) << 16) | SLOW_META_LONG | (static_cast<uint32_t>((pos >> 32) & 0xFFu) << 24);
         out.pos_lo = static_cast<uint32_t>(pos);
+#ifdef WP_K2L_TRACE
+        printf("K1 tile %u LONG k %u wpos %d pos %llu slot %u long_at %u seg %u (thread %d, lo %u hi %u)\n", rel_tile, k, wpos,
+               static_cast<unsigned long long>(pos), slow_base + i, long_at, out.seg, tid, lo, hi);
+#endif
         if (long_at < P.long_capacity) P.long_list[long_at] = slow_base + i;  // K2L's work list
         long_at++;
       } else {
@@ -1234,9 +1244,8 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
       cursor += __popc(needm);  // may pass cursor_end; entries beyond it are simply not taken
       if (cursor + lane < cursor_end) prefetch_l2(&P.slow[cursor + lane]);  // the next 32 entries of this share
       if (!have && i < cursor_end) {
-        // (L2, coherent: K2 itself rewrites entries of this array, and the array is rewritten by every call.  With
-        // a non-coherent load a lane could be served a line that an earlier call left in the SM's cache, take a
-        // LONG entry for the plain entry that used to sit there, and overwrite it with a result)
+        // (L2, coherent: K2 itself rewrites entries of this array — results are stored in place — so the
+        // non-coherent path, which PTX allows only for data that is read-only during the whole kernel, is out)
         const uint4 raw = __ldcg(reinterpret_cast<const uint4 *>(&P.slow[i]));
         const uint32_t meta = raw.y;
         if (!(meta & SLOW_META_LONG)) {  // LONG entries are matched by K2L
@@ -1352,6 +1361,9 @@ __global__ void __launch_bounds__(MATCH_THREADS, WP_K2_BLOCKS) wp_match_kernel(E
       out[2] = t2;
       res = make_uint4(nid, area, 0u, 0u);
     }
+#ifdef WP_K2L_TRACE
+    if (seg_len > 300u) printf("K2 writes a result to slot %u: seg_len %u seg %u nid %u\n", ent_index, seg_len, seg, nid);
+#endif
     *reinterpret_cast<uint4 *>(&P.slow[ent_index]) = res;
     P.seg_result[seg] = SEG_RESULT_SLOW | (min(nid, SEG_SLOW_COUNT_MAX) << SEG_SLOW_INDEX_BITS) | ent_index;
     have = false;
@@ -1445,6 +1457,10 @@ __global__ void __launch_bounds__(LONG_THREADS) wp_long_kernel(EncodeParams P) {
     if (sm.entry >= n_long) break;
     const uint32_t si = P.long_list[sm.entry];
     const SlowEntry ent = P.slow[si];
+#ifdef WP_K2L_TRACE
+    if (tid == 0)
+      printf("K2L entry %u takes slot %u: off %u meta 0x%x pos_lo %u seg %u\n", sm.entry, si, ent.off, ent.meta, ent.pos_lo, ent.seg);
+#endif
     const size_t start = static_cast<size_t>(ent.pos_lo) | (static_cast<size_t>(ent.meta >> 24) << 32);
     uint32_t len0, cls0;
     gnext(tv, start, &len0, &cls0);  // the start is a valid lead of a non-space class
