@@ -58,10 +58,30 @@ def main():
             os.environ["WORDPIECE_B200_PIPE_CHUNK"] = str(rng.choice([4096, 20000, 150000]))
         else:
             os.environ.pop("WORDPIECE_B200_PIPE_CHUNK", None)
-        entry = rng.choice(["encode", "encode_into", "encode_into_pinned", "encode_device", "encode_text"])
+        os.environ["WORDPIECE_B200_TICKET"] = "1" if rng.random() < 0.1 else "0"
+        entry = rng.choice(["encode", "encode_into", "encode_into_pinned", "encode_device", "encode_text", "encode_batch"])
         v = wordpiece_b200.Vocab(vocab, device=0)
+        if rng.random() < 0.3:  # a handle that has already encoded something else (scratch, memo and shared memory in use)
+            other, _ = textgen.case(seed + 77777, min(n, 200000), **kw)
+            v.encode(other)
         try:
-            if entry == "encode":
+            if entry == "encode_batch":
+                # the text cut at arbitrary BYTE positions (also inside a UTF-8 sequence, inside a word): every piece
+                # must get the ids the oracle gives that piece alone
+                k_cuts = rng.choice([0, 1, 3, 17, 200, 3000])
+                cuts = sorted(rng.randrange(0, len(text) + 1) for _ in range(k_cuts)) if text else []
+                pieces = [text[a:b] for a, b in zip([0] + cuts, cuts + [len(text)])]
+                if rng.random() < 0.5:
+                    os.environ["WORDPIECE_B200_BATCH_PART"] = str(rng.choice([256, 5000, 70000]))
+                else:
+                    os.environ.pop("WORDPIECE_B200_BATCH_PART", None)
+                o = Oracle(vocab)
+                exp_parts = [o.encode(p) for p in pieces]
+                exp = np.concatenate(exp_parts) if exp_parts else np.zeros(0, np.int32)
+                got, offs = v.encode_batch(pieces)
+                exp_offs = np.concatenate([[0], np.cumsum([len(e) for e in exp_parts])])
+                assert np.array_equal(np.asarray(offs, dtype=np.int64), exp_offs.astype(np.int64)), "text offsets differ"
+            elif entry == "encode":
                 got = v.encode(text)
             elif entry == "encode_into":
                 out = np.full(len(exp) + 3, -7, np.int32)

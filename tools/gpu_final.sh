@@ -18,3 +18,5 @@ for wl in en ja; do
       --metrics lts__t_sector_hit_rate.pct,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum,lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum,l1tex__t_sector_hit_rate.pct,dram__bytes_read.sum,gpu__time_duration.sum \
       --log-file $OUT/k2_warm_l2_${wl}_$TAG.csv python tools/profile_workload.py $wl --mib 128 --reps 1 > $OUT/k2_warm_${wl}_$TAG.log 2>&1; echo "k2 warm-cache $wl rc=$?"
 done
+WORDPIECE_B200_TRACE=1 timeout -k 10 200 python tools/batch_trace.py > $OUT/batch_trace_$TAG.log 2>&1; echo "batch trace rc=$?"
+WORDPIECE_B200_TRACE=2 timeout -k 10 200 python tools/batch_trace.py > $OUT/batch_stages_$TAG.log 2>&1; echo "batch stages rc=$?"
