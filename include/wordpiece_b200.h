@@ -205,6 +205,9 @@ size_t wp_debug_table_nodes(const wp_vocab *v);
 size_t wp_debug_long_tokens(const wp_vocab *v);
 /* chunk plan of the host-buffer pipeline (cut offsets, first 0, last n); 0 if the text cannot be cut */
 size_t wp_debug_plan_chunks(const char *text, size_t n, size_t chunk, size_t *cuts, size_t cap);
+/* host-only run of the staging copies: mode 0/1 = the batch packer (ordinary / streaming stores), 2/3 = the
+ * pooled copy of texts[0]; returns the bytes written to out */
+size_t wp_debug_stage(const char *const *texts, const size_t *lens, size_t n, char *out, size_t out_cap, int mode);
 /* code points of single-char word-initial tokens whose word-table slot lies at least min_displacement slots
  * from its home slot; returns their number */
 size_t wp_debug_displaced_singles(const wp_vocab *v, uint32_t min_displacement, uint32_t *out, size_t cap);

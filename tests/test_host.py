@@ -266,3 +266,40 @@ def test_batch_packing_rule_is_exact():
         whole = o.encode(b"".join(t + b" " for t in texts))
         parts = np.concatenate([o.encode(t) for t in texts])
         assert np.array_equal(whole, parts)
+
+
+def test_staging_copies_are_exact():
+    """The copies that stage caller memory into pinned buffers (batch packer, pooled copy) with ordinary and with
+    streaming stores: byte-exact for every alignment and size, including texts that share a cache line, empty
+    texts, pieces longer than the writer's gather buffer, and shares cut across the pool's threads."""
+    import random
+
+    from wordpiece_b200._capi import debug_stage
+
+    rng = random.Random(5)
+    blob = bytes(rng.randrange(256) for _ in range(70000))
+
+    def piece(n):
+        a = rng.randrange(0, len(blob) - n + 1) if n <= len(blob) else 0
+        return (blob * (n // len(blob) + 2))[a:a + n]
+
+    shapes = [
+        [],
+        [b""],
+        [b"", b"", b""],
+        [b"a"],
+        [piece(n) for n in (1, 2, 62, 63, 64, 65, 127, 128, 129, 0, 255, 256, 257)],
+        [piece(rng.randrange(0, 40)) for _ in range(3000)],               # many texts per cache line
+        [piece(rng.randrange(0, 9000)) for _ in range(300)],              # around the gather buffer's size
+        [piece(8192), piece(8191), piece(8193), piece(16384), piece(100000), b"x", piece(70001)],
+        [piece(rng.randrange(3000, 5000)) for _ in range(700)],           # > 1 MiB: packed by the whole pool
+        [piece(1), piece(3 << 20), piece(5)],                             # one long text across the shares
+    ]
+    for texts in shapes:
+        want = b"".join(t + b" " for t in texts)
+        for mode in (0, 1):
+            assert debug_stage(texts, mode) == want, (mode, len(texts))
+    for n in (0, 1, 63, 64, 255, 256, 257, 4096, 1 << 20, (1 << 20) + 1, (3 << 20) + 77):
+        src = piece(n)
+        for mode in (2, 3):
+            assert debug_stage([src], mode) == src, (mode, n)

@@ -36,7 +36,7 @@ def main():
     for r in rows[2:]:
         d = dict(zip(hdr, r))
         u = dict(zip(hdr, units))
-        name = d["Kernel Name"].split("(")[0]
+        name = d["Kernel Name"].split("(")[0].replace("void ", "").split("<")[0].split("::")[-1]  # wp_split_kernel<3072> -> wp_split_kernel
         k = {}
         for m, short in METRICS.items():
             if m in d and d[m] != "":

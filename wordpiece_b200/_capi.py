@@ -96,6 +96,7 @@ EXPORTED_SYMBOLS = [
     "wp_debug_static_words",
     "wp_debug_word_lookup",
     "wp_debug_plan_chunks",
+    "wp_debug_stage",
 ]
 
 _lib = None
@@ -174,6 +175,8 @@ def load_library() -> C.CDLL:
         getattr(L, f).restype = sz
     L.wp_debug_plan_chunks.argtypes = [vp, sz, sz, C.POINTER(sz), sz]
     L.wp_debug_plan_chunks.restype = sz
+    L.wp_debug_stage.argtypes = [C.POINTER(C.c_char_p), C.POINTER(sz), sz, vp, sz, C.c_int]
+    L.wp_debug_stage.restype = sz
     L.wp_debug_displaced_singles.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint32), sz]
     L.wp_debug_displaced_singles.restype = sz
     L.wp_debug_word_lookup.argtypes = [vp, C.c_char_p, sz, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]
@@ -462,6 +465,19 @@ def debug_plan_chunks(text: bytes, chunk: int) -> list:
     buf = (C.c_size_t * cap)()
     n = int(L.wp_debug_plan_chunks(text, len(text), chunk, buf, cap))
     return [int(buf[i]) for i in range(min(n, cap))]
+
+
+def debug_stage(texts: Sequence[bytes], mode: int) -> bytes:
+    """The library's staging copies run on the host (test hook, no device): mode 0/1 = batch packer with ordinary /
+    streaming stores, 2/3 = pooled copy of texts[0] ordinary / streamed."""
+    L = load_library()
+    n = len(texts)
+    ptrs = (C.c_char_p * max(n, 1))(*texts)
+    lens = (C.c_size_t * max(n, 1))(*[len(t) for t in texts])
+    cap = sum(len(t) for t in texts) + n + 64
+    out = C.create_string_buffer(cap)
+    k = int(L.wp_debug_stage(ptrs, lens, n, out, cap, mode))
+    return out.raw[:k]
 
 
 def _cached_vocab(tokens: Sequence[Union[str, bytes]], device: Optional[int]) -> Vocab:

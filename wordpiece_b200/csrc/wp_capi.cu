@@ -3,6 +3,7 @@
 // All tokenisation work happens in the CUDA kernels of wp_encode.cu; there is no
 // CPU fallback — without a usable CUDA device every call fails loudly.
 #include <cuda_runtime.h>
+#include <emmintrin.h>
 
 #include <algorithm>
 #include <atomic>
@@ -527,6 +528,105 @@ wp_status run_encode(wp_vocab *v, const void *d_text, size_t n_bytes, int32_t *d
   return fail(WP_ERR_CUDA, "internal scratch overflow");
 }
 
+// ---- copies into pinned staging memory with STREAMING (non-temporal) stores
+// Measured on the B200 box (profiles/r2r_batch_stages.txt): the H2D copy of an 8 MiB pinned block that the CPU
+// has just written with ordinary stores runs at 6 GB/s, a D2H of the same size at 50 GB/s — the DMA engine has to
+// pull every line out of the writing cores' caches.  Streaming stores go to memory through the write-combining
+// buffers and leave nothing behind in the caches, so the copy engine reads plain DRAM.  (glibc's memcpy does this
+// on its own only above a threshold of several MB per call.)  WORDPIECE_B200_STREAM_STORES=0 switches back.
+bool stream_stores() {
+  static const bool on = [] {
+    const char *e = std::getenv("WORDPIECE_B200_STREAM_STORES");
+    return e == nullptr || std::atoi(e) != 0;
+  }();
+  return on;
+}
+
+// dst 64-byte aligned, n a multiple of 64
+inline void stream_lines(char *dst, const char *src, size_t n) {
+  for (size_t i = 0; i < n; i += 64) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
+    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 16));
+    const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 32));
+    const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 48));
+    _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), a);
+    _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 16), b);
+    _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 32), c);
+    _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 48), d);
+  }
+}
+
+// memcpy whose whole cache lines are written with streaming stores (the ragged head and tail with ordinary ones).
+// The caller issues stream_fence() once it has written its share, before anybody is told that the data is there.
+inline void stream_copy(void *dst, const void *src, size_t n) {
+  char *d = static_cast<char *>(dst);
+  const char *s = static_cast<const char *>(src);
+  if (n < 256) {
+    std::memcpy(d, s, n);
+    return;
+  }
+  const size_t head = (64 - (reinterpret_cast<uintptr_t>(d) & 63u)) & 63u;
+  std::memcpy(d, s, head);
+  const size_t body = (n - head) & ~size_t(63);
+  stream_lines(d + head, s + head, body);
+  std::memcpy(d + head + body, s + head + body, n - head - body);
+}
+inline void stream_fence() { _mm_sfence(); }
+
+// Many small pieces -> one contiguous destination, streamed: the pieces are gathered in a small buffer that
+// stays in the core's L1 and leave it as whole cache lines, so that a line shared by two texts is still written
+// once, by one streaming store.
+class StreamWriter {
+ public:
+  explicit StreamWriter(char *dst) : dst_(dst) {}
+  void put(const char *p, size_t n) {
+    while (n) {
+      if (fill_ == 0 && (reinterpret_cast<uintptr_t>(dst_) & 63u)) {  // (only at the start: up to the first line border)
+        size_t k = 64 - (reinterpret_cast<uintptr_t>(dst_) & 63u);
+        if (k > n) k = n;
+        std::memcpy(dst_, p, k);
+        dst_ += k;
+        p += k;
+        n -= k;
+        continue;
+      }
+      if (fill_ == 0 && n >= sizeof(buf_)) {  // a long piece: straight from the source
+        const size_t k = n & ~size_t(63);
+        stream_lines(dst_, p, k);
+        dst_ += k;
+        p += k;
+        n -= k;
+        continue;
+      }
+      size_t k = sizeof(buf_) - fill_;
+      if (k > n) k = n;
+      std::memcpy(buf_ + fill_, p, k);
+      fill_ += k;
+      p += k;
+      n -= k;
+      if (fill_ == sizeof(buf_)) {
+        stream_lines(dst_, buf_, fill_);
+        dst_ += fill_;
+        fill_ = 0;
+      }
+    }
+  }
+  void put(char c) { put(&c, 1); }
+  void finish() {
+    const size_t k = fill_ & ~size_t(63);
+    stream_lines(dst_, buf_, k);
+    std::memcpy(dst_ + k, buf_ + k, fill_ - k);
+    dst_ += fill_;
+    fill_ = 0;
+    stream_fence();
+  }
+
+ private:
+  char *dst_;
+  size_t fill_ = 0;
+  alignas(64) char buf_[8192];
+};
+
 // Host threads that copy between a caller's pageable memory and the pinned staging buffers of the pipeline.
 // One memcpy stream moves 5-10 GB/s (less into pages that are touched for the first time, e.g. the storage of
 // a fresh std::vector), a quarter of what PCIe 5 x16 takes: the copy is cut into one slice per thread.
@@ -558,16 +658,30 @@ class CopyPool {
     cv_done_.wait(lk, [&] { return pending_ == 0; });
     job_ = nullptr;
   }
-  // memcpy(dst, src, n) in one slice per thread
-  void copy(void *dst, const void *src, size_t n) {
+  // memcpy(dst, src, n) in one slice per thread.  `streamed`: the destination is pinned memory that a copy engine
+  // reads next (see stream_copy).
+  void copy(void *dst, const void *src, size_t n, bool streamed = false) {
+    streamed = streamed && stream_stores();
     if (n < (size_t(1) << 20) || n_workers_ == 0) {
-      std::memcpy(dst, src, n);
+      if (streamed) {
+        stream_copy(dst, src, n);
+        stream_fence();
+      } else {
+        std::memcpy(dst, src, n);
+      }
       return;
     }
     run([&](size_t part, size_t parts) {
       const size_t slice = ((n + parts - 1) / parts + 4095) & ~size_t(4095);
       const size_t lo = part * slice;
-      if (lo < n) std::memcpy(static_cast<char *>(dst) + lo, static_cast<const char *>(src) + lo, n - lo < slice ? n - lo : slice);
+      if (lo >= n) return;
+      const size_t len = n - lo < slice ? n - lo : slice;
+      if (streamed) {
+        stream_copy(static_cast<char *>(dst) + lo, static_cast<const char *>(src) + lo, len);
+        stream_fence();
+      } else {
+        std::memcpy(static_cast<char *>(dst) + lo, static_cast<const char *>(src) + lo, len);
+      }
     });
   }
 
@@ -801,7 +915,7 @@ wp_status encode_pipelined(wp_vocab *v, const char *text, size_t n_bytes, int32_
     const char *src = text + begin;
     if (stage_in) {
       if (i >= kPipeSlots) WP_CUDA(cudaEventSynchronize(sl.h2d_done));  // the slot's previous text has left
-      pool.copy(sl.h_text, src, len);
+      pool.copy(sl.h_text, src, len, /*streamed=*/true);
       src = reinterpret_cast<const char *>(sl.h_text);
     }
     WP_CUDA(cudaMemcpyAsync(sl.d_text, src, len, cudaMemcpyHostToDevice, v->s_h2d));
@@ -1235,7 +1349,8 @@ wp_status ensure_batch_slot(wp_vocab::BatchSlot &b, const PartPlan &p, size_t id
 }
 
 // texts -> the part's pinned input block (text starts, tile index, the texts with their separators)
-void pack_part(wp_vocab::BatchSlot &b, const PartPlan &p, const char *const *texts, const size_t *lens) {
+void pack_part(wp_vocab::BatchSlot &b, const PartPlan &p, const char *const *texts, const size_t *lens,
+               bool streamed = stream_stores()) {
   const size_t n = p.last - p.first;
   uint32_t *tile_bound = reinterpret_cast<uint32_t *>(b.h_in);
   unsigned long long *bounds = reinterpret_cast<unsigned long long *>(b.h_in + p.off_bounds);
@@ -1250,6 +1365,16 @@ void pack_part(wp_vocab::BatchSlot &b, const PartPlan &p, const char *const *tex
     const unsigned long long hi = static_cast<unsigned long long>(p.packed) * (part + 1) / parts;
     size_t i = static_cast<size_t>(std::lower_bound(bounds, bounds + n, lo) - bounds);
     const size_t end = part + 1 == parts ? n : static_cast<size_t>(std::lower_bound(bounds, bounds + n, hi) - bounds);
+    if (streamed) {  // (the texts of a share are contiguous in the packed buffer)
+      if (i >= end) return;
+      StreamWriter w(text + bounds[i]);
+      for (; i < end; i++) {
+        w.put(texts[p.first + i], lens[p.first + i]);
+        w.put(' ');
+      }
+      w.finish();
+      return;
+    }
     for (; i < end; i++) {
       char *dst = text + bounds[i];
       const size_t len = lens[p.first + i];
@@ -1740,6 +1865,28 @@ size_t wp_debug_plan_chunks(const char *text, size_t n, size_t chunk, size_t *cu
   if (!text || chunk < 64 || !plan_chunks(text, n, chunk, &c)) return 0;
   for (size_t i = 0; i < c.size() && i < cap; i++) cuts[i] = c[i];
   return c.size();
+}
+
+/* Host-only run of the staging code (no device): mode 0/1 = the batch packer with ordinary / streaming stores —
+ * out receives the packed texts (every text followed by one space), returns the packed size (0 if out is too
+ * small); mode 2/3 = CopyPool::copy of texts[0] (lens[0] bytes) to out, ordinary / streamed. */
+size_t wp_debug_stage(const char *const *texts, const size_t *lens, size_t n, char *out, size_t out_cap, int mode) {
+  if (!out || (n > 0 && (!texts || !lens))) return 0;
+  if (mode >= 2) {
+    if (n < 1 || lens[0] > out_cap) return 0;
+    CopyPool::get().copy(out, texts[0], lens[0], mode == 3);
+    return lens[0];
+  }
+  const PartPlan p = plan_part(lens, 0, n);
+  if (p.packed > out_cap) return 0;
+  wp_vocab::BatchSlot b;
+  void *block = nullptr;
+  if (posix_memalign(&block, 256, p.in_bytes + 64) != 0) return 0;
+  b.h_in = static_cast<uint8_t *>(block);
+  pack_part(b, p, texts, lens, mode == 1);
+  std::memcpy(out, b.h_in + p.off_text, p.packed);
+  std::free(block);
+  return p.packed;
 }
 
 /* Fills out[0..cap) with the code points of single-char word-initial tokens whose word-table slot is at least
