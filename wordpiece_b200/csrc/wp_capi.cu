@@ -901,7 +901,9 @@ wp_status encode_pipelined(wp_vocab *v, const char *text, size_t n_bytes, int32_
     if (!stage_out || counts[j] == 0 || overflow || offsets[j] + counts[j] > capacity) return WP_OK;
     wp_vocab::PipeSlot &sl = v->slot[j % kPipeSlots];
     WP_CUDA(cudaEventSynchronize(sl.d2h_done));
-    pool.copy(ids + offsets[j], sl.h_ids, counts[j] * sizeof(int32_t));
+    // (streamed: the caller's fresh pages are written without being read into the caches first)
+    static const bool stream_out = std::getenv("WORDPIECE_B200_STREAM_OUT") != nullptr && std::atoi(std::getenv("WORDPIECE_B200_STREAM_OUT")) != 0;
+    pool.copy(ids + offsets[j], sl.h_ids, counts[j] * sizeof(int32_t), stream_out);
     return WP_OK;
   };
 
