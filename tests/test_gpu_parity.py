@@ -661,3 +661,45 @@ def test_repeated_calls_on_one_handle_with_long_runs(gpu_device):
             got = v.encode(t)
             assert np.array_equal(exp, got), (a, b, rep, len(exp), len(got))
     v.close()
+
+
+def test_two_handles_in_two_host_threads(gpu_device):
+    """Handles are independent: two host threads, each with its own handle (own stream, scratch and word memo) on
+    the same device, encoding at the same time (ctypes releases the GIL during the calls) — device-resident
+    calls, host-buffer calls large enough for the chunk pipeline (shared copy pool), and batches."""
+    import threading
+
+    from wordpiece_b200 import Vocab
+
+    os.environ["WORDPIECE_B200_PIPE_CHUNK"] = "150000"
+    try:
+        jobs = []
+        for seed in (4101, 4102):
+            text, vocab = textgen.case(seed, 900_000, invalid_rate=0.001, long_run_rate=0.01, long_tokens=5)
+            o = Oracle(vocab)
+            cuts = sorted(random.Random(seed).sample(range(len(text)), 40))
+            pieces = [text[a:b] for a, b in zip([0] + cuts, cuts + [len(text)])]
+            jobs.append((text, vocab, o.encode(text), pieces, [o.encode(p) for p in pieces]))
+        errors = []
+
+        def work(i):
+            try:
+                text, vocab, exp, pieces, exp_pieces = jobs[i]
+                v = Vocab(vocab, device=gpu_device)
+                for rep in range(6):
+                    assert np.array_equal(v.encode(text), exp), (i, rep, "encode")
+                    ids, offs = v.encode_batch(pieces)
+                    for k, e in enumerate(exp_pieces):
+                        assert np.array_equal(ids[int(offs[k]):int(offs[k + 1])], e), (i, rep, "batch", k)
+                v.close()
+            except BaseException as e:  # noqa: BLE001
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors[0]
+    finally:
+        os.environ.pop("WORDPIECE_B200_PIPE_CHUNK", None)
