@@ -1727,7 +1727,8 @@ struct ScatterSmem {
 
 // ids of one segment that K1 did not settle with a single id -> dst[0..cnt): inline in the slow entry, from
 // the arena, or from the word-table slot
-__device__ __forceinline__ void scatter_fetch(const EncodeParams &P, uint32_t res, uint32_t cnt, int32_t *dst) {
+template <class Params>
+__device__ __forceinline__ void scatter_fetch(const Params &P, uint32_t res, uint32_t cnt, int32_t *dst) {
   if (res & SEG_RESULT_SLOW) {
     const uint32_t si = res & SEG_SLOW_INDEX_MASK;
     if (si >= P.slow_capacity) return;
@@ -1800,6 +1801,120 @@ __device__ __forceinline__ void scatter_direct(const EncodeParams &P, unsigned l
     }
     o += cnt;
   }
+}
+
+// A block whose ids do not fit the staging buffer because of a few LONG segments (URLs, blobs: hundreds of ids
+// each) among ordinary ones — the usual shape of such a block.  The ids of the ordinary segments are staged
+// densely (they fit), the long ones are left out of the buffer: staged id i goes to out0 + i + shift, where
+// shift = the ids of all long segments before it.  Every long segment k records key_k = the staged ids before
+// it and shift_k = the shift that holds behind it; the keys ascend, so a binary search finds the shift of a
+// staged id.  Then the staged ids go out in order (coalesced but for the jumps) and every long segment is
+// copied from the arena by one warp.  Returns false (uniform, nothing written) when the ordinary ids alone do
+// not fit or there are too many long segments: the caller falls back to scatter_direct.  Out of line: rare.
+constexpr uint32_t MIXED_MAX_BIG = SCATTER_SEGS / 2;  // keys in desc_pos[0..), shifts in desc_pos[MAX_BIG..), slow indices in desc_src
+
+// what scatter_mixed needs of the kernel's parameters, by value (a reference to the parameter struct would make the
+// kernel keep a copy of all of it in local memory)
+struct ScatterView {
+  const uint32_t *seg_result;
+  const SlowEntry *slow;
+  const uint32_t *arena;
+  const WordSlot *words;
+  volatile unsigned long long *block_state;
+  CallCounters *call;
+  int32_t *ids;
+  unsigned long long capacity;
+  uint32_t slow_capacity, arena_capacity, range_parity;
+};
+
+__device__ __noinline__ bool scatter_mixed(const ScatterView P, ScatterSmem &sm, unsigned long long first,
+                                           unsigned long long n_segs, uint32_t b, uint32_t n_blocks,
+                                           unsigned long long ids_in, uint32_t total, uint32_t at) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto count_of = [&](uint32_t res) -> uint32_t {
+    if (res < SEG_RESULT_WORD) return 1u;
+    uint32_t c = (res >> SEG_SLOW_INDEX_BITS) & ((res & SEG_RESULT_SLOW) ? SEG_SLOW_COUNT_MAX : 0xFu);
+    if (c == SEG_SLOW_COUNT_MAX && (res & SEG_RESULT_SLOW)) {
+      const uint32_t si = res & SEG_SLOW_INDEX_MASK;
+      c = si < P.slow_capacity ? (P.slow[si].off & ~SLOW_RESULT_INLINE) : 0u;
+    }
+    return c;
+  };
+  auto is_big = [&](uint32_t res, uint32_t c) {
+    return (res & SEG_RESULT_SLOW) && res >= SEG_RESULT_WORD && c > SCATTER_BIG && (res & SEG_SLOW_INDEX_MASK) < P.slow_capacity;
+  };
+  // pass 1: my ordinary ids and my long segments
+  uint32_t my_small = 0, my_big = 0;
+#pragma unroll 1
+  for (int j = 0; j < SCATTER_ITEMS; j++) {
+    if (first + j >= n_segs) break;
+    const uint32_t res = P.seg_result[first + j];
+    const uint32_t c = count_of(res);
+    if (is_big(res, c)) my_big++;
+    else my_small += c;
+  }
+  uint32_t totals;
+  const uint32_t ex = block_exclusive_scan<SCATTER_THREADS / 32>(sm.warp_sums, my_small | (my_big << 16), &totals);
+  const uint32_t n_small = totals & 0xFFFFu, n_big = totals >> 16;  // (at most 2048 x 15 ordinary ids: 16 bits hold them)
+  if (n_small > SCATTER_STAGE || n_big > MIXED_MAX_BIG || n_big == 0) return false;  // uniform
+  if (warp == 0) {
+    const unsigned long long base = lookback_walk(P.block_state, b, total, lane);
+    if (lane == 0) {
+      sm.base = base;
+      if (b == n_blocks - 1) P.call->ids_total[P.range_parity ^ 1u] = ids_in + base + total;
+    }
+  }
+  // pass 2: stage the ordinary ids, list the long segments
+  uint32_t spos = ex & 0xFFFFu, bk = ex >> 16, pos = at;
+#pragma unroll 1
+  for (int j = 0; j < SCATTER_ITEMS; j++) {
+    if (first + j >= n_segs) break;
+    const uint32_t res = P.seg_result[first + j];
+    const uint32_t c = count_of(res);
+    if (c == 0) continue;
+    if (res < SEG_RESULT_WORD) {
+      sm.stage[spos++] = static_cast<int32_t>(res) - 1;
+    } else if (is_big(res, c)) {
+      WP_CHECK(bk < MIXED_MAX_BIG);
+      sm.desc_pos[bk] = spos;                          // key: staged ids before this segment
+      sm.desc_pos[MIXED_MAX_BIG + bk] = pos + c - spos;  // shift of the staged ids behind it
+      sm.desc_src[bk] = res & SEG_SLOW_INDEX_MASK;
+      bk++;
+    } else {
+      WP_CHECK(spos + c <= SCATTER_STAGE);
+      scatter_fetch(P, res, c, sm.stage + spos);
+      spos += c;
+    }
+    pos += c;
+  }
+  __syncthreads();
+  const unsigned long long out0 = ids_in + sm.base;
+  // the staged ids
+  for (uint32_t i = tid; i < n_small; i += SCATTER_THREADS) {
+    uint32_t lo = 0, hi = n_big;  // number of keys <= i
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (sm.desc_pos[mid] <= i) lo = mid + 1;
+      else hi = mid;
+    }
+    const uint32_t shift = lo ? sm.desc_pos[MIXED_MAX_BIG + lo - 1] : 0u;
+    const unsigned long long o = out0 + i + shift;
+    WP_CHECK(i + shift < total);
+    if (o < P.capacity) P.ids[o] = sm.stage[i];
+  }
+  // the long segments, one warp each
+  for (uint32_t k = warp; k < n_big; k += SCATTER_THREADS / 32) {
+    const uint32_t si = sm.desc_src[k];
+    const uint4 e = *reinterpret_cast<const uint4 *>(&P.slow[si]);
+    const uint32_t cnt = e.x & ~SLOW_RESULT_INLINE;
+    if ((e.x & SLOW_RESULT_INLINE) || static_cast<unsigned long long>(e.y) + cnt > P.arena_capacity) continue;
+    const unsigned long long o = out0 + (sm.desc_pos[MIXED_MAX_BIG + k] - cnt + sm.desc_pos[k]);
+    WP_CHECK(sm.desc_pos[MIXED_MAX_BIG + k] + sm.desc_pos[k] <= total && sm.desc_pos[MIXED_MAX_BIG + k] + sm.desc_pos[k] >= cnt);
+    for (uint32_t t = lane; t < cnt; t += 32) {
+      if (o + t < P.capacity) P.ids[o + t] = static_cast<int32_t>(P.arena[e.y + t]);
+    }
+  }
+  return true;
 }
 
 __global__ void __launch_bounds__(SCATTER_THREADS, WP_K3_BLOCKS) wp_scatter_kernel(EncodeParams P) {
@@ -1945,7 +2060,17 @@ __global__ void __launch_bounds__(SCATTER_THREADS, WP_K3_BLOCKS) wp_scatter_kern
         }
       }
     } else {
-      // a block with unusually many ids (long words cut into many pieces): write directly
+      // a block with unusually many ids (long words cut into many pieces).  Usually a few long segments among
+      // ordinary ones: those are kept out of the staging buffer (scatter_mixed)
+#ifndef WP_K3_NO_MIXED
+      const ScatterView view{P.seg_result, P.slow, P.arena, P.words, P.block_state, P.call, P.ids,
+                             static_cast<unsigned long long>(P.capacity), P.slow_capacity, P.arena_capacity, P.range_parity};
+      if (scatter_mixed(view, sm, first, n_segs, b, n_blocks, ids_in, total, at)) {  // uniform
+        if (tid == 0) sm.block_index[(it + 1u) & 1u] = atomicAdd(&P.counters->scatter_ticket, 1u);
+        continue;
+      }
+#endif
+      // otherwise: write directly
       if (warp == 0) {
         const unsigned long long base = lookback_walk(P.block_state, b, total, lane);
         if (lane == 0) {
