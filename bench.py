@@ -414,9 +414,19 @@ def dropin_and_process(text: np.ndarray, vocab_tokens, n_ids: int):
         if os.path.exists(exe):
             text.tofile(tf)
             try:
-                r = subprocess.run([exe, tf, vf, "3"], capture_output=True, text=True, timeout=600)
+                r = subprocess.run([exe, tf, vf, "3", "10000", "4096"], capture_output=True, text=True, timeout=600)
                 info = json.loads(r.stdout.strip().splitlines()[-1])
                 ok = info.get("n_ids") == n_ids
+                b = info.get("batch")
+                if b:
+                    res["batch_cpp_10000x4KiB"] = {
+                        "texts": b["texts"], "text_bytes": b["bytes"], "ids": b["n_ids"],
+                        "gb_per_s_fresh_vector": b["bytes"] / b["fresh_vector_best_seconds"] / 1e9,
+                        "gb_per_s_reused_vector": b["bytes"] / b["reused_vector_best_seconds"] / 1e9,
+                        "seconds_best_of_5": [b["fresh_vector_best_seconds"], b["reused_vector_best_seconds"]],
+                        "call": "word_piece::fast::Encoder::encodeBatch(const std::vector<std::string>&, std::vector<int>&, "
+                                "std::vector<size_t>&) (include/word_piece.hpp): pageable strings in, a std::vector<int> "
+                                "out (a fresh one / one that keeps its storage between calls)"}
                 res["e2e_dropin"] = {"value": text.size / info["best_seconds"] / 1e9, "unit": UNIT,
                                      "call": "word_piece::fast::encode(const std::string&, const std::vector<std::string>&) "
                                              "-> std::vector<int> (include/word_piece.hpp), pageable memory both ways",

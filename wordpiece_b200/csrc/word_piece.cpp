@@ -14,6 +14,7 @@
 #include <unistd.h>
 
 #include <chrono>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -173,6 +174,35 @@ constexpr bool kUninitializedVectors = true;
 constexpr bool kUninitializedVectors = false;
 #endif
 
+// The storage of a large fresh vector comes straight from mmap and is touched for the first time by whoever copies
+// the ids into it: with 4 KiB pages that is 280 000 page faults for the ids of a 1 GiB text.  Asking for transparent
+// huge pages (MADV_HUGEPAGE) makes them a few hundred.  Measured on B200 boxes (16 cores, THP and defrag in "madvise"
+// mode; profiles/r2z_hugepage_ab.jsonl):
+//  * Encoder::encodeBatch, where ONE thread (the driver's pageable device-to-host copy) touches the storage:
+//    10 000 x 4 KiB texts into a fresh vector 22.5 ms without the advice, 10.8 ms with it -> on by default there;
+//  * fast::encode on 1 GiB, where the sixteen threads of the copy pool touch it: SLOWER with the advice, 15.2 ->
+//    14.0 GB/s in three interleaved pairs (the threads wait while single faults zero 2 MiB each) -> off by default.
+// WORDPIECE_B200_HUGEPAGES=0 / =1 forces it off / on everywhere.  Only blocks the allocator certainly took from mmap
+// (>= 64 MiB) are advised; where THP is off the advice changes nothing.
+void advise_huge_pages(void *p, size_t bytes, bool by_default) {
+#if defined(MADV_HUGEPAGE)
+  constexpr uintptr_t kHuge = uintptr_t(2) << 20;
+  if (p == nullptr || bytes < (size_t(64) << 20)) return;
+  static const int forced = [] {
+    const char *e = std::getenv("WORDPIECE_B200_HUGEPAGES");
+    return e == nullptr ? -1 : (std::atoi(e) != 0 ? 1 : 0);
+  }();
+  if (forced == 0 || (forced < 0 && !by_default)) return;
+  const uintptr_t lo = (reinterpret_cast<uintptr_t>(p) + kHuge - 1) & ~(kHuge - 1);
+  const uintptr_t hi = (reinterpret_cast<uintptr_t>(p) + bytes) & ~(kHuge - 1);
+  if (hi > lo) (void)::madvise(reinterpret_cast<void *>(lo), hi - lo, MADV_HUGEPAGE);
+#else
+  (void)p;
+  (void)bytes;
+  (void)by_default;
+#endif
+}
+
 // fast.cpp:143-150
 std::vector<int> encode_buffer(wp_vocab *v, const char *text, size_t size) {
   if (size == 0) return {};
@@ -186,6 +216,7 @@ std::vector<int> encode_buffer(wp_vocab *v, const char *text, size_t size) {
     wp_status st;
     if (kUninitializedVectors) {
       out.reserve(cap);
+      advise_huge_pages(out.data(), out.capacity() * sizeof(int), /*by_default=*/false);
       st = wp_encode_into(v, text, size, reinterpret_cast<int32_t *>(out.data()), cap, &n);
 #if defined(__GLIBCXX__)
       if (st == WP_OK) static_cast<VectorTail &>(out).set_size(n);
@@ -355,16 +386,30 @@ void Encoder::encodeBatch(const std::vector<std::string> &texts, std::vector<int
   // first guess: half an id per byte (English-like text needs a quarter); the call reports the exact count if short
   size_t cap = bytes / 2 + 64;
   for (int attempt = 0;; attempt++) {
-    ids.resize(cap);
     size_t n = 0;
-    const wp_status st = wp_encode_batch(v, ptrs.data(), lens.data(), texts.size(), reinterpret_cast<int32_t *>(ids.data()),
-                                         ids.size(), offsets.data(), &n);
+    wp_status st;
+    if (kUninitializedVectors) {
+      // no zero-fill of the guess (resize() would touch 2 bytes of ids per text byte with one thread, several
+      // times what the call itself takes); a vector the caller reuses keeps its storage and its touched pages
+      ids.clear();
+      ids.reserve(cap);
+      advise_huge_pages(ids.data(), ids.capacity() * sizeof(int), /*by_default=*/true);
+      st = wp_encode_batch(v, ptrs.data(), lens.data(), texts.size(), reinterpret_cast<int32_t *>(ids.data()),
+                           ids.capacity(), offsets.data(), &n);
+#if defined(__GLIBCXX__)
+      if (st == WP_OK) static_cast<VectorTail &>(ids).set_size(n);
+#endif
+    } else {
+      ids.resize(cap);
+      st = wp_encode_batch(v, ptrs.data(), lens.data(), texts.size(), reinterpret_cast<int32_t *>(ids.data()),
+                           ids.size(), offsets.data(), &n);
+      if (st == WP_OK) ids.resize(n);
+    }
     if (st == WP_ERR_CAPACITY && attempt == 0) {
       cap = n;
       continue;
     }
     if (st != WP_OK) raise(st);
-    ids.resize(n);
     break;
   }
   wp_stats stats{};
