@@ -69,6 +69,44 @@ def test_reference_drivers_compile_against_the_drop_in_headers(tmp_path):
         assert r.returncode == 0, f"{driver}:\n{r.stderr[-2000:]}"
 
 
+def test_runner_argv_contract_without_a_device(tmp_path):
+    """tests/runner.cpp:13-65 — everything the CLI decides before it encodes: argument count, the 50 MB floor of
+    memory_limit_mb, external mode without a limit, unknown and out-of-scope modes; errors are uncaught
+    std::runtime_error like the reference's (non-zero exit, message on stderr).  And with valid arguments but no
+    CUDA device (this container) `fast` must fail loudly — there is no CPU path behind the CLI either."""
+    import subprocess
+
+    import torch
+
+    runner = os.path.join(ROOT, "wordpiece_b200", "lib", "runner")
+    if not os.path.exists(runner):
+        pytest.skip("runner not built")
+    tf, vf = tmp_path / "t.txt", tmp_path / "v.txt"
+    tf.write_bytes(b"hello world")
+    vf.write_bytes(b"[UNK]\nhello\nworld\n")
+
+    def run(*argv):
+        r = subprocess.run([runner, *map(str, argv)], capture_output=True, text=True)
+        return r.returncode, r.stdout, r.stderr
+
+    for argv, message in [
+        (("fast", tf), "Usage: ./runner <mode> <text_file> <vocab_file>"),
+        (("fast", tf, vf, 8, "o", 50, "extra"), "Usage: ./runner"),
+        (("fast-external", tf, vf, 8, tmp_path / "o.txt", 49), "memory_limit cannot be less than 50Mb"),
+        (("fast-external", tf, vf, 8, tmp_path / "o.txt"), "For external mode provide out_file and memory_limit"),
+        (("fast-external", tf, vf), "For external mode provide out_file and memory_limit"),
+        (("linear", tf, vf), "not part of wordpiece_b200"),
+        (("linear-external", tf, vf, 8, tmp_path / "o.txt", 50), "not part of wordpiece_b200"),
+        (("slow", tf, vf), "Unknown mode"),
+    ]:
+        rc, out, err = run(*argv)
+        assert rc != 0 and message in err and out == "", (argv, rc, out, err)
+    assert not (tmp_path / "o.txt").exists()
+    if not torch.cuda.is_available():
+        rc, out, err = run("fast", tf, vf, 8)
+        assert rc != 0 and "Total ids" not in out and err.strip(), (rc, out, err)
+
+
 def test_no_device_fails_loudly():
     """Without a CUDA device (this container) creation on device 0 must fail — never fall back to a CPU path."""
     import torch
